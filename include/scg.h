@@ -1,0 +1,204 @@
+/*
+ * scg.h -- C-ABI of libscg_cuda.so: the B200 (sm_100a) device twin of
+ * solvcon's space-time CESE march.
+ *
+ * The reference has no FFI of its own for this path: its boundary is the
+ * pybind11 class surface of the `_solvcon` extension.
+ * Each entry point below is what the C++ method named beside it forwards to
+ * when a maintainer puts the device library under the unchanged classes
+ * (INTEGRATION.md shows the binding).  Conventions:
+ *
+ *   - every function returns 0 on success, non-zero on failure; the message is
+ *     available from scg_last_error() (thread-local).  No exception and no
+ *     C++/torch type crosses this boundary.
+ *   - handles are opaque; plain pointers + sizes only.
+ *   - host arrays use the reference's own SimpleArray layout (row-major,
+ *     time planes interleaved in 1D, ghost rows FIRST in the multidim tables)
+ *     so a SimpleArray's data() pointer can be passed as is.  The device keeps
+ *     its own SoA / reordered layout; upload/download convert.
+ *   - all reals are fp64, all indices int32 (reference: cpp/solvcon/base.hpp:71-81).
+ *   - there is no CPU fallback: without a CUDA device every call fails.
+ */
+#ifndef SCG_H
+#define SCG_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCG_API __attribute__((visibility("default")))
+
+/* ------------------------------------------------------------------ runtime */
+
+SCG_API const char * scg_last_error(void);
+/* 1 if the library was built without FMA contraction (bit-parity build), 0 for the speed variant */
+SCG_API int scg_build_is_strict(void);
+SCG_API int scg_device_count(int * count);
+/* bind this process/thread to one device and create the library's work stream */
+SCG_API int scg_init(int device);
+SCG_API int scg_shutdown(void);
+SCG_API int scg_sync(void);
+/* device memory info in bytes */
+SCG_API int scg_mem_info(int64_t * free_bytes, int64_t * total_bytes);
+/* kernels launched by this library since the last reset (for bench.py "gpu_launches") */
+SCG_API int64_t scg_launch_count(int reset);
+/* CUDA-event timer on the library's work stream: start, stop -> elapsed ms */
+SCG_API int scg_timer_start(void);
+SCG_API int scg_timer_stop(double * elapsed_ms);
+/* write `bytes` of device scratch (>= L2 size) to evict L2 between timed iterations */
+SCG_API int scg_flush_l2(int64_t bytes);
+/* pinned host memory for the end-to-end path */
+SCG_API int scg_host_alloc(void ** ptr, int64_t bytes);
+SCG_API int scg_host_free(void * ptr);
+
+/* --------------------------------------------------------------- 1D scalar
+ * replaces spacetime::SolverBase<...> for LinearScalar / InviscidBurgers
+ * (cpp/solvcon/spacetime/core.hpp:946-1036, kernel/linear_scalar.hpp:45-87,
+ * kernel/inviscid_burgers.hpp:51-109).
+ */
+typedef struct scg_st scg_st;
+
+#define SCG_EQ_LINEAR 0
+#define SCG_EQ_BURGERS 1
+
+#define SCG_PH_SO0 0 /* march_half_so0(odd)        core.hpp:946-956  */
+#define SCG_PH_CFL 1 /* update_cfl(odd)            core.hpp:958-967  */
+#define SCG_PH_SO1 2 /* march_half_so1_alpha<A>    core.hpp:969-980  */
+#define SCG_PH_BC0 3 /* treat_boundary_so0()       core.hpp:982-992  */
+#define SCG_PH_BC1 4 /* treat_boundary_so1()       core.hpp:994-1004 */
+
+/* ncelm conservation elements -> nx = 2*ncelm+5 coordinate slots (core.cpp:74) */
+SCG_API int scg_st_create(scg_st ** out, int eq, int64_t ncelm, double time_increment);
+SCG_API int scg_st_destroy(scg_st * s);
+SCG_API int scg_st_set_time_increment(scg_st * s, double time_increment); /* Field::set_time_increment core.cpp:111-116 */
+/* fill the grid on the device exactly as Grid::Grid(xmin,xmax,ncelm) does (core.cpp:14-99) */
+SCG_API int scg_st_grid_uniform(scg_st * s, double xmin, double xmax);
+/* host -> device; any pointer may be NULL (skipped).  Arrays have nx entries. */
+SCG_API int scg_st_upload(scg_st * s, const double * x, const double * so0, const double * so1, const double * cfl);
+/* device -> host; any pointer may be NULL */
+SCG_API int scg_st_download(scg_st * s, double * x, double * so0, double * so1, double * cfl);
+SCG_API int scg_st_phase(scg_st * s, int phase, int odd_plane, int alpha);
+/* march_alpha<A>(steps), core.hpp:1027-1036; alpha in {0,1,2} */
+SCG_API int scg_st_march(scg_st * s, int alpha, int64_t steps);
+/* min / max of cfl over the plane points the reference fills, and sum(so0) over the even plane */
+SCG_API int scg_st_reduce(scg_st * s, double * cfl_min, double * cfl_max, double * so0_sum);
+/* slab decomposition: this object owns CEs [ce_begin, ce_end) of a global ncelm_global grid;
+ * halo points are exchanged by the caller through scg_st_halo_pack/unpack */
+SCG_API int scg_st_halo_pack(scg_st * s, int odd_plane, double * dev_send_left, double * dev_send_right);
+SCG_API int scg_st_halo_unpack(scg_st * s, int odd_plane, const double * dev_recv_left, const double * dev_recv_right);
+
+/* ---------------------------------------------------------------- 1D Euler
+ * replaces onedim::Euler1DCore (cpp/solvcon/onedim/Euler1DCore.hpp:41-145,
+ * Euler1DCore.cpp:70-172).
+ */
+typedef struct scg_e1d scg_e1d;
+
+SCG_API int scg_e1d_create(scg_e1d ** out, int64_t ncoord, double time_increment);
+SCG_API int scg_e1d_destroy(scg_e1d * s);
+/* arrays: coord[ncoord], gamma[ncoord], so0[ncoord][3], so1[ncoord][3], cfl[ncoord]; NULL = skip */
+SCG_API int scg_e1d_upload(scg_e1d * s, const double * coord, const double * gamma, const double * so0,
+                           const double * so1, const double * cfl);
+SCG_API int scg_e1d_download(scg_e1d * s, double * so0, double * so1, double * cfl);
+/* phases as SCG_PH_*: Euler1DCore::{march_half_so0,update_cfl,march_half_so1_alpha<A>,
+ * treat_boundary_so0,treat_boundary_so1}; alpha in {1,2} (wrap_onedim.cpp:113-115) */
+SCG_API int scg_e1d_phase(scg_e1d * s, int phase, int odd_plane, int alpha);
+/* march_alpha<A>(steps), Euler1DCore.hpp:339-349 */
+SCG_API int scg_e1d_march(scg_e1d * s, int alpha, int64_t steps);
+SCG_API int scg_e1d_reduce(scg_e1d * s, double * cfl_min, double * cfl_max, double * mass);
+
+/* ---------------------------------------------------------- multidim Euler
+ * replaces EulerCore over StaticMesh (cpp/solvcon/multidim/euler.hpp:56-211,
+ * euler_{ce,march,solution,gradient,bc}.cpp, GradientElement.cpp).
+ */
+typedef struct scg_mesh scg_mesh;
+typedef struct scg_md scg_md;
+
+#define SCG_ORDER_NONE 0   /* reference cell order, grouped by cell type (stable) */
+#define SCG_ORDER_MORTON 1 /* Morton (Z-curve) key of the cell centroid within each type group */
+#define SCG_ORDER_RCM 2    /* reverse Cuthill-McKee rank within each type group */
+
+/*
+ * Upload the StaticMesh tables the march reads (StaticMesh.hpp:425-447).  Every
+ * pointer addresses the first STORED row (ghost rows first, as SimpleArray::data()):
+ *   cltpn[ngstcell+ncell], clfcs[ngstcell+ncell][7], clcnd[ngstcell+ncell][ndim],
+ *   fccls[ngstface+nface][4], fcnds[ngstface+nface][5], fccnd/fcnml[ngstface+nface][ndim],
+ *   ndcrd[ngstnode+nnode][ndim].
+ * `order` selects the device cell ordering (results are returned in reference order).
+ */
+SCG_API int scg_mesh_create(scg_mesh ** out, int ndim,
+                            int64_t nnode, int64_t nface, int64_t ncell,
+                            int64_t ngstnode, int64_t ngstface, int64_t ngstcell,
+                            const int32_t * cltpn, const int32_t * clfcs, const int32_t * fccls,
+                            const int32_t * fcnds, const double * ndcrd, const double * fccnd,
+                            const double * fcnml, const double * clcnd, int order);
+SCG_API int scg_mesh_destroy(scg_mesh * m);
+/* device order <-> reference order permutation: perm[k] = reference cell id stored at device slot k */
+SCG_API int scg_mesh_perm(scg_mesh * m, int32_t * perm /* ncell */);
+
+#define SCG_MD_UPDATE 0     /* EulerCore::update()        euler.hpp:123-127         */
+#define SCG_MD_SOLT 1       /* calc_solt()                euler_march.cpp:161-191   */
+#define SCG_MD_SOLN 2       /* calc_soln()                euler_march.cpp:197-303   */
+#define SCG_MD_BC_SOLN 3    /* bc_soln()                  euler_bc.cpp:143-215      */
+#define SCG_MD_CFL 4        /* calc_cfl()                 euler_solution.cpp:106-160*/
+#define SCG_MD_DSOLN 5      /* calc_dsoln()               euler_gradient.cpp:23-130 */
+#define SCG_MD_BC_DSOLN 6   /* bc_dsoln()                 euler_bc.cpp:219-320      */
+#define SCG_MD_PREPARE_CE 7 /* prepare_ce()               euler_ce.cpp:62-347       */
+#define SCG_MD_SUBSTEP 8    /* march_substep()            euler_march.cpp:339-348   */
+
+#define SCG_BC_NONREFL 0  /* EulerBC::NonReflective euler.hpp:27-32 */
+#define SCG_BC_SLIPWALL 1
+#define SCG_BC_INLET 2
+
+/* array ids for upload/download (EulerCore accessors, euler.hpp:105-118) */
+#define SCG_A_CEVOL 0
+#define SCG_A_CECND 1
+#define SCG_A_SFCND 2
+#define SCG_A_SFNML 3
+#define SCG_A_SO0C 4
+#define SCG_A_SO0N 5
+#define SCG_A_SO0T 6
+#define SCG_A_SO1C 7
+#define SCG_A_SO1N 8
+#define SCG_A_CFLO 9
+#define SCG_A_CFLC 10
+#define SCG_A_GAMMA 11
+#define SCG_A_COUNT 12
+
+/* EulerCore(mesh, time_increment): allocates the device store and runs prepare_ce on the device */
+SCG_API int scg_md_create(scg_md ** out, scg_mesh * mesh, double time_increment);
+SCG_API int scg_md_destroy(scg_md * s);
+SCG_API int scg_md_set_params(scg_md * s, double sigma0, double taumin, double tauscale); /* euler.hpp:99-104 */
+/* init_solution(gamma, rho, v, p), euler_solution.cpp:54-99 (v has 3 entries) */
+SCG_API int scg_md_init_solution(scg_md * s, double gamma, double rho, const double * v, double p);
+/* add_bc(kind, faces, value), euler_bc.cpp:324-389; same validation, same order semantics */
+SCG_API int scg_md_add_bc(scg_md * s, int kind, const int32_t * faces, int64_t nface, const double * value, int nvalue);
+SCG_API int scg_md_clear_bc(scg_md * s);
+/* host array (reference layout, ghost rows first) <-> device store */
+SCG_API int scg_md_upload(scg_md * s, int array_id, const double * host);
+SCG_API int scg_md_download(scg_md * s, int array_id, double * host);
+SCG_API int scg_md_phase(scg_md * s, int phase);
+/* march(steps) = steps x 2 fused substeps, euler_march.cpp:350-359 */
+SCG_API int scg_md_march(scg_md * s, int64_t steps);
+/* caller-side reductions of solvcon/multidim/euler/_field.py:138-148 done on the device:
+ * min/max of cflo over body cells and sum(density * clvol) */
+SCG_API int scg_md_reduce(scg_md * s, const double * clvol_host_or_null, double * cfl_min, double * cfl_max, double * mass);
+/* algorithmic bytes one substep moves for this mesh, for the roofline */
+SCG_API int scg_md_algorithmic_bytes(scg_md * s, int64_t * bytes_per_substep);
+/* get_normal_matrix(ifc), euler_bc.cpp:391-425 (host-side helper, row-major ndim x ndim) */
+SCG_API int scg_md_normal_matrix(scg_md * s, int32_t ifc, double * out);
+
+/* halo exchange support for domain decomposition (one process per GPU; the caller moves the
+ * packed buffers with NCCL send/recv or peer copies, see solvcon_b200/decomp.py):
+ * pack the new state (so0n+so1n, neq*(1+ndim) doubles per cell) of the listed device-order
+ * cells into a contiguous device buffer, and scatter a received buffer into ghost rows. */
+SCG_API int scg_md_halo_set(scg_md * s, const int32_t * send_cells, int64_t nsend, const int32_t * recv_ghosts, int64_t nrecv);
+SCG_API int scg_md_halo_pack(scg_md * s, double ** dev_buffer, int64_t * ndouble);
+SCG_API int scg_md_halo_unpack(scg_md * s, const double * dev_buffer);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* SCG_H */

@@ -1,0 +1,50 @@
+"""Shared deterministic test cases (initial conditions) for the parity tests."""
+import numpy as np
+
+
+def sod_ic(core, xmin=-1.0, xmax=1.0, gamma=1.4, p1=1.0, rho1=1.0, p5=0.1, rho5=0.125):
+    """Sod shock tube IC, restating solvcon/onedim/euler1d.py:47-53,146-166 (ShockTube.build_numerical):
+    coord = linspace, zero field, then left/right constant states with u2 = rho*(ie+ke)."""
+    n = core.ncoord
+    core.coord[...] = np.linspace(xmin, xmax, num=n)
+    core.cfl.fill(0)
+    core.gamma.fill(gamma)
+    core.so0[...] = 0.0
+    core.so1[...] = 0.0
+    x = core.coord
+    left = x < 0  # euler1d.py splits at the origin
+    for mask, rho, p in ((left, rho1, p1), (~left, rho5, p5)):
+        ie = 1.0 / (gamma - 1) * p / rho
+        core.so0[mask, 0] = rho
+        core.so0[mask, 1] = 0.0
+        core.so0[mask, 2] = rho * (ie + 0.0)
+
+
+def smooth_e1d_ic(core, xmin=0.0, xmax=4.0):
+    """A smooth non-trivial 1D Euler state with a non-uniform grid and varying gamma."""
+    n = core.ncoord
+    s = np.linspace(0.0, 1.0, n)
+    core.coord[...] = xmin + (xmax - xmin) * (s + 0.05 * np.sin(2 * np.pi * s) / (2 * np.pi))
+    x = core.coord
+    rho = 1.0 + 0.2 * np.sin(2 * np.pi * x / (xmax - xmin))
+    v = 0.3 * np.cos(2 * np.pi * x / (xmax - xmin))
+    p = 1.0 + 0.1 * np.sin(4 * np.pi * x / (xmax - xmin))
+    core.gamma[...] = 1.4 + 0.05 * np.cos(x)
+    ga = core.gamma
+    core.so0[:, 0] = rho
+    core.so0[:, 1] = rho * v
+    core.so0[:, 2] = p / (ga - 1.0) + 0.5 * rho * v * v
+    core.so1[...] = 0.0
+    core.so1[:, 0] = 0.2 * 2 * np.pi / (xmax - xmin) * np.cos(2 * np.pi * x / (xmax - xmin))
+    core.cfl.fill(0)
+
+
+def scalar_ic(x, so0, so1, cfl=None):
+    """so0 = 1/2 sin x, so1 = 1/2 cos x on the even plane.  The reference
+    leaves its arrays uninitialised, so every slot is written here (cfl too when given)."""
+    so0[...] = 0.0
+    so1[...] = 0.0
+    if cfl is not None:
+        cfl[...] = 0.0
+    so0[2::2] = 0.5 * np.sin(x[2::2])
+    so1[2::2] = 0.5 * np.cos(x[2::2])
