@@ -126,9 +126,10 @@ __global__ void __launch_bounds__(256) e1d_half_kernel(EPlane const ps, EPlane c
     // so[1] <- so[2] is odd slot 0 <- even slot 1, so[N-2] <- so[N-3] is odd slot slast <- even slot slast.
     if ((FLAGS & F_BC) && live && 0 == S)
     {
-        if (s == sbeg || s == slast)
+        for (int side = 0; side < 2; ++side)
         {
-            int64_t const o = (s == sbeg) ? 0 : slast;
+            if (s != (side ? slast : sbeg)) { continue; }
+            int64_t const o = side ? slast : 0;
             pt.u[0][o] = u0;
             pt.u[1][o] = u1;
             pt.u[2][o] = u2;

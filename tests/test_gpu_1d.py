@@ -127,21 +127,26 @@ def test_scalar_march_matches(gpu, bridge, eq, alpha):
 
 
 def test_scalar_known_answer_cfl1(gpu):
-    """Reference known answer (tests/test_spacetime_linear_scalar.py:106-113): 8 cells per period
-    at CFL = 1 reproduce sin(x) after whole periods to 1e-14 and cfl == 1."""
+    """Reference known answer (tests/test_spacetime_linear_scalar.py:15-38,106-113): 8 cells over one
+    period at CFL = 1 reproduce sin(x) after 10 periods to 1e-14, and cfl == 1."""
     from solvcon_b200 import spacetime as st
     resolution, cycle = 8, 10
-    grid = st.Grid(0, 4 * 2 * np.pi, 4 * resolution)
+    xcrd = np.arange(resolution + 1) / resolution
+    xcrd *= 2 * np.pi
+    grid = st.Grid(xcrd)
     dx = (grid.xmax - grid.xmin) / grid.ncelm
-    svr = st.LinearScalarSolver(grid, dx)
-    for e in svr.selms(odd_plane=False):
-        e.set_so0(0, np.sin(e.xctr))
-        e.set_so1(0, np.cos(e.xctr))
-    xcrd = svr.xctr(odd_plane=False).ndarray
+    time_stop = 2 * np.pi
+    nstep = int(np.ceil(time_stop / (dx * 1.0)))
+    dt = time_stop / nstep
+    svr = st.LinearScalarSolver(grid=grid, time_increment=dt)
+    svr.set_so0(0, np.sin(xcrd))
+    svr.set_so1(0, np.cos(xcrd))
     svr.setup_march()
-    svr.march_alpha2(resolution * cycle)
-    np.testing.assert_allclose(svr.get_so0(0).ndarray, np.sin(xcrd), rtol=0, atol=1e-14)
-    np.testing.assert_allclose(svr.get_cfl().ndarray, np.ones(grid.nselm), rtol=0, atol=1e-14)
+    assert svr.xctr().tolist() == xcrd.tolist()
+    assert svr.xctr().tolist() == [e.xctr for e in svr.selms(odd_plane=False)]
+    svr.march_alpha2(nstep * cycle)
+    np.testing.assert_allclose(svr.get_so0(0), np.sin(xcrd), rtol=0, atol=1e-14)
+    np.testing.assert_allclose(svr.get_cfl(), np.ones(grid.nselm), rtol=0, atol=1e-14)
 
 
 @pytest.mark.parametrize("eq", [0, 1])
