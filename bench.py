@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the CESE march on B200 (contract: see the task statement / DESIGN.md).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+
+One "step" = one ``march(chunk)`` call of the solver over the whole mesh/grid (``chunk`` time
+steps = ``2*chunk`` half-steps/substeps), the call a user of the reference makes
+(``svr.march_alpha2(steps)`` / ``EulerCore.march(steps)``).  Unit everywhere: one *update* = one
+solution point (1D) / one body cell (multidim) advanced by one half-step / substep.
+
+* ``value``       device-resident throughput (inputs already in HBM), CUDA events, max over ranks
+* ``e2e``         the same metric through the public solver class with HOST arrays: upload +
+                  march + download inside the timed region
+* ``roofline``    algorithmic bytes per launch / average launch time of the dominant kernel
+* ``cpu_baseline`` the reference's own CPU march (oracle/_ref, else the pinned C port) timed on
+                  this box's host cores on a bounded sample of the same workload
+
+``--impl reference`` runs only the CPU reference arm and prints its line.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "fp64 CESE cell-updates/s (Euler)"
+UNIT = "updates/s"
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------- clocks ---
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason sampler running during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        return False
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------- workloads ---
+
+class E1DWorkload:
+    """1D Euler CESE (onedim.Euler1DCore), Sod shock tube on ncoord points."""
+
+    name = "e1d_sod"
+    dtype = "f64"
+    balg = 128  # bytes per update, SURVEY.md 8(d)
+
+    def __init__(self, ncoord, chunk):
+        self.ncoord = int(ncoord) | 1
+        self.chunk = chunk
+        self.dt = 0.8 * 2.0 / (self.ncoord - 1)
+
+    def describe(self, world):
+        return {"workload": f"1D Euler CESE (onedim), Sod shock tube, ncoord={self.ncoord} per GPU, "
+                            f"march_alpha2({self.chunk}) per step",
+                "points_per_gpu": self.ncoord, "chunk_steps": self.chunk,
+                "l2_policy": "inputs larger than L2 (%.1f GB state per GPU)" % (self.ncoord * 128 / 1e9),
+                "decomposition": "none" if world == 1 else "independent slabs (NRBC ends are local)"}
+
+    def updates_per_step(self):
+        # each half step writes (N-3)/2 (+1 on the odd plane) targets
+        return (self.ncoord - 3) * self.chunk + self.chunk
+
+    def launches_per_step(self):
+        return 2 * self.chunk
+
+    def alg_bytes_per_launch(self):
+        return self.balg * self.updates_per_step() / self.launches_per_step()
+
+    def build_device(self):
+        from cases import sod_ic
+        from solvcon_b200.onedim import Euler1DCore
+        self.dev = Euler1DCore(self.ncoord, self.dt)
+        sod_ic(self.dev)
+        return self.dev
+
+    def resident_begin(self):
+        self.dev.resident(True)
+
+    def resident_step(self):
+        self.dev.march_alpha2(self.chunk)
+
+    def e2e_step(self):
+        # public API with host arrays: upload (coord, gamma, so0, so1, cfl) + march + download
+        self.dev.resident(False) if self.dev._resident else None
+        self.dev.march_alpha2(self.chunk)
+
+    def e2e_bytes(self):
+        n = self.ncoord
+        return n * 8 * (1 + 1 + 3 + 3 + 1), n * 8 * (3 + 3 + 1)
+
+    def result_check(self):
+        return float(self.dev.so0[:, 0].sum())
+
+    # CPU reference arm on a bounded sample
+    def cpu_run(self, budget_s=15.0):
+        from oracle import bridge
+        from cases import sod_ic
+        n = min(self.ncoord, 2_000_001)
+        kind = "reference" if bridge.have_ref() else "port"
+        cls = bridge.RefEuler1D if bridge.have_ref() else bridge.PortEuler1D
+        chk = cls(n, 0.8 * 2.0 / (n - 1))
+        sod_ic(chk)
+        chk.march(2, 1)
+        t0 = time.perf_counter()
+        steps = 0
+        while True:
+            chk.march(2, 2)
+            steps += 2
+            el = time.perf_counter() - t0
+            if el > budget_s or steps >= 64:
+                break
+        upd = (n - 3) * steps + steps
+        return {"value": upd / el, "unit": UNIT, "cores": 1, "kind": kind,
+                "sample": f"1D Euler Sod, ncoord={n}, march_alpha2({steps}) in {el:.2f} s, single thread "
+                          f"(the reference is single-threaded)"}, upd, el
+
+
+def make_workload(args):
+    if args.workload == "e1d":
+        return E1DWorkload(args.size or 100_000_001, args.chunk)
+    if args.workload in ("md3d", "md2d"):
+        from solvcon_b200 import bench_md  # noqa
+        return bench_md.make(args)
+    raise SystemExit(f"unknown workload {args.workload}")
+
+
+# --------------------------------------------------------------------------------- main ---
+
+def dist_setup(n_gpus):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        return rank, world, local, dist
+    return rank, world, local, None
+
+
+def barrier(dist, local):
+    if dist is not None:
+        import torch
+        dist.barrier(device_ids=[local])
+        torch.cuda.synchronize()
+
+
+def max_over_ranks(dist, v, local):
+    if dist is None:
+        return v
+    import torch
+    t = torch.tensor([v], dtype=torch.float64, device=f"cuda:{local}")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(dist, v, local):
+    if dist is None:
+        return v
+    import torch
+    t = torch.tensor([v], dtype=torch.float64, device=f"cuda:{local}")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = make_workload(args)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    vals, samples = [], None
+    for i in range(args.warmup + args.steps):
+        base, upd, el = wl.cpu_run(budget_s=args.ref_budget)
+        if i >= args.warmup:
+            vals.append((upd, el))
+            samples = base
+    upd = sum(v[0] for v in vals)
+    el = sum(v[1] for v in vals)
+    value = upd / el
+    samples["value"] = value
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": el / max(len(vals), 1) * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": wl.dtype,
+            "data": "synthetic", "config": wl.describe(world), "cpu_baseline": samples,
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--workload", default=os.environ.get("SCG_BENCH_WORKLOAD", "e1d"))
+    ap.add_argument("--size", type=int, default=0, help="points / cells per GPU (0 = workload default)")
+    ap.add_argument("--chunk", type=int, default=5, help="time steps per march() call (one bench step)")
+    ap.add_argument("--ref-budget", type=float, default=12.0)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    rank, world, local, dist = dist_setup(args.gpus)
+    from solvcon_b200 import _lib
+    _lib.init(local)
+    lib = _lib.load()
+    wl = make_workload(args)
+    wl.rank, wl.world, wl.dist, wl.local = rank, world, dist, local
+    wl.build_device()
+
+    # ---- device-resident arm
+    wl.resident_begin()
+    for _ in range(args.warmup):
+        wl.resident_step()
+    _lib.sync()
+    barrier(dist, local)
+    _lib.launch_count(reset=True)
+    with ClockSampler(local) as clk:
+        with _lib.Timer() as t:
+            for _ in range(args.steps):
+                wl.resident_step()
+        _lib.sync()
+    barrier(dist, local)
+    launches = _lib.launch_count()
+    ms = max_over_ranks(dist, t.ms, local)
+    upd_total = sum_over_ranks(dist, float(wl.updates_per_step()), local) * args.steps
+    value = upd_total / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (this rank's launches, timed above on the library stream)
+    peak, peak_src = measured_peak()
+    n_dom = wl.launches_per_step() * args.steps
+    ach = wl.alg_bytes_per_launch() / (t.ms * 1e-3 / n_dom) / 1e9
+    roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            "traffic": getattr(wl, "ncu_traffic", None), "peak_source": peak_src,
+            "kernel": getattr(wl, "dominant_kernel", "e1d_half_kernel"),
+            "alg_bytes_per_launch": wl.alg_bytes_per_launch(),
+            "avg_launch_ms": t.ms / n_dom}
+
+    # ---- end-to-end arm through the public class with host arrays
+    e2e = None
+    if not args.no_e2e:
+        wl.dev.resident(False)
+        wl.e2e_step()
+        n_e2e = max(1, min(args.steps, 3))
+        barrier(dist, local)
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            wl.e2e_step()
+        _lib.sync()
+        barrier(dist, local)
+        el = max_over_ranks(dist, time.perf_counter() - t0, local)
+        hi, lo = wl.e2e_bytes()
+        e2e = {"value": sum_over_ranks(dist, float(wl.updates_per_step()), local) * n_e2e / el, "unit": UNIT,
+               "h2d_bytes_per_step": hi, "d2h_bytes_per_step": lo, "steps": n_e2e,
+               "check": wl.result_check()}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu, _, _ = wl.cpu_run(budget_s=args.ref_budget)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic",
+                "config": wl.describe(world), "clocks": clk.summary(), "e2e": e2e,
+                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+                "strict_fp": bool(lib.scg_build_is_strict())}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
