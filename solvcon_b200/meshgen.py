@@ -1,0 +1,190 @@
+"""Deterministic synthetic meshes (nodes + cells) for the named benchmark configurations.
+
+RNG-free like the reference's own mesher (``solvcon/pilot/apps/obsrefl/_driver.py:149-153``):
+every choice is a closed-form hash of the lattice indices.  The output is the input the
+reference's ``StaticMesh`` takes (``ndcrd``, ``cltpn``, ``clnds`` -- ``tests/test_multidim.py:152-281``
+shows the filling pattern) plus named boundary-face selectors expressed on cell/face geometry.
+
+Cell-type ids and node orders follow ``cpp/solvcon/mesh/StaticMesh.hpp`` (``CellType``):
+3 quadrilateral, 4 triangle, 5 hexahedron, 6 tetrahedron, 7 prism, 8 pyramid; ``clnds`` rows are
+``[nnode, n1, n2, ...]`` padded with -1 to CLMND+1 = 9 columns.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+QUAD, TRI, HEX, TET, PRISM, PYRAMID = 3, 4, 5, 6, 7, 8
+CLMND = 8
+
+
+def _jitter2(i, j, amp):
+    return amp * np.sin(12.9898 * i + 78.233 * j), amp * np.cos(26.651 * i + 41.347 * j)
+
+
+def mixed_2d(nx, ny, lx=3.0, ly=1.0, tri_every=4, jitter=0.0, step=None):
+    """``nx`` x ``ny`` boxes on ``[0,lx] x [0,ly]``; box (i,j) is a quadrilateral unless
+    ``((i*73856093) ^ (j*19349663)) & (tri_every-1) == 0`` -- then two triangles along its
+    ll-ur diagonal.  ``tri_every=0`` gives quads only, ``1`` triangles only.
+    ``step=(x0, y1)`` removes the forward-facing step ``x >= x0, y < y1`` (box-aligned).
+    Returns ``(ndcrd[nnode,2], cltpn[ncell], clnds[ncell,9])``."""
+    ii, jj = np.meshgrid(np.arange(nx + 1), np.arange(ny + 1), indexing="ij")
+    x = ii * (lx / nx)
+    y = jj * (ly / ny)
+    if jitter:
+        jx, jy = _jitter2(ii, jj, jitter)
+        inner = (ii > 0) & (ii < nx) & (jj > 0) & (jj < ny)
+        if step is not None:
+            # keep the step's walls straight: no jitter on lattice lines touching the cut-out
+            sx, sy = int(round(step[0] / lx * nx)), int(round(step[1] / ly * ny))
+            inner &= ~((ii >= sx) & (jj <= sy))
+        x = x + np.where(inner, jx, 0.0) * (lx / nx)
+        y = y + np.where(inner, jy, 0.0) * (ly / ny)
+    nid = (ii * (ny + 1) + jj).astype(np.int64)
+    bi, bj = np.meshgrid(np.arange(nx), np.arange(ny), indexing="ij")
+    bi, bj = bi.ravel(), bj.ravel()
+    if step is not None:
+        sx, sy = int(round(step[0] / lx * nx)), int(round(step[1] / ly * ny))
+        keep = ~((bi >= sx) & (bj < sy))
+        bi, bj = bi[keep], bj[keep]
+    ll = nid[bi, bj]
+    lr = nid[bi + 1, bj]
+    ur = nid[bi + 1, bj + 1]
+    ul = nid[bi, bj + 1]
+    if tri_every == 0:
+        split = np.zeros(len(bi), dtype=bool)
+    elif tri_every == 1:
+        split = np.ones(len(bi), dtype=bool)
+    else:
+        split = (((bi * 73856093) ^ (bj * 19349663)) & (tri_every - 1)) == 0
+    ncl = np.where(split, 2, 1)
+    first = np.concatenate(([0], np.cumsum(ncl)[:-1]))
+    ncell = int(ncl.sum())
+    cltpn = np.empty(ncell, dtype=np.int32)
+    clnds = np.full((ncell, CLMND + 1), -1, dtype=np.int32)
+    q = first[~split]
+    cltpn[q] = QUAD
+    clnds[q, 0] = 4
+    clnds[q, 1:5] = np.stack([ll, lr, ur, ul], axis=1)[~split]
+    t0 = first[split]
+    cltpn[t0] = TRI
+    cltpn[t0 + 1] = TRI
+    clnds[t0, 0] = 3
+    clnds[t0 + 1, 0] = 3
+    clnds[t0, 1:4] = np.stack([ll, lr, ur], axis=1)[split]
+    clnds[t0 + 1, 1:4] = np.stack([ll, ur, ul], axis=1)[split]
+    ndcrd = np.stack([x.ravel(), y.ravel()], axis=1)
+    if step is not None:
+        ndcrd, clnds = _compact_nodes(ndcrd, clnds)
+    return np.ascontiguousarray(ndcrd), cltpn, clnds
+
+
+def _compact_nodes(ndcrd, clnds):
+    used = np.zeros(len(ndcrd), dtype=bool)
+    valid = clnds[:, 1:] >= 0
+    used[clnds[:, 1:][valid]] = True
+    remap = np.cumsum(used) - 1
+    out = clnds.copy()
+    out[:, 1:][valid] = remap[clnds[:, 1:][valid]]
+    return ndcrd[used], out.astype(np.int32)
+
+
+# Kuhn (Freudenthal) split of the unit box into 6 tetrahedra sharing the v000-v111 diagonal; the
+# z-faces are cut along the ll-ur diagonal, matching the prisms' triangles.  Corner c = 4*dx+2*dy+dz.
+_KUHN = []
+for perm in ((0, 1, 2), (0, 2, 1), (1, 0, 2), (1, 2, 0), (2, 0, 1), (2, 1, 0)):
+    c, path = 0, [0]
+    for axis in perm:
+        c += (4, 2, 1)[axis]
+        path.append(c)
+    _KUHN.append(path)
+
+
+def mixed_3d(nx, ny, nz, lx=None, ly=None, lz=None, x1=None, z1=None, kinds="hpt", jitter=0.0):
+    """Stepped channel of ``nx`` x ``ny`` x ``nz`` boxes: block A hexahedra
+    (``i < x1, k < z1``), block B z-axis prisms (``i >= x1, k < z1``; each box split on its vertical
+    ll-ur diagonal plane), block C tetrahedra (``i >= x1, k >= z1``; Kuhn split, 6 per box); the
+    region ``i < x1, k >= z1`` is solid.  All interfaces conform without pyramids (hex|prism share
+    quads at ``i = x1``, prism|tet share triangles at ``k = z1``).  ``kinds`` selects the blocks:
+    ``"h"`` = hex box only (``x1 = nx, z1 = nz``), ``"hp"``, ``"hpt"``; ``"t"`` / ``"p"`` = one kind
+    everywhere.  Returns ``(ndcrd[nnode,3], cltpn, clnds)``."""
+    lx = float(nx) if lx is None else lx
+    ly = float(ny) if ly is None else ly
+    lz = float(nz) if lz is None else lz
+    if kinds == "h":
+        x1, z1 = nx, nz
+    elif kinds in ("t", "p"):
+        x1, z1 = 0, (0 if kinds == "t" else nz)
+    elif kinds == "hp":
+        x1 = nx // 2 if x1 is None else x1
+        z1 = nz
+    else:
+        x1 = nx // 2 if x1 is None else x1
+        z1 = nz // 2 if z1 is None else z1
+    ii, jj, kk = np.meshgrid(np.arange(nx + 1), np.arange(ny + 1), np.arange(nz + 1), indexing="ij")
+    x = ii * (lx / nx)
+    y = jj * (ly / ny)
+    z = kk * (lz / nz)
+    if jitter:
+        inner = (ii > 0) & (ii < nx) & (jj > 0) & (jj < ny) & (kk > 0) & (kk < nz)
+        inner &= ~((ii <= x1) & (kk >= z1))  # keep the solid block's walls planar
+        x = x + np.where(inner, jitter * np.sin(12.9898 * ii + 78.233 * jj + 37.719 * kk), 0.0) * (lx / nx)
+        y = y + np.where(inner, jitter * np.cos(26.651 * ii + 41.347 * jj + 11.135 * kk), 0.0) * (ly / ny)
+        z = z + np.where(inner, jitter * np.sin(63.7264 * ii + 10.873 * jj + 53.127 * kk), 0.0) * (lz / nz)
+    nid = ((ii * (ny + 1) + jj) * (nz + 1) + kk).astype(np.int64)
+    bi, bj, bk = [a.ravel() for a in np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")]
+    solid = (bi < x1) & (bk >= z1)
+    bi, bj, bk = bi[~solid], bj[~solid], bk[~solid]
+    # box corners c = 4*dx + 2*dy + dz
+    cor = np.stack([nid[bi + dx, bj + dy, bk + dz] for dx in (0, 1) for dy in (0, 1) for dz in (0, 1)], axis=1)
+    is_hex = (bi < x1) & (bk < z1)
+    is_pri = (bi >= x1) & (bk < z1)
+    is_tet = (bi >= x1) & (bk >= z1)
+    ncl = np.where(is_hex, 1, np.where(is_pri, 2, 6))
+    first = np.concatenate(([0], np.cumsum(ncl)[:-1]))
+    ncell = int(ncl.sum())
+    cltpn = np.empty(ncell, dtype=np.int32)
+    clnds = np.full((ncell, CLMND + 1), -1, dtype=np.int32)
+    # hexahedron: bottom 000,100,110,010 then top (StaticMesh_interior.cpp add_hexahedron)
+    h = first[is_hex]
+    cltpn[h] = HEX
+    clnds[h, 0] = 8
+    clnds[h, 1:9] = cor[is_hex][:, [0, 4, 6, 2, 1, 5, 7, 3]]
+    # prisms: triangles (000,100,110) and (000,110,010) extruded in z
+    p = first[is_pri]
+    cp = cor[is_pri]
+    for s, tri in enumerate(((0, 4, 6), (0, 6, 2))):
+        cltpn[p + s] = PRISM
+        clnds[p + s, 0] = 6
+        clnds[p + s, 1:4] = cp[:, list(tri)]
+        clnds[p + s, 4:7] = cp[:, [c + 1 for c in tri]]
+    # tetrahedra
+    t = first[is_tet]
+    ct = cor[is_tet]
+    for s, path in enumerate(_KUHN):
+        cltpn[t + s] = TET
+        clnds[t + s, 0] = 4
+        clnds[t + s, 1:5] = ct[:, path]
+    ndcrd = np.stack([x.ravel(), y.ravel(), z.ravel()], axis=1)
+    # positive orientation for the tetrahedra (swap two nodes where the triple product is negative)
+    tets = np.nonzero(cltpn == TET)[0]
+    if len(tets):
+        n = clnds[tets, 1:5]
+        a, b, c, d = (ndcrd[n[:, q]] for q in range(4))
+        vol = np.einsum("ij,ij->i", np.cross(b - a, c - a), d - a)
+        neg = vol < 0
+        n[neg, 2], n[neg, 3] = n[neg, 3].copy(), n[neg, 2].copy()
+        clnds[tets, 1:5] = n
+    ndcrd, clnds = _compact_nodes(ndcrd, clnds)
+    return np.ascontiguousarray(ndcrd), cltpn, clnds
+
+
+def boundary_groups(ndim, fccnd, fccls, nface, lo, hi, tol=1e-9):
+    """Split the boundary faces (``fccls[:,1] < 0``) of a box-shaped domain into inlet (x = lo[0]),
+    outlet (x = hi[0]) and wall (everything else, incl. the step / solid block) face lists.
+    ``fccnd``/``fccls`` are BODY rows of the StaticMesh tables."""
+    bnd = np.nonzero(fccls[:nface, 1] < 0)[0].astype(np.int32)
+    xc = fccnd[bnd, 0]
+    inlet = bnd[np.abs(xc - lo[0]) < tol]
+    outlet = bnd[np.abs(xc - hi[0]) < tol]
+    wall = bnd[(np.abs(xc - lo[0]) >= tol) & (np.abs(xc - hi[0]) >= tol)]
+    return inlet, outlet, wall

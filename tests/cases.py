@@ -48,3 +48,46 @@ def scalar_ic(x, so0, so1, cfl=None):
         cfl[...] = 0.0
     so0[2::2] = 0.5 * np.sin(x[2::2])
     so1[2::2] = 0.5 * np.cos(x[2::2])
+
+
+# ------------------------------------------------------------------ multidim cases ---
+
+def md_mesh_case(name):
+    """Named small meshes (nodes + cells) for the multidim parity tests."""
+    from solvcon_b200 import meshgen
+    if name == "quad2d":
+        return (2,) + meshgen.mixed_2d(12, 6, lx=3.0, ly=1.0, tri_every=0)
+    if name == "tri2d":
+        return (2,) + meshgen.mixed_2d(10, 5, lx=3.0, ly=1.0, tri_every=1, jitter=0.2)
+    if name == "mixed2d":
+        return (2,) + meshgen.mixed_2d(16, 8, lx=3.0, ly=1.0, tri_every=4, jitter=0.25)
+    if name == "step2d":
+        return (2,) + meshgen.mixed_2d(30, 10, lx=3.0, ly=1.0, tri_every=4, jitter=0.2, step=(0.6, 0.2))
+    if name == "hex3d":
+        return (3,) + meshgen.mixed_3d(5, 4, 3, kinds="h", jitter=0.15)
+    if name == "tet3d":
+        return (3,) + meshgen.mixed_3d(3, 3, 2, kinds="t", jitter=0.15)
+    if name == "prism3d":
+        return (3,) + meshgen.mixed_3d(4, 3, 3, kinds="p", jitter=0.15)
+    if name == "mixed3d":
+        return (3,) + meshgen.mixed_3d(6, 4, 4, kinds="hpt", jitter=0.15)
+    raise KeyError(name)
+
+
+def md_bump_ic(core_body, clcnd_body, ndim, gamma=1.4, mach=2.0, amp=0.3):
+    """Supersonic stream + Gaussian bump written into body rows of so0n (``core_body(name)`` returns
+    the writable body view); gradients start at zero like init_solution leaves them."""
+    c = clcnd_body
+    ctr = c.mean(axis=0)
+    span = c.max(axis=0) - c.min(axis=0)
+    r2 = (((c - ctr) / (0.25 * span)) ** 2).sum(axis=1)
+    rho = 1.4 * (1.0 + amp * np.exp(-r2))
+    p = 1.0 * (1.0 + amp * np.exp(-r2))
+    v = np.zeros((len(c), ndim))
+    v[:, 0] = mach * np.sqrt(gamma * 1.0 / 1.4)
+    v[:, 1] = 0.1 * np.sin(3.0 * c[:, 0])
+    so0 = core_body("so0n")
+    so0[:, 0] = rho
+    for d in range(ndim):
+        so0[:, 1 + d] = rho * v[:, d]
+    so0[:, ndim + 1] = p / (gamma - 1.0) + 0.5 * rho * (v * v).sum(axis=1)
