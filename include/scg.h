@@ -170,6 +170,9 @@ SCG_API int scg_mesh_perm(scg_mesh * m, int32_t * perm /* ncell */);
 SCG_API int scg_md_create(scg_md ** out, scg_mesh * mesh, double time_increment);
 SCG_API int scg_md_destroy(scg_md * s);
 SCG_API int scg_md_set_params(scg_md * s, double sigma0, double taumin, double tauscale); /* euler.hpp:99-104 */
+SCG_API int scg_md_set_time_increment(scg_md * s, double time_increment);
+/* 1 (default): march uses the fused soln+cfl+dsoln kernel; 0: one kernel per reference phase */
+SCG_API int scg_md_set_fused(scg_md * s, int fused);
 /* init_solution(gamma, rho, v, p), euler_solution.cpp:54-99 (v has 3 entries) */
 SCG_API int scg_md_init_solution(scg_md * s, double gamma, double rho, const double * v, double p);
 /* add_bc(kind, faces, value), euler_bc.cpp:324-389; same validation, same order semantics */
@@ -189,13 +192,17 @@ SCG_API int scg_md_algorithmic_bytes(scg_md * s, int64_t * bytes_per_substep);
 /* get_normal_matrix(ifc), euler_bc.cpp:391-425 (host-side helper, row-major ndim x ndim) */
 SCG_API int scg_md_normal_matrix(scg_md * s, int32_t ifc, double * out);
 
-/* halo exchange support for domain decomposition (one process per GPU; the caller moves the
- * packed buffers with NCCL send/recv or peer copies, see solvcon_b200/decomp.py):
- * pack the new state (so0n+so1n, neq*(1+ndim) doubles per cell) of the listed device-order
- * cells into a contiguous device buffer, and scatter a received buffer into ghost rows. */
+/* halo exchange support for domain decomposition (one process per GPU; the caller moves the packed
+ * buffers with NCCL send/recv, see solvcon_b200/decomp.py).  A partition is a StaticMesh of the owned
+ * cells whose interface faces are boundary faces; the ghost cell of an interface face is the HALO copy
+ * of the remote neighbour.  send_cells are local reference cell ids, recv_ghosts local ghost indices g
+ * (reference index -(g+1)).  what = 0: the new state so0n+so1n, neq*(1+ndim) doubles per cell, every
+ * substep;  what = 1: solution point + gamma, ndim+1 doubles per cell, once at setup (the halo's
+ * solution point is the remote CE centroid, euler_march.cpp:229-234, not the mirrored centroid).
+ * Buffers are component-major: buf[c * ncells + i]. */
 SCG_API int scg_md_halo_set(scg_md * s, const int32_t * send_cells, int64_t nsend, const int32_t * recv_ghosts, int64_t nrecv);
-SCG_API int scg_md_halo_pack(scg_md * s, double ** dev_buffer, int64_t * ndouble);
-SCG_API int scg_md_halo_unpack(scg_md * s, const double * dev_buffer);
+SCG_API int scg_md_halo_pack(scg_md * s, int what, double ** dev_buffer, int64_t * ndouble);
+SCG_API int scg_md_halo_unpack(scg_md * s, int what, const double * dev_buffer);
 
 #ifdef __cplusplus
 }

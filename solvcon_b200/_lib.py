@@ -74,6 +74,8 @@ _SIGNATURES = {
     "scg_md_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_double]),
     "scg_md_destroy": (C.c_int, [C.c_void_p]),
     "scg_md_set_params": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double]),
+    "scg_md_set_time_increment": (C.c_int, [C.c_void_p, C.c_double]),
+    "scg_md_set_fused": (C.c_int, [C.c_void_p, C.c_int]),
     "scg_md_init_solution": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_double]),
     "scg_md_add_bc": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]),
     "scg_md_clear_bc": (C.c_int, [C.c_void_p]),
@@ -85,8 +87,8 @@ _SIGNATURES = {
     "scg_md_algorithmic_bytes": (C.c_int, [C.c_void_p, I64P]),
     "scg_md_normal_matrix": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "scg_md_halo_set": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]),
-    "scg_md_halo_pack": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), I64P]),
-    "scg_md_halo_unpack": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "scg_md_halo_pack": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), I64P]),
+    "scg_md_halo_unpack": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
 }
 
 _lib = None

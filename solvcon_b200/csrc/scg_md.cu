@@ -1,25 +1,1322 @@
-// scg_md.cu -- multidim Euler CESE on the device (placeholder while the kernels land).
-#include "scg_common.cuh"
+// scg_md.cu -- multidim Euler CESE on the device: the SoA field store, CE geometry setup, the per-phase
+// and fused substep kernels, on-device boundary conditions, reductions and the C-ABI of include/scg.h.
+//
+// Device twin of solvcon::EulerCore (cpp/solvcon/multidim/euler.hpp:56-211).
+#include "scg_md_kernels.cuh"
+
+#include <cmath>
+#include <cstring>
+
 using namespace scg;
-#define NOTYET(name) return fail(name ": not implemented yet")
-extern "C" {
-int scg_mesh_create(scg_mesh **, int, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, const int32_t *, const int32_t *, const int32_t *, const int32_t *, const double *, const double *, const double *, const double *, int) { NOTYET("scg_mesh_create"); }
-int scg_mesh_destroy(scg_mesh *) { return 0; }
-int scg_mesh_perm(scg_mesh *, int32_t *) { NOTYET("scg_mesh_perm"); }
-int scg_md_create(scg_md **, scg_mesh *, double) { NOTYET("scg_md_create"); }
-int scg_md_destroy(scg_md *) { return 0; }
-int scg_md_set_params(scg_md *, double, double, double) { NOTYET("scg_md_set_params"); }
-int scg_md_init_solution(scg_md *, double, double, const double *, double) { NOTYET("scg_md_init_solution"); }
-int scg_md_add_bc(scg_md *, int, const int32_t *, int64_t, const double *, int) { NOTYET("scg_md_add_bc"); }
-int scg_md_clear_bc(scg_md *) { NOTYET("scg_md_clear_bc"); }
-int scg_md_upload(scg_md *, int, const double *) { NOTYET("scg_md_upload"); }
-int scg_md_download(scg_md *, int, double *) { NOTYET("scg_md_download"); }
-int scg_md_phase(scg_md *, int) { NOTYET("scg_md_phase"); }
-int scg_md_march(scg_md *, int64_t) { NOTYET("scg_md_march"); }
-int scg_md_reduce(scg_md *, const double *, double *, double *, double *) { NOTYET("scg_md_reduce"); }
-int scg_md_algorithmic_bytes(scg_md *, int64_t *) { NOTYET("scg_md_algorithmic_bytes"); }
-int scg_md_normal_matrix(scg_md *, int32_t, double *) { NOTYET("scg_md_normal_matrix"); }
-int scg_md_halo_set(scg_md *, const int32_t *, int64_t, const int32_t *, int64_t) { NOTYET("scg_md_halo_set"); }
-int scg_md_halo_pack(scg_md *, double **, int64_t *) { NOTYET("scg_md_halo_pack"); }
-int scg_md_halo_unpack(scg_md *, const double *) { NOTYET("scg_md_halo_unpack"); }
+
+namespace
+{
+
+// ================================================================================================
+// CE geometry: EulerCore::prepare_ce_2d / prepare_ce_3d (euler_ce.cpp:78-347), one thread per cell,
+// straight from the reference-layout mesh tables (body pointers; ghost rows at negative indices).
+// ================================================================================================
+struct RawMesh
+{
+    int32_t const * clfcs; // body pointers
+    int32_t const * fccls;
+    int32_t const * fcnds;
+    double const * ndcrd;
+    double const * fccnd;
+    double const * clcnd;
+    int32_t const * perm;
+};
+
+template <int TYPE>
+__global__ void __launch_bounds__(128) md_prepare_ce_kernel(RawMesh const M, MdGeo const G, double * solpt, int64_t S)
+{
+    constexpr int ND = ct_ndim(TYPE);
+    constexpr int NFC = ct_nfc(TYPE);
+    int32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= G.n) { return; }
+    int64_t const n = G.n;
+    int64_t const k = G.beg + i;
+    int64_t const icl = M.perm[k];
+    double volc = 0.0;
+    double cc[ND];
+    double ci[ND];
+#pragma unroll
+    for (int d = 0; d < ND; ++d)
+    {
+        cc[d] = 0.0;
+        ci[d] = M.clcnd[icl * ND + d];
+    }
+#pragma unroll 1
+    for (int f = 0; f < NFC; ++f)
+    {
+        int64_t const ifc = M.clfcs[icl * 7 + 1 + f];
+        int64_t const jcl = M.fccls[ifc * 4 + 0] + M.fccls[ifc * 4 + 1] - static_cast<int32_t>(icl);
+        double ce[ND];
+#pragma unroll
+        for (int d = 0; d < ND; ++d) { ce[d] = M.clcnd[jcl * ND + d]; }
+        int const q0 = ct_sfoff(TYPE, f);
+        if (2 == ND)
+        {
+            // euler_ce.cpp:92-170
+            int64_t const ind0 = M.fcnds[ifc * 5 + 1];
+            int64_t const ind1 = M.fcnds[ifc * 5 + 2];
+            double const crd10 = M.ndcrd[ind0 * 2 + 0];
+            double const crd11 = M.ndcrd[ind0 * 2 + 1];
+            double const crd20 = M.ndcrd[ind1 * 2 + 0];
+            double const crd21 = M.ndcrd[ind1 * 2 + 1];
+            double const cndi0 = (crd10 + crd20 + ci[0]) / 3.0;
+            double const cndi1 = (crd11 + crd21 + ci[1]) / 3.0;
+            double const voli = fabs((crd10 - ci[0]) * (crd21 - ci[1]) - (crd11 - ci[1]) * (crd20 - ci[0])) / 2.0;
+            double const cnde0 = (crd10 + crd20 + ce[0]) / 3.0;
+            double const cnde1 = (crd11 + crd21 + ce[1]) / 3.0;
+            double const cross = (crd10 - ce[0]) * (crd21 - ce[1]) - (crd11 - ce[1]) * (crd20 - ce[0]);
+            double const vole = fabs(cross) / 2.0;
+            double const volb = voli + vole;
+            G.cevol[(f + 1) * n + i] = volb;
+            G.cecnd[(f * 2 + 0) * n + i] = (cndi0 * voli + cnde0 * vole) / volb;
+            G.cecnd[(f * 2 + 1) * n + i] = (cndi1 * voli + cnde1 * vole) / volb;
+            volc += volb;
+            cc[0] += (cndi0 * voli + cnde0 * vole);
+            cc[1] += (cndi1 * voli + cnde1 * vole);
+            double const sgn = (cross > 0.0) ? 1.0 : -1.0;
+            G.sfcnd[((q0 + 0) * 2 + 0) * n + i] = (ce[0] + crd10) / 2.0;
+            G.sfcnd[((q0 + 0) * 2 + 1) * n + i] = (ce[1] + crd11) / 2.0;
+            double const a_dx = ce[0] - crd10;
+            double const a_dy = ce[1] - crd11;
+            G.sfnml[((q0 + 0) * 2 + 0) * n + i] = -a_dy * sgn;
+            G.sfnml[((q0 + 0) * 2 + 1) * n + i] = a_dx * sgn;
+            G.sfcnd[((q0 + 1) * 2 + 0) * n + i] = (crd20 + ce[0]) / 2.0;
+            G.sfcnd[((q0 + 1) * 2 + 1) * n + i] = (crd21 + ce[1]) / 2.0;
+            double const b_dx = crd20 - ce[0];
+            double const b_dy = crd21 - ce[1];
+            G.sfnml[((q0 + 1) * 2 + 0) * n + i] = -b_dy * sgn;
+            G.sfnml[((q0 + 1) * 2 + 1) * n + i] = b_dx * sgn;
+        }
+        else
+        {
+            // euler_ce.cpp:192-340
+            constexpr int Z = ND - 1;
+            int const fcnnd = ct_fnnd(TYPE, f);
+            double fc[3];
+            double crd[FCMND + 2][3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) { fc[d] = M.fccnd[ifc * 3 + d]; }
+            for (int inf = 1; inf <= fcnnd; ++inf)
+            {
+                int64_t const ind = M.fcnds[ifc * 5 + inf];
+                for (int d = 0; d < 3; ++d) { crd[inf][d] = M.ndcrd[ind * 3 + d]; }
+            }
+            for (int d = 0; d < 3; ++d) { crd[fcnnd + 1][d] = crd[1][d]; }
+            double volb = 0.0;
+            double bc[3] = {0.0, 0.0, 0.0};
+            double const voe = (M.fccls[ifc * 4] == icl) ? 0.5 : -0.5;
+            for (int inf = 1; inf <= fcnnd; ++inf)
+            {
+                double du[3], dv[3], dw[3], wi[3], we[3];
+                for (int d = 0; d < 3; ++d)
+                {
+                    du[d] = crd[inf][d] - fc[d];
+                    dv[d] = crd[inf + 1][d] - fc[d];
+                }
+                dw[0] = du[1] * dv[2] - du[2] * dv[1];
+                dw[1] = du[2] * dv[0] - du[0] * dv[2];
+                dw[2] = du[0] * dv[1] - du[1] * dv[0];
+                for (int d = 0; d < 3; ++d)
+                {
+                    wi[d] = ci[d < ND ? d : Z] - fc[d];
+                    we[d] = ce[d < ND ? d : Z] - fc[d];
+                }
+                double const voli = fabs(dw[0] * wi[0] + dw[1] * wi[1] + dw[2] * wi[2]) / 6.0;
+                double const vole = fabs(dw[0] * we[0] + dw[1] * we[1] + dw[2] * we[2]) / 6.0;
+                volb += voli + vole;
+                for (int d = 0; d < 3; ++d)
+                {
+                    double const cndi = (crd[inf][d] + crd[inf + 1][d] + fc[d] + ci[d < ND ? d : Z]) / 4.0;
+                    double const cnde = (crd[inf][d] + crd[inf + 1][d] + fc[d] + ce[d < ND ? d : Z]) / 4.0;
+                    bc[d] += cndi * voli + cnde * vole;
+                }
+                int64_t const q = q0 + (inf - 1);
+                double su[3], sv[3];
+                for (int d = 0; d < 3; ++d)
+                {
+                    double const cev = ce[d < ND ? d : Z];
+                    G.sfcnd[(q * 3 + d) * n + i] = (cev + crd[inf][d] + crd[inf + 1][d]) / 3.0;
+                    su[d] = crd[inf][d] - cev;
+                    sv[d] = crd[inf + 1][d] - cev;
+                }
+                G.sfnml[(q * 3 + 0) * n + i] = (su[1] * sv[2] - su[2] * sv[1]) * voe;
+                G.sfnml[(q * 3 + 1) * n + i] = (su[2] * sv[0] - su[0] * sv[2]) * voe;
+                G.sfnml[(q * 3 + 2) * n + i] = (su[0] * sv[1] - su[1] * sv[0]) * voe;
+            }
+            G.cevol[(f + 1) * n + i] = volb;
+            for (int d = 0; d < ND; ++d)
+            {
+                G.cecnd[(f * ND + d) * n + i] = bc[d] / volb;
+                cc[d] += bc[d];
+            }
+            volc += volb;
+        }
+    }
+    G.cevol[i] = volc;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) { solpt[d * S + k] = cc[d] / volc; }
 }
+
+// ghost solution points are the (mirrored) mesh cell centroids (euler_march.cpp:231-234)
+__global__ void md_ghost_solpt_kernel(double const * clcnd_stored, int ndim, int64_t ngst, int64_t ncell, double * solpt, int64_t S)
+{
+    int64_t const g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (g >= ngst) { return; }
+    int64_t const row = ngst - 1 - g; // stored row of reference index -(g+1)
+    for (int d = 0; d < ndim; ++d) { solpt[d * S + ncell + g] = clcnd_stored[row * ndim + d]; }
+}
+
+// ================================================================================================
+// phases
+// ================================================================================================
+template <int ND>
+__global__ void __launch_bounds__(256) md_solt_kernel(MdField const F, int32_t row0, int32_t nrow)
+{
+    int32_t const r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrow) { return; }
+    int64_t const k = row0 + r;
+    int64_t const S = F.S;
+    double u[ND + 2], g[ND + 2][ND], t[ND + 2];
+#pragma unroll
+    for (int e = 0; e < ND + 2; ++e)
+    {
+        u[e] = F.so0c[e * S + k];
+#pragma unroll
+        for (int d = 0; d < ND; ++d) { g[e][d] = F.so1c[(e * ND + d) * S + k]; }
+    }
+    Jaco<ND> J;
+    jaco_update<ND>(J, F.gamma[k], u);
+    solt_row<ND>(J, g, t);
+#pragma unroll
+    for (int e = 0; e < ND + 2; ++e) { F.so0t[e * S + k] = t[e]; }
+}
+
+template <int TYPE>
+__global__ void __launch_bounds__(128) md_soln_kernel(MdField const F, MdGeo const G)
+{
+    constexpr int NEQ = ct_ndim(TYPE) + 2;
+    int32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= G.n) { return; }
+    double un[NEQ];
+    cell_soln<TYPE>(F, G, i, un);
+    int64_t const k = G.beg + i;
+#pragma unroll
+    for (int e = 0; e < NEQ; ++e) { F.so0n[e * F.S + k] = un[e]; }
+}
+
+template <int TYPE>
+__global__ void __launch_bounds__(128) md_cfl_kernel(MdField const F, MdGeo const G)
+{
+    constexpr int NEQ = ct_ndim(TYPE) + 2;
+    int32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= G.n) { return; }
+    int64_t const k = G.beg + i;
+    double un[NEQ];
+#pragma unroll
+    for (int e = 0; e < NEQ; ++e) { un[e] = F.so0n[e * F.S + k]; }
+    double cflo, cflc;
+    cell_cfl<TYPE>(F, G, i, un, cflo, cflc);
+    F.cflo[k] = cflo;
+    F.cflc[k] = cflc;
+    F.so0n[(NEQ - 1) * F.S + k] = un[NEQ - 1];
+}
+
+template <int TYPE>
+__global__ void __launch_bounds__(128) md_dsoln_kernel(MdField const F, MdGeo const G)
+{
+    constexpr int ND = ct_ndim(TYPE);
+    constexpr int NEQ = ND + 2;
+    int32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= G.n) { return; }
+    int64_t const k = G.beg + i;
+    double un[NEQ];
+#pragma unroll
+    for (int e = 0; e < NEQ; ++e) { un[e] = F.so0n[e * F.S + k]; }
+    double gn[NEQ][ND];
+    cell_dsoln<TYPE>(F, G, i, un, F.cflc[k], gn);
+#pragma unroll
+    for (int e = 0; e < NEQ; ++e)
+    {
+#pragma unroll
+        for (int d = 0; d < ND; ++d) { F.so1n[(e * ND + d) * F.S + k] = gn[e][d]; }
+    }
+}
+
+// Fused substep for body cells: calc_soln -> calc_cfl -> calc_dsoln of one cell in one pass.  The
+// phases only couple through the cell's own so0n (SURVEY.md 8a hazard 2), so no grid-wide sync is
+// needed.  Ghost cells must see the energy BEFORE calc_cfl's fix-up (hazard 1: bc_soln runs between
+// calc_soln and calc_cfl, euler_march.cpp:343-345); cells beside a ghost therefore park that raw
+// energy in eraw[ghost] for the boundary kernel.
+template <int TYPE>
+__global__ void __launch_bounds__(128) md_substep_kernel(MdField const F, MdGeo const G, double * eraw)
+{
+    constexpr int ND = ct_ndim(TYPE);
+    constexpr int NEQ = ND + 2;
+    constexpr int NFC = ct_nfc(TYPE);
+    int32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= G.n) { return; }
+    int64_t const k = G.beg + i;
+    int64_t const S = F.S;
+    double un[NEQ];
+    cell_soln<TYPE>(F, G, i, un);
+#pragma unroll
+    for (int f = 0; f < NFC; ++f)
+    {
+        int32_t const j = G.nbr[f * int64_t(G.n) + i];
+        if (j >= F.ncell) { eraw[j - F.ncell] = un[NEQ - 1]; }
+    }
+    double cflo, cflc;
+    cell_cfl<TYPE>(F, G, i, un, cflo, cflc);
+    F.cflo[k] = cflo;
+    F.cflc[k] = cflc;
+#pragma unroll
+    for (int e = 0; e < NEQ; ++e) { F.so0n[e * S + k] = un[e]; }
+    double gn[NEQ][ND];
+    cell_dsoln<TYPE>(F, G, i, un, cflc, gn);
+#pragma unroll
+    for (int e = 0; e < NEQ; ++e)
+    {
+#pragma unroll
+        for (int d = 0; d < ND; ++d) { F.so1n[(e * ND + d) * S + k] = gn[e][d]; }
+    }
+}
+
+// ================================================================================================
+// boundary conditions: one thread per (deduplicated) boundary face
+// ================================================================================================
+struct BcDev
+{
+    int32_t const * icl; // interior cell (device index)
+    int32_t const * jcl; // ghost cell (device index)
+    int32_t const * kind;
+    double const * mat;  // [ndim*ndim][n] normal matrix
+    double const * val;  // [neq][n] conserved inlet state
+    int32_t n;
+};
+
+template <int ND>
+__device__ __forceinline__ void matvec(double const (&m)[ND][ND], double const (&v)[ND], double (&r)[ND])
+{
+#pragma unroll
+    for (int a = 0; a < ND; ++a)
+    {
+        r[a] = 0.0;
+#pragma unroll
+        for (int b = 0; b < ND; ++b) { r[a] += m[a][b] * v[b]; }
+    }
+}
+
+template <int ND>
+__device__ __forceinline__ void matmat(double const (&a)[ND][ND], double const (&b)[ND][ND], double (&r)[ND][ND])
+{
+#pragma unroll
+    for (int p = 0; p < ND; ++p)
+    {
+#pragma unroll
+        for (int q = 0; q < ND; ++q)
+        {
+            r[p][q] = 0.0;
+#pragma unroll
+            for (int c = 0; c < ND; ++c) { r[p][q] += a[p][c] * b[c][q]; }
+        }
+    }
+}
+
+// bc_soln_impl, euler_bc.cpp:143-215.  USE_ERAW: take the interior energy from eraw[ghost] (fused march).
+template <int ND, bool USE_ERAW>
+__global__ void __launch_bounds__(128) md_bc_soln_kernel(MdField const F, BcDev const B, double const * eraw)
+{
+    constexpr int NEQ = ND + 2;
+    int32_t const b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B.n) { return; }
+    int64_t const S = F.S;
+    int64_t const icl = B.icl[b];
+    int64_t const jcl = B.jcl[b];
+    int const kind = B.kind[b];
+    double ui[NEQ], uj[NEQ];
+#pragma unroll
+    for (int e = 0; e < NEQ; ++e) { ui[e] = F.so0n[e * S + icl]; }
+    if (USE_ERAW) { ui[NEQ - 1] = eraw[jcl - F.ncell]; }
+    if (SCG_BC_NONREFL == kind)
+    {
+#pragma unroll
+        for (int e = 0; e < NEQ; ++e) { uj[e] = ui[e]; }
+    }
+    else if (SCG_BC_SLIPWALL == kind)
+    {
+        double mat[ND][ND], inv[ND][ND], mom[ND], rot[ND], out[ND];
+#pragma unroll
+        for (int p = 0; p < ND; ++p)
+        {
+#pragma unroll
+            for (int q = 0; q < ND; ++q)
+            {
+                mat[p][q] = B.mat[(p * ND + q) * int64_t(B.n) + b];
+                inv[q][p] = mat[p][q];
+            }
+        }
+        uj[0] = ui[0];
+        uj[NEQ - 1] = ui[NEQ - 1];
+#pragma unroll
+        for (int d = 0; d < ND; ++d) { mom[d] = ui[1 + d]; }
+        matvec<ND>(mat, mom, rot);
+        rot[0] = -rot[0];
+        matvec<ND>(inv, rot, out);
+#pragma unroll
+        for (int d = 0; d < ND; ++d) { uj[1 + d] = out[d]; }
+    }
+    else
+    {
+#pragma unroll
+        for (int e = 0; e < NEQ; ++e) { uj[e] = B.val[e * int64_t(B.n) + b]; }
+    }
+#pragma unroll
+    for (int e = 0; e < NEQ; ++e) { F.so0n[e * S + jcl] = uj[e]; }
+}
+
+// bc_dsoln_impl, euler_bc.cpp:219-320: reads so1c of the interior cell, writes so1n of the ghost
+template <int ND>
+__global__ void __launch_bounds__(128) md_bc_dsoln_kernel(MdField const F, BcDev const B)
+{
+    constexpr int NEQ = ND + 2;
+    int32_t const b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B.n) { return; }
+    int64_t const S = F.S;
+    int64_t const icl = B.icl[b];
+    int64_t const jcl = B.jcl[b];
+    int const kind = B.kind[b];
+    double gi[NEQ][ND], gj[NEQ][ND];
+#pragma unroll
+    for (int e = 0; e < NEQ; ++e)
+    {
+#pragma unroll
+        for (int d = 0; d < ND; ++d) { gi[e][d] = F.so1c[(e * ND + d) * S + icl]; }
+    }
+    if (SCG_BC_INLET == kind)
+    {
+#pragma unroll
+        for (int e = 0; e < NEQ; ++e)
+        {
+#pragma unroll
+            for (int d = 0; d < ND; ++d) { gj[e][d] = 0.0; }
+        }
+    }
+    else
+    {
+        double mat[ND][ND], inv[ND][ND];
+#pragma unroll
+        for (int p = 0; p < ND; ++p)
+        {
+#pragma unroll
+            for (int q = 0; q < ND; ++q)
+            {
+                mat[p][q] = B.mat[(p * ND + q) * int64_t(B.n) + b];
+                inv[q][p] = mat[p][q];
+            }
+        }
+        if (SCG_BC_NONREFL == kind)
+        {
+#pragma unroll
+            for (int e = 0; e < NEQ; ++e)
+            {
+                double rot[ND];
+                matvec<ND>(mat, gi[e], rot);
+                rot[0] = 0.0;
+                matvec<ND>(inv, rot, gj[e]);
+            }
+        }
+        else
+        {
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+            {
+                int const e = q ? NEQ - 1 : 0;
+                double rot[ND];
+                matvec<ND>(mat, gi[e], rot);
+                rot[0] = -rot[0];
+                matvec<ND>(inv, rot, gj[e]);
+            }
+            double mg[ND][ND], t0[ND][ND], uv[ND][ND], t1[ND][ND], out[ND][ND];
+#pragma unroll
+            for (int a = 0; a < ND; ++a)
+            {
+#pragma unroll
+                for (int c = 0; c < ND; ++c) { mg[a][c] = gi[1 + a][c]; }
+            }
+            matmat<ND>(mat, mg, t0);
+            matmat<ND>(t0, inv, uv);
+#pragma unroll
+            for (int it = 1; it < ND; ++it)
+            {
+                uv[0][it] = -uv[0][it];
+                uv[it][0] = -uv[it][0];
+            }
+            matmat<ND>(inv, uv, t1);
+            matmat<ND>(t1, mat, out);
+#pragma unroll
+            for (int a = 0; a < ND; ++a)
+            {
+#pragma unroll
+                for (int c = 0; c < ND; ++c) { gj[1 + a][c] = out[a][c]; }
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < NEQ; ++e)
+    {
+#pragma unroll
+        for (int d = 0; d < ND; ++d) { F.so1n[(e * ND + d) * S + jcl] = gj[e][d]; }
+    }
+}
+
+// ================================================================================================
+// host layout (reference AoS, ghost rows first, reference cell order) <-> device SoA
+// ================================================================================================
+template <bool TO_DEVICE>
+__global__ void md_rows_kernel(double * stage, int64_t row0, int64_t nrow, int ncomp, int32_t const * rowmap, double * dev, int64_t S)
+{
+    int64_t const t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= nrow * ncomp) { return; }
+    int64_t const r = t / ncomp;
+    int const c = static_cast<int>(t % ncomp);
+    int64_t const k = rowmap[row0 + r];
+    if (TO_DEVICE) { dev[c * S + k] = stage[t]; }
+    else { stage[t] = dev[c * S + k]; }
+}
+
+__device__ __forceinline__ int find_group(GroupTable const & GT, int32_t k)
+{
+    int g = 0;
+    while (g + 1 < GT.ngroup && k >= GT.g[g + 1].beg) { ++g; }
+    return g;
+}
+
+// which: SCG_A_CEVOL / CECND / SFCND / SFNML.  Host rows: cevol[T][7], cecnd[T][7*ndim] (ghost rows first),
+// sfcnd/sfnml[ncell][24][ndim] (body only).
+template <bool TO_DEVICE>
+__global__ void md_geo_rows_kernel(int which, double * stage, int64_t row0, int64_t nrow, int ncomp, int ndim, int64_t ngst,
+                                   int32_t const * rowmap, GroupTable const GT, double * geo, double * solpt, int64_t S)
+{
+    int64_t const t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= nrow * ncomp) { return; }
+    int64_t const r = row0 + t / ncomp;
+    int const c = static_cast<int>(t % ncomp);
+    bool const has_ghost_rows = (SCG_A_CEVOL == which || SCG_A_CECND == which);
+    int64_t const stored = has_ghost_rows ? r : r + ngst;
+    double * slot = nullptr;
+    if (stored >= ngst)
+    {
+        int32_t const k = rowmap[stored];
+        MeshGroup const & g = GT.g[find_group(GT, k)];
+        int64_t const i = k - g.beg;
+        int64_t const n = g.n;
+        int const nfc = ct_nfc(g.type);
+        if (SCG_A_CEVOL == which)
+        {
+            if (c <= nfc) { slot = geo + g.geo_cevol() + c * n + i; }
+        }
+        else if (SCG_A_CECND == which)
+        {
+            int const f = c / ndim, d = c % ndim;
+            if (0 == f) { slot = solpt + d * S + k; }
+            else if (f <= nfc) { slot = geo + g.geo_cecnd() + ((f - 1) * ndim + d) * n + i; }
+        }
+        else
+        {
+            int const d = c % ndim;
+            int const fl = (c / ndim) / FCMND, inf = (c / ndim) % FCMND;
+            if (fl < nfc && inf < ct_fnnd(g.type, fl))
+            {
+                int64_t const q = ct_sfoff(g.type, fl) + inf;
+                slot = geo + (SCG_A_SFCND == which ? g.geo_sfcnd() : g.geo_sfnml()) + (q * ndim + d) * n + i;
+            }
+        }
+    }
+    if (TO_DEVICE)
+    {
+        if (slot) { *slot = stage[t]; }
+    }
+    else { stage[t] = slot ? *slot : 0.0; }
+}
+
+__global__ void md_fill_kernel(double * p, int64_t n, double v)
+{
+    int64_t const t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t < n) { p[t] = v; }
+}
+
+// init_solution, euler_solution.cpp:54-99: uniform conserved state into so0n body rows
+__global__ void md_init_kernel(double * so0n, int64_t S, int64_t ncell, int neq, double u0, double u1, double u2, double u3, double u4)
+{
+    int64_t const k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (k >= ncell) { return; }
+    double const u[5] = {u0, u1, u2, u3, u4};
+    for (int e = 0; e < neq; ++e) { so0n[e * S + k] = u[e]; }
+}
+
+// callers' numpy reductions done on the device (solvcon/multidim/euler/_field.py:138-148)
+__global__ void __launch_bounds__(256) md_reduce_kernel(double const * cflo, double const * rho, double const * vol, int64_t ncell, double * out)
+{
+    double mn = DBL_MAX, mx = -DBL_MAX, sm = 0.0;
+    int64_t const stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; k < ncell; k += stride)
+    {
+        double const c = cflo[k];
+        mn = fmin(mn, c);
+        mx = fmax(mx, c);
+        if (vol) { sm += rho[k] * vol[k]; }
+    }
+    for (int off = 16; off > 0; off >>= 1)
+    {
+        mn = fmin(mn, __shfl_down_sync(0xffffffffu, mn, off));
+        mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, off));
+        sm += __shfl_down_sync(0xffffffffu, sm, off);
+    }
+    __shared__ double smn[8], smx[8], ssm[8];
+    int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (0 == lane)
+    {
+        smn[warp] = mn;
+        smx[warp] = mx;
+        ssm[warp] = sm;
+    }
+    __syncthreads();
+    if (0 == threadIdx.x)
+    {
+        for (int w = 1; w < 8; ++w)
+        {
+            mn = fmin(mn, smn[w]);
+            mx = fmax(mx, smx[w]);
+            sm += ssm[w];
+        }
+        out[3 * blockIdx.x + 0] = mn;
+        out[3 * blockIdx.x + 1] = mx;
+        out[3 * blockIdx.x + 2] = sm;
+    }
+}
+
+// halo exchange support: gather the listed cells' new state / scatter into ghost rows
+__global__ void md_halo_pack_kernel(double const * so0, double const * so1, double const * solpt, double const * gamma, int what,
+                                    int32_t const * cells, int64_t ncells, int neq, int ndim, int64_t S, double * buf)
+{
+    int64_t const t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= ncells) { return; }
+    int64_t const k = cells[t];
+    if (0 == what)
+    {
+        for (int e = 0; e < neq; ++e) { buf[e * ncells + t] = so0[e * S + k]; }
+        for (int c = 0; c < neq * ndim; ++c) { buf[(neq + c) * ncells + t] = so1[c * S + k]; }
+    }
+    else
+    {
+        for (int d = 0; d < ndim; ++d) { buf[d * ncells + t] = solpt[d * S + k]; }
+        buf[ndim * ncells + t] = gamma[k];
+    }
+}
+
+__global__ void md_halo_unpack_kernel(double * so0, double * so1, double * solpt, double * gamma, int what, int32_t const * ghosts,
+                                      int64_t nghost, int neq, int ndim, int64_t S, double const * buf)
+{
+    int64_t const t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= nghost) { return; }
+    int64_t const k = ghosts[t];
+    if (0 == what)
+    {
+        for (int e = 0; e < neq; ++e) { so0[e * S + k] = buf[e * nghost + t]; }
+        for (int c = 0; c < neq * ndim; ++c) { so1[c * S + k] = buf[(neq + c) * nghost + t]; }
+    }
+    else
+    {
+        for (int d = 0; d < ndim; ++d) { solpt[d * S + k] = buf[d * nghost + t]; }
+        gamma[k] = buf[ndim * nghost + t];
+    }
+}
+
+struct BcReg
+{
+    int kind;
+    std::vector<int32_t> faces;
+    std::vector<double> value;
+};
+
+constexpr int64_t STAGE_DOUBLES = int64_t(1) << 23; // 64 MiB staging buffer
+
+} // namespace
+
+struct scg_md
+{
+    scg_mesh * mesh = nullptr;
+    int ndim = 0, neq = 0;
+    double dt = 0, sigma0 = 3.0, taumin = 0.0, tauscale = 1.0; // euler.hpp:184-188
+    int cur = 0;                                               // so0[cur] is so0c, so0[1-cur] is so0n
+    DevBuf<double> so0[2], so1[2], so0t, gamma, cflo, cflc, solpt, geo, eraw, stage, red, clvol;
+    bool have_clvol = false;
+    bool fused = true;
+    std::vector<BcReg> regs;
+    bool bc_dirty = true;
+    int32_t nbc = 0;
+    DevBuf<int32_t> bc_icl, bc_jcl, bc_kind;
+    DevBuf<double> bc_mat, bc_val;
+    // halo
+    DevBuf<int32_t> halo_send, halo_recv;
+    DevBuf<double> halo_buf;
+    int64_t nsend = 0, nrecv = 0;
+};
+
+namespace
+{
+
+MdField field_of(scg_md * s)
+{
+    MdField F;
+    F.so0c = s->so0[s->cur].p;
+    F.so0n = s->so0[1 - s->cur].p;
+    F.so1c = s->so1[s->cur].p;
+    F.so1n = s->so1[1 - s->cur].p;
+    F.so0t = s->so0t.p;
+    F.gamma = s->gamma.p;
+    F.cflo = s->cflo.p;
+    F.cflc = s->cflc.p;
+    F.solpt = s->solpt.p;
+    F.S = s->mesh->stride;
+    F.ncell = static_cast<int32_t>(s->mesh->ncell);
+    F.T = static_cast<int32_t>(s->mesh->T);
+    F.dt = s->dt;
+    F.sigma0 = s->sigma0;
+    F.taumin = s->taumin;
+    F.tauscale = s->tauscale;
+    return F;
+}
+
+MdGeo geo_of(scg_md * s, MeshGroup const & g)
+{
+    MdGeo G;
+    G.nbr = s->mesh->d_nbr.p + g.off_nbr;
+    G.cevol = s->geo.p + g.geo_cevol();
+    G.cecnd = s->geo.p + g.geo_cecnd();
+    G.sfcnd = s->geo.p + g.geo_sfcnd();
+    G.sfnml = s->geo.p + g.geo_sfnml();
+    G.beg = g.beg;
+    G.n = g.n;
+    return G;
+}
+
+GroupTable table_of(scg_md * s)
+{
+    GroupTable GT;
+    GT.ngroup = static_cast<int>(s->mesh->groups.size());
+    for (int q = 0; q < GT.ngroup; ++q) { GT.g[q] = s->mesh->groups[q]; }
+    return GT;
+}
+
+enum CellPhase
+{
+    CP_PREPARE,
+    CP_SOLN,
+    CP_CFL,
+    CP_DSOLN,
+    CP_SUBSTEP,
+};
+
+template <int TYPE>
+void launch_cell_phase_t(scg_md * s, MeshGroup const & g, CellPhase ph)
+{
+    MdField const F = field_of(s);
+    MdGeo const G = geo_of(s, g);
+    unsigned const grid = static_cast<unsigned>(ceil_div(g.n, 128));
+    switch (ph)
+    {
+    case CP_PREPARE:
+    {
+        scg_mesh * m = s->mesh;
+        RawMesh M;
+        M.clfcs = m->d_clfcs.p + m->ngstcell * 7;
+        M.fccls = m->d_fccls.p + m->ngstface * 4;
+        M.fcnds = m->d_fcnds.p + m->ngstface * 5;
+        M.ndcrd = m->d_ndcrd.p + m->ngstnode * m->ndim;
+        M.fccnd = m->d_fccnd.p + m->ngstface * m->ndim;
+        M.clcnd = m->d_clcnd.p + m->ngstcell * m->ndim;
+        M.perm = m->d_perm.p;
+        md_prepare_ce_kernel<TYPE><<<grid, 128, 0, stream()>>>(M, G, s->solpt.p, F.S);
+        break;
+    }
+    case CP_SOLN: md_soln_kernel<TYPE><<<grid, 128, 0, stream()>>>(F, G); break;
+    case CP_CFL: md_cfl_kernel<TYPE><<<grid, 128, 0, stream()>>>(F, G); break;
+    case CP_DSOLN: md_dsoln_kernel<TYPE><<<grid, 128, 0, stream()>>>(F, G); break;
+    case CP_SUBSTEP: md_substep_kernel<TYPE><<<grid, 128, 0, stream()>>>(F, G, s->eraw.p); break;
+    }
+    count_launch();
+}
+
+void launch_cell_phase(scg_md * s, CellPhase ph)
+{
+    for (auto const & g : s->mesh->groups)
+    {
+        switch (g.type)
+        {
+        case CT_QUAD: launch_cell_phase_t<CT_QUAD>(s, g, ph); break;
+        case CT_TRI: launch_cell_phase_t<CT_TRI>(s, g, ph); break;
+        case CT_HEX: launch_cell_phase_t<CT_HEX>(s, g, ph); break;
+        case CT_TET: launch_cell_phase_t<CT_TET>(s, g, ph); break;
+        case CT_PRISM: launch_cell_phase_t<CT_PRISM>(s, g, ph); break;
+        case CT_PYRAMID: launch_cell_phase_t<CT_PYRAMID>(s, g, ph); break;
+        default: break;
+        }
+    }
+}
+
+void launch_solt(scg_md * s)
+{
+    MdField const F = field_of(s);
+    unsigned const grid = static_cast<unsigned>(ceil_div(F.T, 256));
+    if (2 == s->ndim) { md_solt_kernel<2><<<grid, 256, 0, stream()>>>(F, 0, F.T); }
+    else { md_solt_kernel<3><<<grid, 256, 0, stream()>>>(F, 0, F.T); }
+    count_launch();
+}
+
+int prepare_ce(scg_md * s)
+{
+    scg_mesh * m = s->mesh;
+    SCG_REQUIRE(m->d_clfcs.p != nullptr, "prepare_ce: the raw mesh tables were released");
+    launch_cell_phase(s, CP_PREPARE);
+    if (m->ngstcell > 0)
+    {
+        md_ghost_solpt_kernel<<<static_cast<unsigned>(ceil_div(m->ngstcell, 256)), 256, 0, stream()>>>(
+            m->d_clcnd.p, m->ndim, m->ngstcell, m->ncell, s->solpt.p, m->stride);
+        count_launch();
+    }
+    SCG_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// Flatten the registered boundaries (registration order, later entries overwrite earlier ones on the
+// same face: SURVEY.md 8a hazard 6) into one entry per ghost cell and upload.
+int rebuild_bc(scg_md * s)
+{
+    if (!s->bc_dirty) { return 0; }
+    scg_mesh * m = s->mesh;
+    int const nd = s->ndim, neq = s->neq;
+    std::vector<int32_t> last(static_cast<size_t>(m->nface), -1);
+    for (size_t r = 0; r < s->regs.size(); ++r)
+    {
+        for (int32_t const f : s->regs[r].faces) { last[f] = static_cast<int32_t>(r); }
+    }
+    std::vector<char> emitted(static_cast<size_t>(m->nface), 0);
+    std::vector<int32_t> icl, jcl, kind, faces, reg_of;
+    for (size_t r = 0; r < s->regs.size(); ++r)
+    {
+        for (int32_t const f : s->regs[r].faces)
+        {
+            if (last[f] != static_cast<int32_t>(r) || emitted[f]) { continue; }
+            emitted[f] = 1;
+            faces.push_back(f);
+            reg_of.push_back(static_cast<int32_t>(r));
+            icl.push_back(m->iperm[m->h_fccls[2 * static_cast<size_t>(f)]]);
+            jcl.push_back(static_cast<int32_t>(m->ncell + (-m->h_fccls[2 * static_cast<size_t>(f) + 1] - 1)));
+            kind.push_back(s->regs[r].kind);
+        }
+    }
+    int64_t const n = static_cast<int64_t>(faces.size());
+    std::vector<double> mat(static_cast<size_t>(n) * nd * nd, 0.0), val(static_cast<size_t>(n) * neq, 0.0);
+    for (int64_t b = 0; b < n; ++b)
+    {
+        double mm[9];
+        normal_matrix_host(nd, &m->h_fcnml[static_cast<size_t>(faces[b]) * nd], mm);
+        for (int c = 0; c < nd * nd; ++c) { mat[c * n + b] = mm[c]; }
+        BcReg const & reg = s->regs[reg_of[b]];
+        if (SCG_BC_INLET == reg.kind)
+        {
+            // euler_bc.cpp:192-210
+            double const * v = reg.value.data();
+            double const rho = v[0];
+            double const p = v[1 + nd];
+            double const ga = v[2 + nd];
+            double vsq = 0.0;
+            for (int d = 0; d < nd; ++d) { vsq += v[1 + d] * v[1 + d]; }
+            val[0 * n + b] = rho;
+            for (int d = 0; d < nd; ++d) { val[(1 + d) * n + b] = rho * v[1 + d]; }
+            val[(neq - 1) * n + b] = p / (ga - 1.0) + 0.5 * rho * vsq;
+        }
+    }
+    s->nbc = static_cast<int32_t>(n);
+    if (n > 0)
+    {
+        SCG_CUDA(s->bc_icl.alloc(n));
+        SCG_CUDA(s->bc_jcl.alloc(n));
+        SCG_CUDA(s->bc_kind.alloc(n));
+        SCG_CUDA(s->bc_mat.alloc(n * nd * nd));
+        SCG_CUDA(s->bc_val.alloc(n * neq));
+        SCG_CUDA(cudaMemcpyAsync(s->bc_icl.p, icl.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, stream()));
+        SCG_CUDA(cudaMemcpyAsync(s->bc_jcl.p, jcl.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, stream()));
+        SCG_CUDA(cudaMemcpyAsync(s->bc_kind.p, kind.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, stream()));
+        SCG_CUDA(cudaMemcpyAsync(s->bc_mat.p, mat.data(), sizeof(double) * mat.size(), cudaMemcpyHostToDevice, stream()));
+        SCG_CUDA(cudaMemcpyAsync(s->bc_val.p, val.data(), sizeof(double) * val.size(), cudaMemcpyHostToDevice, stream()));
+        SCG_CUDA(cudaStreamSynchronize(stream()));
+    }
+    s->bc_dirty = false;
+    return 0;
+}
+
+BcDev bc_of(scg_md * s)
+{
+    BcDev B;
+    B.icl = s->bc_icl.p;
+    B.jcl = s->bc_jcl.p;
+    B.kind = s->bc_kind.p;
+    B.mat = s->bc_mat.p;
+    B.val = s->bc_val.p;
+    B.n = s->nbc;
+    return B;
+}
+
+int launch_bc_soln(scg_md * s, bool use_eraw)
+{
+    if (int rc = rebuild_bc(s)) { return rc; }
+    if (0 == s->nbc) { return 0; }
+    MdField const F = field_of(s);
+    BcDev const B = bc_of(s);
+    unsigned const grid = static_cast<unsigned>(ceil_div(s->nbc, 128));
+    if (2 == s->ndim)
+    {
+        if (use_eraw) { md_bc_soln_kernel<2, true><<<grid, 128, 0, stream()>>>(F, B, s->eraw.p); }
+        else { md_bc_soln_kernel<2, false><<<grid, 128, 0, stream()>>>(F, B, s->eraw.p); }
+    }
+    else
+    {
+        if (use_eraw) { md_bc_soln_kernel<3, true><<<grid, 128, 0, stream()>>>(F, B, s->eraw.p); }
+        else { md_bc_soln_kernel<3, false><<<grid, 128, 0, stream()>>>(F, B, s->eraw.p); }
+    }
+    count_launch();
+    return 0;
+}
+
+int launch_bc_dsoln(scg_md * s)
+{
+    if (int rc = rebuild_bc(s)) { return rc; }
+    if (0 == s->nbc) { return 0; }
+    MdField const F = field_of(s);
+    BcDev const B = bc_of(s);
+    unsigned const grid = static_cast<unsigned>(ceil_div(s->nbc, 128));
+    if (2 == s->ndim) { md_bc_dsoln_kernel<2><<<grid, 128, 0, stream()>>>(F, B); }
+    else { md_bc_dsoln_kernel<3><<<grid, 128, 0, stream()>>>(F, B); }
+    count_launch();
+    return 0;
+}
+
+// march_substep, euler_march.cpp:339-348
+int substep(scg_md * s)
+{
+    s->cur ^= 1; // update(): swap so0c<->so0n, so1c<->so1n (euler.hpp:123-127)
+    launch_solt(s);
+    if (s->fused)
+    {
+        launch_cell_phase(s, CP_SUBSTEP);
+        if (int rc = launch_bc_soln(s, true)) { return rc; }
+    }
+    else
+    {
+        launch_cell_phase(s, CP_SOLN);
+        if (int rc = launch_bc_soln(s, false)) { return rc; }
+        launch_cell_phase(s, CP_CFL);
+        launch_cell_phase(s, CP_DSOLN);
+    }
+    return launch_bc_dsoln(s);
+}
+
+struct ArrayInfo
+{
+    int ncomp;
+    bool geo;
+    bool body_only;
+    double * dev;
+};
+
+int array_info(scg_md * s, int id, ArrayInfo & a)
+{
+    int const nd = s->ndim, neq = s->neq;
+    a.geo = false;
+    a.body_only = false;
+    switch (id)
+    {
+    case SCG_A_CEVOL: a = {CLMFC + 1, true, false, nullptr}; break;
+    case SCG_A_CECND: a = {(CLMFC + 1) * nd, true, false, nullptr}; break;
+    case SCG_A_SFCND: a = {CLMFC * FCMND * nd, true, true, nullptr}; break;
+    case SCG_A_SFNML: a = {CLMFC * FCMND * nd, true, true, nullptr}; break;
+    case SCG_A_SO0C: a = {neq, false, false, s->so0[s->cur].p}; break;
+    case SCG_A_SO0N: a = {neq, false, false, s->so0[1 - s->cur].p}; break;
+    case SCG_A_SO0T: a = {neq, false, false, s->so0t.p}; break;
+    case SCG_A_SO1C: a = {neq * nd, false, false, s->so1[s->cur].p}; break;
+    case SCG_A_SO1N: a = {neq * nd, false, false, s->so1[1 - s->cur].p}; break;
+    case SCG_A_CFLO: a = {1, false, false, s->cflo.p}; break;
+    case SCG_A_CFLC: a = {1, false, false, s->cflc.p}; break;
+    case SCG_A_GAMMA: a = {1, false, false, s->gamma.p}; break;
+    default: return fail("scg_md: unknown array id %d", id);
+    }
+    return 0;
+}
+
+template <bool TO_DEVICE>
+int transfer(scg_md * s, int id, double * host)
+{
+    ArrayInfo a;
+    if (int rc = array_info(s, id, a)) { return rc; }
+    scg_mesh * m = s->mesh;
+    int64_t const nrows = a.body_only ? m->ncell : m->T;
+    int64_t const chunk = STAGE_DOUBLES / a.ncomp;
+    GroupTable const GT = table_of(s);
+    for (int64_t r0 = 0; r0 < nrows; r0 += chunk)
+    {
+        int64_t const nr = (nrows - r0 < chunk) ? nrows - r0 : chunk;
+        int64_t const cnt = nr * a.ncomp;
+        unsigned const grid = static_cast<unsigned>(ceil_div(cnt, 256));
+        if (TO_DEVICE)
+        {
+            SCG_CUDA(cudaMemcpyAsync(s->stage.p, host + r0 * a.ncomp, sizeof(double) * cnt, cudaMemcpyHostToDevice, stream()));
+        }
+        if (a.geo)
+        {
+            md_geo_rows_kernel<TO_DEVICE><<<grid, 256, 0, stream()>>>(id, s->stage.p, r0, nr, a.ncomp, s->ndim, m->ngstcell,
+                                                                      m->d_rowmap.p, GT, s->geo.p, s->solpt.p, m->stride);
+        }
+        else
+        {
+            md_rows_kernel<TO_DEVICE><<<grid, 256, 0, stream()>>>(s->stage.p, r0, nr, a.ncomp, m->d_rowmap.p, a.dev, m->stride);
+        }
+        count_launch();
+        if (!TO_DEVICE)
+        {
+            SCG_CUDA(cudaMemcpyAsync(host + r0 * a.ncomp, s->stage.p, sizeof(double) * cnt, cudaMemcpyDeviceToHost, stream()));
+        }
+        // the staging buffer is reused by the next chunk
+        SCG_CUDA(cudaStreamSynchronize(stream()));
+    }
+    SCG_CUDA(cudaGetLastError());
+    return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+int scg_md_create(scg_md ** out, scg_mesh * mesh, double time_increment)
+{
+    if (int rc = ensure_init()) { return rc; }
+    SCG_REQUIRE(out && mesh, "scg_md_create: null argument");
+    auto * s = new scg_md;
+    s->mesh = mesh;
+    s->ndim = mesh->ndim;
+    s->neq = mesh->ndim + 2;
+    s->dt = time_increment;
+    int64_t const S = mesh->stride;
+    int const nd = s->ndim, neq = s->neq;
+    bool ok = true;
+    auto z = [&](DevBuf<double> & b, int64_t n) { ok = ok && cudaSuccess == b.alloc_zero(n); };
+    for (int q = 0; q < 2; ++q)
+    {
+        z(s->so0[q], S * neq);
+        z(s->so1[q], S * neq * nd);
+    }
+    z(s->so0t, S * neq);
+    z(s->gamma, S);
+    z(s->cflo, S);
+    z(s->cflc, S);
+    z(s->solpt, S * nd);
+    z(s->geo, mesh->geo_total);
+    z(s->eraw, mesh->ngstcell > 0 ? mesh->ngstcell : 1);
+    ok = ok && cudaSuccess == s->stage.alloc(STAGE_DOUBLES) && cudaSuccess == s->red.alloc(3 * 1024);
+    if (!ok)
+    {
+        cudaError_t const e = cudaGetLastError();
+        delete s;
+        return fail("scg_md_create: device allocation failed: %s", cudaGetErrorString(e));
+    }
+    mesh->refcount += 1;
+    if (int rc = prepare_ce(s))
+    {
+        mesh->refcount -= 1;
+        delete s;
+        return rc;
+    }
+    if (cudaSuccess != cudaStreamSynchronize(stream()))
+    {
+        mesh->refcount -= 1;
+        delete s;
+        return fail("scg_md_create: prepare_ce failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    *out = s;
+    return 0;
+}
+
+int scg_md_destroy(scg_md * s)
+{
+    if (s)
+    {
+        cudaStreamSynchronize(stream());
+        s->mesh->refcount -= 1;
+        delete s;
+    }
+    return 0;
+}
+
+int scg_md_set_params(scg_md * s, double sigma0, double taumin, double tauscale)
+{
+    SCG_REQUIRE(s, "scg_md_set_params: null solver");
+    s->sigma0 = sigma0;
+    s->taumin = taumin;
+    s->tauscale = tauscale;
+    return 0;
+}
+
+int scg_md_set_time_increment(scg_md * s, double time_increment)
+{
+    SCG_REQUIRE(s, "scg_md_set_time_increment: null solver");
+    s->dt = time_increment;
+    return 0;
+}
+
+int scg_md_set_fused(scg_md * s, int fused)
+{
+    SCG_REQUIRE(s, "scg_md_set_fused: null solver");
+    s->fused = fused != 0;
+    return 0;
+}
+
+int scg_md_init_solution(scg_md * s, double gamma, double rho, const double * v, double p)
+{
+    SCG_REQUIRE(s && v, "scg_md_init_solution: null argument");
+    // same guards and messages as euler_solution.cpp:63-78
+    SCG_REQUIRE(gamma > 1.0, "EulerCore::init_solution: gamma %g must be > 1", gamma);
+    SCG_REQUIRE(rho > 0.0, "EulerCore::init_solution: rho %g must be > 0", rho);
+    SCG_REQUIRE(p >= 0.0, "EulerCore::init_solution: pressure %g must be >= 0", p);
+    double vsq = 0.0;
+    for (int d = 0; d < s->ndim; ++d) { vsq += v[d] * v[d]; }
+    double const energy = p / (gamma - 1.0) + 0.5 * rho * vsq;
+    double u[5] = {0, 0, 0, 0, 0};
+    u[0] = rho;
+    for (int d = 0; d < s->ndim; ++d) { u[1 + d] = rho * v[d]; }
+    u[s->neq - 1] = energy;
+    scg_mesh * m = s->mesh;
+    md_fill_kernel<<<static_cast<unsigned>(ceil_div(m->stride, 256)), 256, 0, stream()>>>(s->gamma.p, m->stride, gamma);
+    md_init_kernel<<<static_cast<unsigned>(ceil_div(m->ncell, 256)), 256, 0, stream()>>>(s->so0[1 - s->cur].p, m->stride, m->ncell,
+                                                                                      s->neq, u[0], u[1], u[2], u[3], u[4]);
+    count_launch(2);
+    SCG_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int scg_md_add_bc(scg_md * s, int kind, const int32_t * faces, int64_t nface, const double * value, int nvalue)
+{
+    SCG_REQUIRE(s, "scg_md_add_bc: null solver");
+    SCG_REQUIRE(kind >= SCG_BC_NONREFL && kind <= SCG_BC_INLET, "scg_md_add_bc: unknown boundary kind %d", kind);
+    scg_mesh * m = s->mesh;
+    // same validation and messages as EulerCore::add_bc, euler_bc.cpp:324-389
+    for (int64_t q = 0; q < nface; ++q)
+    {
+        int32_t const ifc = faces[q];
+        SCG_REQUIRE(ifc >= 0 && ifc < m->nface, "EulerCore::add_bc: face %d out of range [0, %lld)", ifc,
+                    static_cast<long long>(m->nface));
+        SCG_REQUIRE(m->h_fccls[2 * static_cast<size_t>(ifc) + 1] < 0, "EulerCore::add_bc: face %d is not a boundary face", ifc);
+    }
+    if (SCG_BC_INLET == kind)
+    {
+        SCG_REQUIRE(nvalue == s->ndim + 3, "EulerCore::add_bc: inlet value size %d must equal ndim+3 = %d", nvalue, s->ndim + 3);
+        double const rho = value[0];
+        double const p = value[1 + s->ndim];
+        double const gamma = value[2 + s->ndim];
+        SCG_REQUIRE(gamma > 1.0, "EulerCore::add_bc: inlet gamma %g must be > 1", gamma);
+        SCG_REQUIRE(rho > 0.0, "EulerCore::add_bc: inlet rho %g must be > 0", rho);
+        SCG_REQUIRE(p >= 0.0, "EulerCore::add_bc: inlet pressure %g must be >= 0", p);
+    }
+    BcReg reg;
+    reg.kind = kind;
+    reg.faces.assign(faces, faces + nface);
+    if (value && nvalue > 0) { reg.value.assign(value, value + nvalue); }
+    s->regs.push_back(std::move(reg));
+    s->bc_dirty = true;
+    return 0;
+}
+
+int scg_md_clear_bc(scg_md * s)
+{
+    SCG_REQUIRE(s, "scg_md_clear_bc: null solver");
+    s->regs.clear();
+    s->bc_dirty = true;
+    return 0;
+}
+
+int scg_md_upload(scg_md * s, int array_id, const double * host)
+{
+    SCG_REQUIRE(s && host, "scg_md_upload: null argument");
+    return transfer<true>(s, array_id, const_cast<double *>(host));
+}
+
+int scg_md_download(scg_md * s, int array_id, double * host)
+{
+    SCG_REQUIRE(s && host, "scg_md_download: null argument");
+    return transfer<false>(s, array_id, host);
+}
+
+int scg_md_phase(scg_md * s, int phase)
+{
+    SCG_REQUIRE(s, "scg_md_phase: null solver");
+    switch (phase)
+    {
+    case SCG_MD_UPDATE: s->cur ^= 1; break;
+    case SCG_MD_SOLT: launch_solt(s); break;
+    case SCG_MD_SOLN: launch_cell_phase(s, CP_SOLN); break;
+    case SCG_MD_BC_SOLN:
+        if (int rc = launch_bc_soln(s, false)) { return rc; }
+        break;
+    case SCG_MD_CFL: launch_cell_phase(s, CP_CFL); break;
+    case SCG_MD_DSOLN: launch_cell_phase(s, CP_DSOLN); break;
+    case SCG_MD_BC_DSOLN:
+        if (int rc = launch_bc_dsoln(s)) { return rc; }
+        break;
+    case SCG_MD_PREPARE_CE:
+        if (int rc = prepare_ce(s)) { return rc; }
+        break;
+    case SCG_MD_SUBSTEP:
+        if (int rc = substep(s)) { return rc; }
+        break;
+    default: return fail("scg_md_phase: unknown phase %d", phase);
+    }
+    SCG_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int scg_md_march(scg_md * s, int64_t steps)
+{
+    SCG_REQUIRE(s, "scg_md_march: null solver");
+    SCG_REQUIRE(steps >= 0, "scg_md_march: negative step count");
+    for (int64_t it = 0; it < steps; ++it)
+    {
+        for (int sub = 0; sub < 2; ++sub) // SUBSTEP_RUN, euler.hpp:165
+        {
+            if (int rc = substep(s)) { return rc; }
+        }
+    }
+    SCG_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int scg_md_reduce(scg_md * s, const double * clvol_host_or_null, double * cfl_min, double * cfl_max, double * mass)
+{
+    SCG_REQUIRE(s, "scg_md_reduce: null solver");
+    scg_mesh * m = s->mesh;
+    if (clvol_host_or_null)
+    {
+        // clvol arrives in the host layout (ghost rows first); keep a device copy in device order
+        if (!s->clvol.p) { SCG_CUDA(s->clvol.alloc_zero(m->stride)); }
+        int64_t const chunk = STAGE_DOUBLES;
+        for (int64_t r0 = 0; r0 < m->T; r0 += chunk)
+        {
+            int64_t const nr = (m->T - r0 < chunk) ? m->T - r0 : chunk;
+            SCG_CUDA(cudaMemcpyAsync(s->stage.p, clvol_host_or_null + r0, sizeof(double) * nr, cudaMemcpyHostToDevice, stream()));
+            md_rows_kernel<true><<<static_cast<unsigned>(ceil_div(nr, 256)), 256, 0, stream()>>>(s->stage.p, r0, nr, 1, m->d_rowmap.p,
+                                                                                              s->clvol.p, m->stride);
+            count_launch();
+            SCG_CUDA(cudaStreamSynchronize(stream()));
+        }
+        s->have_clvol = true;
+    }
+    int const nblk = 592; // 4 CTAs per SM
+    md_reduce_kernel<<<nblk, 256, 0, stream()>>>(s->cflo.p, s->so0[1 - s->cur].p, s->have_clvol ? s->clvol.p : nullptr, m->ncell,
+                                                 s->red.p);
+    count_launch();
+    std::vector<double> h(3 * nblk);
+    SCG_CUDA(cudaMemcpyAsync(h.data(), s->red.p, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, stream()));
+    SCG_CUDA(cudaStreamSynchronize(stream()));
+    double mn = DBL_MAX, mx = -DBL_MAX, sm = 0.0;
+    for (int b = 0; b < nblk; ++b)
+    {
+        mn = h[3 * b] < mn ? h[3 * b] : mn;
+        mx = h[3 * b + 1] > mx ? h[3 * b + 1] : mx;
+        sm += h[3 * b + 2];
+    }
+    if (cfl_min) { *cfl_min = mn; }
+    if (cfl_max) { *cfl_max = mx; }
+    if (mass) { *mass = sm; }
+    return 0;
+}
+
+int scg_md_algorithmic_bytes(scg_md * s, int64_t * bytes_per_substep)
+{
+    SCG_REQUIRE(s && bytes_per_substep, "scg_md_algorithmic_bytes: null argument");
+    int64_t b = 0;
+    for (auto const & g : s->mesh->groups) { b += int64_t(ct_balg(g.type)) * g.n; }
+    *bytes_per_substep = b;
+    return 0;
+}
+
+int scg_md_normal_matrix(scg_md * s, int32_t ifc, double * out)
+{
+    SCG_REQUIRE(s && out, "scg_md_normal_matrix: null argument");
+    SCG_REQUIRE(ifc >= 0 && ifc < s->mesh->nface, "get_normal_matrix: face %d out of range", ifc);
+    normal_matrix_host(s->ndim, &s->mesh->h_fcnml[static_cast<size_t>(ifc) * s->ndim], out);
+    return 0;
+}
+
+int scg_md_halo_set(scg_md * s, const int32_t * send_cells, int64_t nsend, const int32_t * recv_ghosts, int64_t nrecv)
+{
+    SCG_REQUIRE(s, "scg_md_halo_set: null solver");
+    scg_mesh * m = s->mesh;
+    std::vector<int32_t> snd(static_cast<size_t>(nsend)), rcv(static_cast<size_t>(nrecv));
+    for (int64_t q = 0; q < nsend; ++q)
+    {
+        SCG_REQUIRE(send_cells[q] >= 0 && send_cells[q] < m->ncell, "scg_md_halo_set: send cell %d out of range", send_cells[q]);
+        snd[q] = m->iperm[send_cells[q]];
+    }
+    for (int64_t q = 0; q < nrecv; ++q)
+    {
+        SCG_REQUIRE(recv_ghosts[q] >= 0 && recv_ghosts[q] < m->ngstcell, "scg_md_halo_set: ghost %d out of range", recv_ghosts[q]);
+        rcv[q] = static_cast<int32_t>(m->ncell + recv_ghosts[q]);
+    }
+    s->nsend = nsend;
+    s->nrecv = nrecv;
+    int64_t const width = s->neq * (1 + s->ndim);
+    SCG_CUDA(s->halo_send.alloc(nsend > 0 ? nsend : 1));
+    SCG_CUDA(s->halo_recv.alloc(nrecv > 0 ? nrecv : 1));
+    SCG_CUDA(s->halo_buf.alloc((nsend > 0 ? nsend : 1) * width));
+    if (nsend) { SCG_CUDA(cudaMemcpyAsync(s->halo_send.p, snd.data(), sizeof(int32_t) * nsend, cudaMemcpyHostToDevice, stream())); }
+    if (nrecv) { SCG_CUDA(cudaMemcpyAsync(s->halo_recv.p, rcv.data(), sizeof(int32_t) * nrecv, cudaMemcpyHostToDevice, stream())); }
+    SCG_CUDA(cudaStreamSynchronize(stream()));
+    return 0;
+}
+
+int scg_md_halo_pack(scg_md * s, int what, double ** dev_buffer, int64_t * ndouble)
+{
+    SCG_REQUIRE(s && dev_buffer && ndouble, "scg_md_halo_pack: null argument");
+    int64_t const width = (0 == what) ? s->neq * (1 + s->ndim) : s->ndim + 1;
+    if (s->nsend > 0)
+    {
+        md_halo_pack_kernel<<<static_cast<unsigned>(ceil_div(s->nsend, 128)), 128, 0, stream()>>>(
+            s->so0[1 - s->cur].p, s->so1[1 - s->cur].p, s->solpt.p, s->gamma.p, what, s->halo_send.p, s->nsend, s->neq, s->ndim,
+            s->mesh->stride, s->halo_buf.p);
+        count_launch();
+    }
+    *dev_buffer = s->halo_buf.p;
+    *ndouble = s->nsend * width;
+    SCG_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int scg_md_halo_unpack(scg_md * s, int what, const double * dev_buffer)
+{
+    SCG_REQUIRE(s && dev_buffer, "scg_md_halo_unpack: null argument");
+    if (s->nrecv > 0)
+    {
+        md_halo_unpack_kernel<<<static_cast<unsigned>(ceil_div(s->nrecv, 128)), 128, 0, stream()>>>(
+            s->so0[1 - s->cur].p, s->so1[1 - s->cur].p, s->solpt.p, s->gamma.p, what, s->halo_recv.p, s->nrecv, s->neq, s->ndim,
+            s->mesh->stride, dev_buffer);
+        count_launch();
+    }
+    SCG_CUDA(cudaGetLastError());
+    return 0;
+}
+
+} // extern "C"

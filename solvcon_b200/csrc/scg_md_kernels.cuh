@@ -1,0 +1,608 @@
+// scg_md_kernels.cuh -- device code of the multidim Euler CESE march.
+//
+// Device twin of EulerCore's phases (cpp/solvcon/multidim/euler_{ce,march,solution,gradient,bc}.cpp,
+// GradientElement.cpp).  Every kernel is a pure gather: one thread owns one output row (a body cell,
+// a stored row, or a boundary face) and nothing is accumulated across threads, so results do not
+// depend on the launch shape or the cell ordering.  Arithmetic keeps the reference's expression
+// order operation by operation; with -fmad=false (the strict build) the results are bit-equal to the
+// x86-64 reference.  Work that is provably bit-neutral is removed:
+//   * structural zeros / ones of the flux Jacobian are skipped (adding +-0 to a partial sum that
+//     started from +0 never changes it; 1*x == x),
+//   * adj(D) and det(D) of a gradient element are computed once, not once per equation
+//     (euler_gradient.cpp:74-77 recomputes them),
+//   * the per-face Taylor difference u_j + hdt*ut_j - u_i + jdis.grad(u_j) is evaluated once per face,
+//     not once per gradient element that uses the face.
+#pragma once
+
+#include "scg_md.cuh"
+
+#include <cfloat>
+
+namespace scg
+{
+
+constexpr double MD_TINY = 1.e-60;         // euler_march.cpp:30,89; euler_solution.cpp:108
+constexpr double MD_ALMOST_ZERO = 1.e-200; // euler_gradient.cpp:28
+
+struct MdField // by value to every kernel
+{
+    double * so0c;
+    double * so0n;
+    double * so0t;
+    double * so1c;
+    double * so1n;
+    double * gamma;
+    double * cflo;
+    double * cflc;
+    double * solpt; // [ndim][stride] solution point: cecnd[icl,0] for body cells, clcnd for ghosts
+    int64_t S;      // component stride
+    int32_t ncell;
+    int32_t T;
+    double dt, sigma0, taumin, tauscale;
+};
+
+struct MdGeo // one cell-type group
+{
+    int32_t const * nbr; // [nfc][n]
+    double * cevol;      // [nfc+1][n]
+    double * cecnd;      // [nfc*ndim][n]  (faces 1..nfc)
+    double * sfcnd;      // [nsf*ndim][n]
+    double * sfnml;      // [nsf*ndim][n]
+    int32_t beg;
+    int32_t n;
+};
+
+// ------------------------------------------------------------------------------------------------
+// flux function and Jacobian, detail::EulerJacobian<2>/<3>::update (euler_march.cpp:35-81, 94-157)
+// ------------------------------------------------------------------------------------------------
+template <int ND>
+struct Jaco
+{
+    double fcn[ND + 2][ND];
+    double jac[ND + 2][ND + 2][ND];
+};
+
+// structural kind of jac[i][j][d]: 0 = zero, 1 = one, 2 = general value
+template <int ND>
+__host__ __device__ constexpr int jkind(int i, int j, int d)
+{
+    if (0 == i) { return (j == d + 1) ? 1 : 0; }
+    if (ND + 1 == i) { return 2; }
+    if (0 == j) { return 2; }
+    if (ND + 1 == j) { return (d == i - 1) ? 2 : 0; }
+    return (i == j || d == i - 1 || d == j - 1) ? 2 : 0;
+}
+
+template <int ND>
+__device__ __forceinline__ void jaco_update(Jaco<ND> & J, double ga, double const (&u)[ND + 2]);
+
+template <>
+__device__ __forceinline__ void jaco_update<2>(Jaco<2> & J, double ga, double const (&u)[4])
+{
+    double const ga1 = ga - 1;
+    double const ga3 = ga - 3;
+    double const ga1h = ga1 / 2;
+    double const u1 = u[0] + MD_TINY;
+    double const u2 = u[1];
+    double const u3 = u[2];
+    double const u4 = u[3];
+    double const rho2 = u1 * u1;
+    double const v1 = u2 / u1;
+    double const v1o2 = v1 * v1;
+    double const v2 = u3 / u1;
+    double const v2o2 = v2 * v2;
+    double const ke2 = (u2 * u2 + u3 * u3) / u1;
+    double const g1ke2 = ga1 * ke2;
+    double const vs = ke2 / u1;
+    double const gretot = ga * u4;
+    double const getot = gretot / u1;
+    double const pr = ga1 * u4 - ga1h * ke2;
+
+    J.fcn[0][0] = u2;              J.fcn[0][1] = u3;
+    J.fcn[1][0] = pr + u2 * v1;    J.fcn[1][1] = u2 * v2;
+    J.fcn[2][0] = u3 * v1;         J.fcn[2][1] = pr + u3 * v2;
+    J.fcn[3][0] = (pr + u4) * v1;  J.fcn[3][1] = (pr + u4) * v2;
+
+    J.jac[1][0][0] = -v1o2 + ga1h * vs;  J.jac[1][0][1] = -v1 * v2;
+    J.jac[1][1][0] = -ga3 * v1;          J.jac[1][1][1] = v2;
+    J.jac[1][2][0] = -ga1 * v2;          J.jac[1][2][1] = v1;
+    J.jac[1][3][0] = ga1;
+
+    J.jac[2][0][0] = -v2 * v1;           J.jac[2][0][1] = -v2o2 + ga1h * vs;
+    J.jac[2][1][0] = v2;                 J.jac[2][1][1] = -ga1 * v1;
+    J.jac[2][2][0] = v1;                 J.jac[2][2][1] = -ga3 * v2;
+    J.jac[2][3][1] = ga1;
+
+    J.jac[3][0][0] = (-gretot + g1ke2) * u2 / rho2;
+    J.jac[3][0][1] = (-gretot + g1ke2) * u3 / rho2;
+    J.jac[3][1][0] = getot - ga1h * (vs + 2 * v1o2);
+    J.jac[3][1][1] = -ga1 * v1 * v2;
+    J.jac[3][2][0] = -ga1 * v2 * v1;
+    J.jac[3][2][1] = getot - ga1h * (vs + 2 * v2o2);
+    J.jac[3][3][0] = ga * v1;
+    J.jac[3][3][1] = ga * v2;
+}
+
+template <>
+__device__ __forceinline__ void jaco_update<3>(Jaco<3> & J, double ga, double const (&u)[5])
+{
+    double const ga1 = ga - 1;
+    double const ga3 = ga - 3;
+    double const ga1h = ga1 / 2;
+    double const u1 = u[0] + MD_TINY;
+    double const u2 = u[1];
+    double const u3 = u[2];
+    double const u4 = u[3];
+    double const u5 = u[4];
+    double const rho2 = u1 * u1;
+    double const v1 = u2 / u1;
+    double const v1o2 = v1 * v1;
+    double const v2 = u3 / u1;
+    double const v2o2 = v2 * v2;
+    double const v3 = u4 / u1;
+    double const v3o2 = v3 * v3;
+    double const ke2 = (u2 * u2 + u3 * u3 + u4 * u4) / u1;
+    double const g1ke2 = ga1 * ke2;
+    double const vs = ke2 / u1;
+    double const gretot = ga * u5;
+    double const getot = gretot / u1;
+    double const pr = ga1 * u5 - ga1h * ke2;
+
+    J.fcn[0][0] = u2;             J.fcn[0][1] = u3;             J.fcn[0][2] = u4;
+    J.fcn[1][0] = pr + u2 * v1;   J.fcn[1][1] = u2 * v2;        J.fcn[1][2] = u2 * v3;
+    J.fcn[2][0] = u3 * v1;        J.fcn[2][1] = pr + u3 * v2;   J.fcn[2][2] = u3 * v3;
+    J.fcn[3][0] = u4 * v1;        J.fcn[3][1] = u4 * v2;        J.fcn[3][2] = pr + u4 * v3;
+    J.fcn[4][0] = (pr + u5) * v1; J.fcn[4][1] = (pr + u5) * v2; J.fcn[4][2] = (pr + u5) * v3;
+
+    J.jac[1][0][0] = -v1o2 + ga1h * vs; J.jac[1][0][1] = -v1 * v2; J.jac[1][0][2] = -v1 * v3;
+    J.jac[1][1][0] = -ga3 * v1;         J.jac[1][1][1] = v2;       J.jac[1][1][2] = v3;
+    J.jac[1][2][0] = -ga1 * v2;         J.jac[1][2][1] = v1;
+    J.jac[1][3][0] = -ga1 * v3;                                    J.jac[1][3][2] = v1;
+    J.jac[1][4][0] = ga1;
+
+    J.jac[2][0][0] = -v2 * v1; J.jac[2][0][1] = -v2o2 + ga1h * vs; J.jac[2][0][2] = -v2 * v3;
+    J.jac[2][1][0] = v2;       J.jac[2][1][1] = -ga1 * v1;
+    J.jac[2][2][0] = v1;       J.jac[2][2][1] = -ga3 * v2;         J.jac[2][2][2] = v3;
+                               J.jac[2][3][1] = -ga1 * v3;         J.jac[2][3][2] = v2;
+                               J.jac[2][4][1] = ga1;
+
+    J.jac[3][0][0] = -v3 * v1; J.jac[3][0][1] = -v3 * v2; J.jac[3][0][2] = -v3o2 + ga1h * vs;
+    J.jac[3][1][0] = v3;                                  J.jac[3][1][2] = -ga1 * v1;
+                               J.jac[3][2][1] = v3;       J.jac[3][2][2] = -ga1 * v2;
+    J.jac[3][3][0] = v1;       J.jac[3][3][1] = v2;       J.jac[3][3][2] = -ga3 * v3;
+                                                          J.jac[3][4][2] = ga1;
+
+    J.jac[4][0][0] = (-gretot + g1ke2) * u2 / rho2;
+    J.jac[4][0][1] = (-gretot + g1ke2) * u3 / rho2;
+    J.jac[4][0][2] = (-gretot + g1ke2) * u4 / rho2;
+    J.jac[4][1][0] = getot - ga1h * (vs + 2 * v1o2); J.jac[4][1][1] = -ga1 * v1 * v2; J.jac[4][1][2] = -ga1 * v1 * v3;
+    J.jac[4][2][0] = -ga1 * v2 * v1; J.jac[4][2][1] = getot - ga1h * (vs + 2 * v2o2); J.jac[4][2][2] = -ga1 * v2 * v3;
+    J.jac[4][3][0] = -ga1 * v3 * v1; J.jac[4][3][1] = -ga1 * v3 * v2; J.jac[4][3][2] = getot - ga1h * (vs + 2 * v3o2);
+    J.jac[4][4][0] = ga * v1; J.jac[4][4][1] = ga * v2; J.jac[4][4][2] = ga * v3;
+}
+
+// acc += jac[i][j][d] * x with the structural zeros skipped and the ones not multiplied
+#define SCG_JTERM(ND, J, i, j, d, x, acc)                   \
+    do                                                      \
+    {                                                       \
+        if (2 == jkind<ND>(i, j, d)) { acc += J.jac[i][j][d] * (x); } \
+        else if (1 == jkind<ND>(i, j, d)) { acc += (x); }   \
+    } while (0)
+
+// calc_solt_impl body, euler_march.cpp:175-189: so0t[i] = -sum_d sum_j jac[i][j][d] * g[j][d]
+template <int ND>
+__device__ __forceinline__ void solt_row(Jaco<ND> const & J, double const (&g)[ND + 2][ND], double (&t)[ND + 2])
+{
+#pragma unroll
+    for (int ieq = 0; ieq < ND + 2; ++ieq)
+    {
+        double val = 0.0;
+#pragma unroll
+        for (int idm = 0; idm < ND; ++idm)
+        {
+#pragma unroll
+            for (int jeq = 0; jeq < ND + 2; ++jeq) { SCG_JTERM(ND, J, ieq, jeq, idm, g[jeq][idm], val); }
+        }
+        t[ieq] = -val;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GradientElementTypeGroup tables, GradientElement.cpp:16-79 (0-based local faces here)
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int fge_face(int type, int isub, int ivx)
+{
+    constexpr int quad[4][3] = {{0, 1, -1}, {1, 2, -1}, {2, 3, -1}, {3, 0, -1}};
+    constexpr int tri[3][3] = {{0, 1, -1}, {1, 2, -1}, {2, 0, -1}};
+    constexpr int hex[8][3] = {{1, 2, 4}, {5, 2, 1}, {3, 2, 5}, {4, 2, 3}, {4, 0, 1}, {1, 0, 5}, {5, 0, 3}, {3, 0, 4}};
+    constexpr int tet[4][3] = {{2, 0, 1}, {1, 0, 3}, {3, 0, 2}, {1, 3, 2}};
+    constexpr int prism[6][3] = {{4, 1, 3}, {2, 1, 4}, {3, 1, 2}, {3, 0, 4}, {4, 0, 2}, {2, 0, 3}};
+    constexpr int pyramid[6][3] = {{0, 4, 1}, {1, 4, 2}, {2, 4, 3}, {3, 4, 0}, {0, 2, 3}, {2, 0, 1}};
+    return type == CT_QUAD    ? quad[isub][ivx]
+         : type == CT_TRI     ? tri[isub][ivx]
+         : type == CT_HEX     ? hex[isub][ivx]
+         : type == CT_TET     ? tet[isub][ivx]
+         : type == CT_PRISM   ? prism[isub][ivx]
+                              : pyramid[isub][ivx];
+}
+
+// GradientElement::determinant / adjugate, GradientElement.cpp:215-249 (rows of `a` are vertices)
+template <int ND>
+__device__ __forceinline__ double det_n(double const (&a)[ND][ND])
+{
+    if (2 == ND) { return a[0][0] * a[1][1] - a[0][1] * a[1][0]; }
+    return a[0][0] * (a[1][1] * a[ND - 1][ND - 1] - a[1][ND - 1] * a[ND - 1][1])
+         - a[0][1] * (a[1][0] * a[ND - 1][ND - 1] - a[1][ND - 1] * a[ND - 1][0])
+         + a[0][ND - 1] * (a[1][0] * a[ND - 1][1] - a[1][1] * a[ND - 1][0]);
+}
+
+template <int ND>
+__device__ __forceinline__ void adj_n(double const (&a)[ND][ND], double (&r)[ND][ND])
+{
+    if (2 == ND)
+    {
+        r[0][0] = a[1][1];
+        r[0][1] = -a[0][1];
+        r[1][0] = -a[1][0];
+        r[1][1] = a[0][0];
+        return;
+    }
+    constexpr int Z = ND - 1; // == 2; written so the 2D instantiation stays in bounds
+    r[0][0] = a[1][1] * a[Z][Z] - a[1][Z] * a[Z][1];
+    r[0][1] = a[0][Z] * a[Z][1] - a[0][1] * a[Z][Z];
+    r[0][Z] = a[0][1] * a[1][Z] - a[0][Z] * a[1][1];
+    r[1][0] = a[1][Z] * a[Z][0] - a[1][0] * a[Z][Z];
+    r[1][1] = a[0][0] * a[Z][Z] - a[0][Z] * a[Z][0];
+    r[1][Z] = a[0][Z] * a[1][0] - a[0][0] * a[1][Z];
+    r[Z][0] = a[1][0] * a[Z][1] - a[1][1] * a[Z][0];
+    r[Z][1] = a[0][1] * a[Z][0] - a[0][0] * a[Z][1];
+    r[Z][Z] = a[0][0] * a[1][1] - a[0][1] * a[1][0];
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-cell phases (device functions so the per-phase kernels and the fused substep share them)
+// ------------------------------------------------------------------------------------------------
+
+// calc_soln_impl for one cell, euler_march.cpp:197-303.  Returns so0n in `out`.
+template <int TYPE>
+__device__ __forceinline__ void cell_soln(MdField const & F, MdGeo const & G, int32_t i, double (&out)[ct_ndim(TYPE) + 2])
+{
+    constexpr int ND = ct_ndim(TYPE);
+    constexpr int NEQ = ND + 2;
+    constexpr int NFC = ct_nfc(TYPE);
+    int64_t const n = G.n;
+    int64_t const S = F.S;
+    double const qdt = F.dt * 0.25;
+    double const hdt = F.dt * 0.5;
+    double acc[NEQ];
+#pragma unroll
+    for (int e = 0; e < NEQ; ++e) { acc[e] = 0.0; }
+
+#pragma unroll 1
+    for (int f = 0; f < NFC; ++f)
+    {
+        int64_t const j = G.nbr[f * n + i];
+        double jc[ND], bc[ND];
+#pragma unroll
+        for (int d = 0; d < ND; ++d)
+        {
+            jc[d] = F.solpt[d * S + j];
+            bc[d] = G.cecnd[(f * ND + d) * n + i];
+        }
+        double const bvol = G.cevol[(f + 1) * n + i];
+        double ju[NEQ], jt[NEQ], jg[NEQ][ND];
+#pragma unroll
+        for (int e = 0; e < NEQ; ++e)
+        {
+            ju[e] = F.so0c[e * S + j];
+            jt[e] = F.so0t[e * S + j];
+#pragma unroll
+            for (int d = 0; d < ND; ++d) { jg[e][d] = F.so1c[(e * ND + d) * S + j]; }
+        }
+        double const ga = F.gamma[j];
+        // spatial part over the basic CE (euler_march.cpp:236-249)
+#pragma unroll
+        for (int e = 0; e < NEQ; ++e)
+        {
+            double fusp = ju[e];
+#pragma unroll
+            for (int d = 0; d < ND; ++d) { fusp += (bc[d] - jc[d]) * jg[e][d]; }
+            acc[e] += fusp * bvol;
+        }
+        Jaco<ND> J;
+        jaco_update<ND>(J, ga, ju);
+        // temporal part over the sub-faces (euler_march.cpp:262-294)
+        int const nsf = ct_fnnd(TYPE, f);
+        int const q0 = ct_sfoff(TYPE, f);
+#pragma unroll 1
+        for (int s = 0; s < nsf; ++s)
+        {
+            int64_t const q = q0 + s;
+            double sc[ND], sn[ND];
+#pragma unroll
+            for (int d = 0; d < ND; ++d)
+            {
+                sc[d] = G.sfcnd[(q * ND + d) * n + i];
+                sn[d] = G.sfnml[(q * ND + d) * n + i];
+            }
+            double usfc[NEQ];
+#pragma unroll
+            for (int e = 0; e < NEQ; ++e)
+            {
+                usfc[e] = qdt * jt[e];
+#pragma unroll
+                for (int d = 0; d < ND; ++d) { usfc[e] += (sc[d] - jc[d]) * jg[e][d]; }
+            }
+#pragma unroll
+            for (int e = 0; e < NEQ; ++e)
+            {
+                double dot = 0.0;
+#pragma unroll
+                for (int d2 = 0; d2 < ND; ++d2)
+                {
+                    double dfcn = J.fcn[e][d2];
+#pragma unroll
+                    for (int je = 0; je < NEQ; ++je) { SCG_JTERM(ND, J, e, je, d2, usfc[je], dfcn); }
+                    dot += dfcn * sn[d2];
+                }
+                acc[e] -= hdt * dot;
+            }
+        }
+    }
+    double const cvol = G.cevol[i];
+#pragma unroll
+    for (int e = 0; e < NEQ; ++e) { out[e] = acc[e] / cvol; }
+}
+
+// EulerCore::calc_cfl for one cell, euler_solution.cpp:106-160.  `u` is so0n of the cell; its energy
+// is rewritten in place; returns cflo / cflc.
+template <int TYPE>
+__device__ __forceinline__ void cell_cfl(MdField const & F, MdGeo const & G, int32_t i, double (&u)[ct_ndim(TYPE) + 2],
+                                         double & cflo, double & cflc)
+{
+    constexpr int ND = ct_ndim(TYPE);
+    constexpr int NEQ = ND + 2;
+    constexpr int NFC = ct_nfc(TYPE);
+    int64_t const n = G.n;
+    int64_t const k = G.beg + i;
+    double const hdt = F.dt / 2.0;
+    double cc[ND];
+#pragma unroll
+    for (int d = 0; d < ND; ++d) { cc[d] = F.solpt[d * F.S + k]; }
+    double dist = DBL_MAX;
+#pragma unroll
+    for (int f = 0; f < NFC; ++f)
+    {
+        double d2 = 0.0;
+#pragma unroll
+        for (int d = 0; d < ND; ++d)
+        {
+            double const diff = G.cecnd[(f * ND + d) * n + i] - cc[d];
+            d2 += diff * diff;
+        }
+        double const r = sqrt(d2);
+        dist = (r < dist) ? r : dist; // std::min(dist, r)
+    }
+    double const ga = F.gamma[k];
+    double const ga1 = ga - 1.0;
+    double const density = u[0];
+    double momsq = 0.0;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) { momsq += u[1 + d] * u[1 + d]; }
+    double const ke = momsq / (2.0 * density);
+    double const energy = u[NEQ - 1];
+    double const pr = ga1 * (energy - ke);
+    double const pr_adj = (pr + fabs(pr)) / 2.0;
+    double const wspd = sqrt(ga * pr_adj / density) + sqrt(momsq) / density;
+    cflo = hdt * wspd / dist;
+    cflc = (cflo - 1.0) * pr_adj / (pr_adj + MD_TINY) + 1.0;
+    u[NEQ - 1] = pr_adj / ga1 + ke + MD_TINY;
+}
+
+// EulerCore::calc_dsoln for one cell, euler_gradient.cpp:23-130, with the GradientElement constructor
+// (GradientElement.cpp:137-213) and calc_gge_centroid (:81-133) expanded in place.  `un` is the cell's
+// own so0n (energy already fixed by calc_cfl), `acfl_in` is cflc of the cell.
+template <int TYPE>
+__device__ __forceinline__ void cell_dsoln(MdField const & F, MdGeo const & G, int32_t i, double const (&un)[ct_ndim(TYPE) + 2],
+                                           double cflc, double (&out)[ct_ndim(TYPE) + 2][ct_ndim(TYPE)])
+{
+    constexpr int ND = ct_ndim(TYPE);
+    constexpr int NEQ = ND + 2;
+    constexpr int NFC = ct_nfc(TYPE);
+    constexpr int NFGE = ct_nfge(TYPE);
+    int64_t const n = G.n;
+    int64_t const S = F.S;
+    int64_t const k = G.beg + i;
+    double const hdt = F.dt * 0.5;
+    double const acfl = fabs(cflc);
+    double const sgm0 = F.sigma0 / acfl;
+    double const tau = F.taumin + acfl * F.tauscale;
+    double const ofg1 = 1.0 / NFGE;
+
+    // ---- gradient element geometry
+    double icecnd[ND];
+#pragma unroll
+    for (int d = 0; d < ND; ++d) { icecnd[d] = F.solpt[d * S + k]; }
+    double gp[NFC][ND], jd[NFC][ND];
+    int32_t rcl[NFC];
+#pragma unroll
+    for (int f = 0; f < NFC; ++f)
+    {
+        int32_t const j = G.nbr[f * n + i];
+        rcl[f] = j;
+#pragma unroll
+        for (int d = 0; d < ND; ++d)
+        {
+            double const mid = G.cecnd[(f * ND + d) * n + i];
+            double const jce = F.solpt[d * S + j];
+            gp[f][d] = mid + tau * (jce - mid);
+            jd[f][d] = gp[f][d] - jce;
+        }
+    }
+    double avg[ND];
+#pragma unroll
+    for (int d = 0; d < ND; ++d) { avg[d] = 0.0; }
+#pragma unroll
+    for (int f = 0; f < NFC; ++f)
+    {
+#pragma unroll
+        for (int d = 0; d < ND; ++d) { avg[d] += gp[f][d]; }
+    }
+#pragma unroll
+    for (int d = 0; d < ND; ++d) { avg[d] /= NFC; }
+    double cnd[ND];
+#pragma unroll
+    for (int d = 0; d < ND; ++d) { cnd[d] = 0.0; }
+    double voc = 0.0;
+#pragma unroll
+    for (int isub = 0; isub < NFGE; ++isub)
+    {
+        double subcnd[ND];
+        double dst[ND][ND];
+#pragma unroll
+        for (int d = 0; d < ND; ++d) { subcnd[d] = avg[d]; }
+#pragma unroll
+        for (int ivx = 0; ivx < ND; ++ivx)
+        {
+            int const fl = fge_face(TYPE, isub, ivx);
+#pragma unroll
+            for (int d = 0; d < ND; ++d)
+            {
+                subcnd[d] += gp[fl][d];
+                dst[ivx][d] = gp[fl][d] - avg[d];
+            }
+        }
+#pragma unroll
+        for (int d = 0; d < ND; ++d) { subcnd[d] /= static_cast<double>(ND + 1); }
+        double const vob = det_n<ND>(dst);
+        voc += vob;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) { cnd[d] += subcnd[d] * vob; }
+    }
+#pragma unroll
+    for (int d = 0; d < ND; ++d) { cnd[d] /= voc; }
+
+    // ---- per-face displacement and Taylor difference (shared by the FGEs that use the face)
+    double idis[NFC][ND];
+    double udf[NFC][NEQ];
+#pragma unroll
+    for (int f = 0; f < NFC; ++f)
+    {
+        double jdis[ND];
+#pragma unroll
+        for (int d = 0; d < ND; ++d)
+        {
+            idis[f][d] = gp[f][d] - cnd[d];
+            jdis[d] = jd[f][d] + icecnd[d] - cnd[d];
+        }
+        int64_t const j = rcl[f];
+#pragma unroll
+        for (int e = 0; e < NEQ; ++e)
+        {
+            double val = F.so0c[e * S + j] + hdt * F.so0t[e * S + j] - un[e];
+#pragma unroll
+            for (int d = 0; d < ND; ++d) { val += jdis[d] * F.so1c[(e * ND + d) * S + j]; }
+            udf[f][e] = val;
+        }
+    }
+
+    // ---- per-FGE gradients and W-1/2 weights
+    double grad[NFGE][NEQ][ND];
+    double widv[NFGE][NEQ];
+    double wacc[NEQ];
+#pragma unroll
+    for (int e = 0; e < NEQ; ++e) { wacc[e] = 0.0; }
+#pragma unroll
+    for (int ifge = 0; ifge < NFGE; ++ifge)
+    {
+        double dst[ND][ND], adj[ND][ND];
+#pragma unroll
+        for (int ivx = 0; ivx < ND; ++ivx)
+        {
+            int const fl = fge_face(TYPE, ifge, ivx);
+#pragma unroll
+            for (int d = 0; d < ND; ++d) { dst[ivx][d] = idis[fl][d]; }
+        }
+        adj_n<ND>(dst, adj);
+        double const det = det_n<ND>(dst);
+#pragma unroll
+        for (int e = 0; e < NEQ; ++e)
+        {
+            double sq = 0.0;
+#pragma unroll
+            for (int a = 0; a < ND; ++a)
+            {
+                double r = 0.0;
+#pragma unroll
+                for (int b = 0; b < ND; ++b) { r += adj[a][b] * udf[fge_face(TYPE, ifge, b)][e]; }
+                grad[ifge][e][a] = r / det;
+            }
+#pragma unroll
+            for (int d = 0; d < ND; ++d) { sq += grad[ifge][e][d] * grad[ifge][e][d]; }
+            double const wgt = 1.0 / sqrt(sq + MD_ALMOST_ZERO);
+            wacc[e] += wgt;
+            widv[ifge][e] = wgt;
+        }
+    }
+
+    // ---- W-3/4 limiter (euler_gradient.cpp:90-128)
+#pragma unroll
+    for (int e = 0; e < NEQ; ++e)
+    {
+        double wmax = 0.0, wmin = 0.0;
+#pragma unroll
+        for (int ifge = 0; ifge < NFGE; ++ifge)
+        {
+            double const wgt = widv[ifge][e] / wacc[e] - ofg1;
+            widv[ifge][e] = wgt;
+            wmax = fmax(wmax, wgt);
+            wmin = fmin(wmin, wgt);
+        }
+        double const sm = fmin((1.0 - ofg1) / (wmax + MD_ALMOST_ZERO), -ofg1 / (wmin - MD_ALMOST_ZERO));
+        double const sigma_max = fmin(sm, sgm0);
+        double o[ND];
+#pragma unroll
+        for (int d = 0; d < ND; ++d) { o[d] = 0.0; }
+#pragma unroll
+        for (int isub = 0; isub < NFGE; ++isub)
+        {
+            double const wgt = ofg1 + sigma_max * widv[isub][e];
+#pragma unroll
+            for (int d = 0; d < ND; ++d) { o[d] += wgt * grad[isub][e][d]; }
+        }
+#pragma unroll
+        for (int d = 0; d < ND; ++d) { out[e][d] = o[d]; }
+    }
+}
+
+// normal_matrix<2>/<3>, euler_bc.cpp:90-128 (host side: evaluated once per boundary face at add_bc time)
+inline void normal_matrix_host(int ndim, double const * nv, double * out)
+{
+    if (2 == ndim)
+    {
+        out[0] = nv[0];
+        out[1] = nv[1];
+        out[2] = -nv[1];
+        out[3] = nv[0];
+        return;
+    }
+    double axis[3] = {0.0, 0.0, 0.0};
+    double const ax = std::fabs(nv[0]), ay = std::fabs(nv[1]), az = std::fabs(nv[2]);
+    if (ax <= ay && ax <= az) { axis[0] = 1.0; }
+    else if (ay <= az) { axis[1] = 1.0; }
+    else { axis[2] = 1.0; }
+    double t1[3] = {nv[1] * axis[2] - nv[2] * axis[1], nv[2] * axis[0] - nv[0] * axis[2], nv[0] * axis[1] - nv[1] * axis[0]};
+    double const len = std::sqrt(t1[0] * t1[0] + t1[1] * t1[1] + t1[2] * t1[2]);
+    t1[0] = t1[0] / len;
+    t1[1] = t1[1] / len;
+    t1[2] = t1[2] / len;
+    double const t2[3] = {nv[1] * t1[2] - nv[2] * t1[1], nv[2] * t1[0] - nv[0] * t1[2], nv[0] * t1[1] - nv[1] * t1[0]};
+    for (int d = 0; d < 3; ++d)
+    {
+        out[d] = nv[d];
+        out[3 + d] = t1[d];
+        out[6 + d] = t2[d];
+    }
+}
+
+} // namespace scg

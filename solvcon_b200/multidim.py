@@ -1,0 +1,309 @@
+"""Host-side mirror of ``_solvcon.EulerCore`` over the device library.
+
+Keeps the reference's binding surface (``cpp/solvcon/multidim/pymod/wrap_multidim.cpp:247-408``):
+``EulerCore(mesh, time_increment)``; ``ndim, ncell, ngstcell, neq, time_increment``; ``sigma0, taumin,
+tauscale`` (rw); ``prepare_ce(), init_solution(gamma, rho, v, p), march(steps), march_substep(), update(),
+calc_cfl(), calc_solt(), calc_soln(), calc_dsoln(), add_nonrefl(faces), add_slipwall(faces),
+add_inlet(faces, value), clear_bc(), get_normal_matrix(ifc), bc_soln(), bc_dsoln()``; SimpleArray
+properties ``cevol, cecnd, sfcnd, sfnml, so0c, so0n, so0t, so1c, so1n, stm, cflo, cflc, gamma`` whose
+``.ndarray`` views alias solver memory and may be written through (``tests/multidim/euler/test_field.py:50-83``).
+
+Coherence protocol: the host arrays stay the API-visible storage.  Every compute method
+uploads the state (and the CE geometry if the caller changed it), runs on the device, and downloads
+the state.  ``resident(True)`` suspends the transfers for long marches and benchmarking;
+``sync_to_host()`` brings the field back.  There is no CPU path: without the CUDA library every method
+raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .simplearray import SimpleArray
+
+(MD_UPDATE, MD_SOLT, MD_SOLN, MD_BC_SOLN, MD_CFL, MD_DSOLN, MD_BC_DSOLN, MD_PREPARE_CE, MD_SUBSTEP) = range(9)
+BC_NONREFL, BC_SLIPWALL, BC_INLET = 0, 1, 2
+ORDER_NONE, ORDER_MORTON, ORDER_RCM = 0, 1, 2
+_ORDERS = {"none": 0, "morton": 1, "rcm": 2, 0: 0, 1: 1, 2: 2}
+
+ARRAY_IDS = {"cevol": 0, "cecnd": 1, "sfcnd": 2, "sfnml": 3, "so0c": 4, "so0n": 5, "so0t": 6, "so1c": 7,
+             "so1n": 8, "cflo": 9, "cflc": 10, "gamma": 11}
+_GEOMETRY = ("cevol", "cecnd", "sfcnd", "sfnml")
+_STATE = ("so0c", "so0n", "so0t", "so1c", "so1n", "cflo", "cflc", "gamma")
+CLMFC, FCMND = 6, 4
+
+
+def _raise(exc=None):
+    msg = _lib.load().scg_last_error().decode()
+    if exc is None:
+        exc = ValueError if msg.startswith("EulerCore::") else _lib.ScgError
+    raise exc(msg)
+
+
+def _table(mesh, name):
+    """Full stored table (ghost rows first) of a mesh object as a C-contiguous ndarray."""
+    t = getattr(mesh, name)
+    a = t.ndarray if hasattr(t, "ndarray") else np.asarray(t)
+    return np.ascontiguousarray(a)
+
+
+class DeviceMesh:
+    """Device copy of the StaticMesh tables the march reads, in the reordered device layout
+    (``scg_mesh_create``).  ``order``: ``"none" | "morton" | "rcm"``."""
+
+    def __init__(self, mesh, order="morton"):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        self.order = _ORDERS[order]
+        self.ndim = int(mesh.ndim)
+        self.ncell, self.nface, self.nnode = int(mesh.ncell), int(mesh.nface), int(mesh.nnode)
+        self.ngstcell, self.ngstface, self.ngstnode = int(mesh.ngstcell), int(mesh.ngstface), int(mesh.ngstnode)
+        if self.ngstcell == 0 and getattr(mesh, "nbound", 1) != 0:
+            raise ValueError("EulerCore: the mesh has no ghost cells; call build_boundary() and build_ghost() first")
+        t = {n: _table(mesh, n) for n in ("cltpn", "clfcs", "fccls", "fcnds", "ndcrd", "fccnd", "fcnml", "clcnd")}
+        for n in ("cltpn", "clfcs", "fccls", "fcnds"):
+            if t[n].dtype != np.int32:
+                t[n] = t[n].astype(np.int32)
+        rc = self._lib.scg_mesh_create(
+            C.byref(self._h), self.ndim, self.nnode, self.nface, self.ncell, self.ngstnode, self.ngstface,
+            self.ngstcell, _lib.ptr(t["cltpn"]), _lib.ptr(t["clfcs"]), _lib.ptr(t["fccls"]), _lib.ptr(t["fcnds"]),
+            _lib.ptr(t["ndcrd"]), _lib.ptr(t["fccnd"]), _lib.ptr(t["fcnml"]), _lib.ptr(t["clcnd"]), self.order)
+        if rc:
+            _raise(ValueError)
+
+    @property
+    def perm(self):
+        """``perm[k]`` = reference cell id stored at device slot ``k``."""
+        out = np.zeros(self.ncell, dtype=np.int32)
+        _lib.check(self._lib.scg_mesh_perm(self._h, _lib.ptr(out)))
+        return out
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            self._lib.scg_mesh_destroy(h)
+            self._h = None
+
+
+class EulerCore:
+    """Device twin of ``solvcon::EulerCore`` (``cpp/solvcon/multidim/euler.hpp:56-211``)."""
+
+    def __init__(self, mesh, time_increment, order="morton"):
+        self._lib = _lib.load()
+        self._mesh = mesh
+        self._dmesh = mesh if isinstance(mesh, DeviceMesh) else DeviceMesh(mesh, order)
+        dm = self._dmesh
+        self._ndim, self._ncell, self._ngst = dm.ndim, dm.ncell, dm.ngstcell
+        self._neq = self._ndim + 2
+        self._dt = float(time_increment)
+        self._h = C.c_void_p()
+        if self._lib.scg_md_create(C.byref(self._h), dm._h, self._dt):
+            _raise(_lib.ScgError)
+        T, nd, neq, nc, ng = self._ncell + self._ngst, self._ndim, self._neq, self._ncell, self._ngst
+
+        def arr(shape, nghost):
+            return SimpleArray(shape, 0.0, nghost=nghost)
+
+        # allocation shapes: euler_ce.cpp:31-60, euler_solution.cpp:19-41
+        self._a = {
+            "cevol": arr((T, CLMFC + 1), ng), "cecnd": arr((T, (CLMFC + 1) * nd), ng),
+            "sfcnd": arr((nc, CLMFC * FCMND, nd), 0), "sfnml": arr((nc, CLMFC * FCMND, nd), 0),
+            "so0c": arr((T, neq), ng), "so0n": arr((T, neq), ng), "so0t": arr((T, neq), ng),
+            "so1c": arr((T, neq, nd), ng), "so1n": arr((T, neq, nd), ng), "stm": arr((T, neq), ng),
+            "cflo": arr((T,), ng), "cflc": arr((T,), ng), "gamma": arr((T,), ng),
+        }
+        self._sigma0, self._taumin, self._tauscale = 3.0, 0.0, 1.0  # euler.hpp:184-188
+        self._resident = False
+        self._geo_seen = {}
+        self._pull(_GEOMETRY)
+        for n in _GEOMETRY:
+            self._geo_seen[n] = self._a[n].ndarray.copy()
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            self._lib.scg_md_destroy(h)
+            self._h = None
+
+    # -- scalars ---------------------------------------------------------------------------------
+    ndim = property(lambda self: self._ndim)
+    ncell = property(lambda self: self._ncell)
+    ngstcell = property(lambda self: self._ngst)
+    neq = property(lambda self: self._neq)
+    time_increment = property(lambda self: self._dt)
+    mesh = property(lambda self: self._mesh)
+
+    def _set_param(self, name, v):
+        setattr(self, name, float(v))
+        _lib.check(self._lib.scg_md_set_params(self._h, self._sigma0, self._taumin, self._tauscale))
+
+    sigma0 = property(lambda self: self._sigma0, lambda self, v: self._set_param("_sigma0", v))
+    taumin = property(lambda self: self._taumin, lambda self, v: self._set_param("_taumin", v))
+    tauscale = property(lambda self: self._tauscale, lambda self, v: self._set_param("_tauscale", v))
+
+    # -- arrays ------------------------------------------------------------------------------------
+    cevol = property(lambda self: self._a["cevol"])
+    cecnd = property(lambda self: self._a["cecnd"])
+    sfcnd = property(lambda self: self._a["sfcnd"])
+    sfnml = property(lambda self: self._a["sfnml"])
+    so0c = property(lambda self: self._a["so0c"])
+    so0n = property(lambda self: self._a["so0n"])
+    so0t = property(lambda self: self._a["so0t"])
+    so1c = property(lambda self: self._a["so1c"])
+    so1n = property(lambda self: self._a["so1n"])
+    stm = property(lambda self: self._a["stm"])
+    cflo = property(lambda self: self._a["cflo"])
+    cflc = property(lambda self: self._a["cflc"])
+    gamma = property(lambda self: self._a["gamma"])
+
+    # -- coherence ---------------------------------------------------------------------------------
+    def _push(self, names=_STATE, force=False):
+        if self._resident and not force:
+            return
+        for n in names:
+            _lib.check(self._lib.scg_md_upload(self._h, ARRAY_IDS[n], _lib.ptr(self._a[n].ndarray)))
+        # the CE geometry only travels when the caller wrote into it
+        for n in _GEOMETRY:
+            cur = self._a[n].ndarray
+            if n in self._geo_seen and not np.array_equal(cur, self._geo_seen[n]):
+                _lib.check(self._lib.scg_md_upload(self._h, ARRAY_IDS[n], _lib.ptr(cur)))
+                self._geo_seen[n] = cur.copy()
+
+    def _pull(self, names=_STATE, force=False):
+        if self._resident and not force:
+            return
+        for n in names:
+            _lib.check(self._lib.scg_md_download(self._h, ARRAY_IDS[n], _lib.ptr(self._a[n].ndarray)))
+
+    def resident(self, flag=True):
+        """Keep the field on the device between calls (uploads once now)."""
+        if flag and not self._resident:
+            self._push(force=True)
+        if not flag and self._resident:
+            self.sync_to_host()
+        self._resident = bool(flag)
+        return self
+
+    def sync_to_host(self):
+        self._pull(force=True)
+
+    def _swap_host(self):
+        a = self._a
+        a["so0c"], a["so0n"] = a["so0n"], a["so0c"]
+        a["so1c"], a["so1n"] = a["so1n"], a["so1c"]
+
+    def _phase(self, phase):
+        self._push()
+        if self._lib.scg_md_phase(self._h, phase):
+            _raise()
+        self._pull()
+
+    # -- preparation (wrap_multidim.cpp:275-307) ----------------------------------------------------------
+    def prepare_ce(self):
+        self._push()
+        if self._lib.scg_md_phase(self._h, MD_PREPARE_CE):
+            _raise()
+        self._pull(_GEOMETRY, force=True)
+        for n in _GEOMETRY:
+            self._geo_seen[n] = self._a[n].ndarray.copy()
+
+    def init_solution(self, gamma, rho, v, p):
+        v = list(v)
+        if len(v) != self._ndim:
+            raise ValueError(f"EulerCore::init_solution: velocity size {len(v)} must equal ndim {self._ndim}")
+        vv = (C.c_double * 3)(*(list(map(float, v)) + [0.0] * (3 - len(v))))
+        self._push()
+        if self._lib.scg_md_init_solution(self._h, float(gamma), float(rho), vv, float(p)):
+            _raise(ValueError)
+        self._pull()
+
+    # -- march (wrap_multidim.cpp:309-327) -----------------------------------------------------------------
+    def march(self, steps):
+        self._push()
+        if self._lib.scg_md_march(self._h, int(steps)):
+            _raise()
+        self._pull()
+
+    def march_substep(self):
+        self._push()
+        if self._lib.scg_md_phase(self._h, MD_SUBSTEP):
+            _raise()
+        self._swap_host()
+        self._pull()
+
+    def update(self):
+        # pointer swap on both sides (euler.hpp:123-127): views taken earlier alias the other buffer
+        _lib.check(self._lib.scg_md_phase(self._h, MD_UPDATE))
+        self._swap_host()
+
+    def calc_cfl(self):
+        self._phase(MD_CFL)
+
+    def calc_solt(self):
+        self._phase(MD_SOLT)
+
+    def calc_soln(self):
+        self._phase(MD_SOLN)
+
+    def calc_dsoln(self):
+        self._phase(MD_DSOLN)
+
+    def bc_soln(self):
+        self._phase(MD_BC_SOLN)
+
+    def bc_dsoln(self):
+        self._phase(MD_BC_DSOLN)
+
+    # -- boundaries (wrap_multidim.cpp:329-383) ----------------------------------------------------------------
+    def _add_bc(self, kind, faces, value=()):
+        f = np.ascontiguousarray(faces, dtype=np.int32)
+        val = np.ascontiguousarray(value, dtype=np.float64)
+        rc = self._lib.scg_md_add_bc(self._h, kind, _lib.ptr(f) if len(f) else None, len(f),
+                                     _lib.ptr(val) if len(val) else None, len(val))
+        if rc:
+            _raise(ValueError)
+
+    def add_nonrefl(self, faces):
+        self._add_bc(BC_NONREFL, faces)
+
+    def add_slipwall(self, faces):
+        self._add_bc(BC_SLIPWALL, faces)
+
+    def add_inlet(self, faces, value):
+        self._add_bc(BC_INLET, faces, value)
+
+    def clear_bc(self):
+        _lib.check(self._lib.scg_md_clear_bc(self._h))
+
+    def get_normal_matrix(self, ifc):
+        ifc = int(ifc)
+        nface = self._dmesh.nface
+        if ifc < 0 or ifc >= nface:
+            raise IndexError(f"EulerCore: face {ifc} out of range [0, {nface})")
+        out = np.zeros((self._ndim, self._ndim))
+        _lib.check(self._lib.scg_md_normal_matrix(self._h, ifc, _lib.ptr(out)))
+        return out.tolist()
+
+    # -- additive API -----------------------------------------------------------------------------------
+    def set_fused(self, flag):
+        """march() with the fused soln+cfl+dsoln kernel (default) or one kernel per reference phase."""
+        _lib.check(self._lib.scg_md_set_fused(self._h, int(bool(flag))))
+
+    def reduce(self, clvol=None):
+        """(cflo.min, cflo.max, sum(density*clvol)) over body cells on the device -- the callers' numpy
+        reductions of ``solvcon/multidim/euler/_field.py:138-148``.  ``clvol``: the mesh's full table
+        (ghost rows first); cached on the device after the first call."""
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        if not self._resident:
+            self._push()
+        vol = None if clvol is None else np.ascontiguousarray(clvol, dtype=np.float64)
+        _lib.check(self._lib.scg_md_reduce(self._h, _lib.ptr(vol), C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def algorithmic_bytes(self):
+        """Algorithmic bytes one substep moves on this mesh."""
+        v = C.c_int64()
+        _lib.check(self._lib.scg_md_algorithmic_bytes(self._h, C.byref(v)))
+        return v.value

@@ -1,0 +1,195 @@
+"""GPU parity of the multidim device path against the CPU checkers, through the C-ABI of include/scg.h
+(via solvcon_b200.multidim.EulerCore).  Strict build: bit-equal, array by array, phase by phase."""
+import numpy as np
+import pytest
+
+from cases import md_bump_ic, md_mesh_case
+
+pytestmark = pytest.mark.gpu
+
+MESHES = ["quad2d", "tri2d", "mixed2d", "step2d", "hex3d", "tet3d", "prism3d", "mixed3d"]
+STATE = ("so0c", "so0n", "so0t", "so1c", "so1n", "cflo", "cflc", "gamma")
+GEOM = ("cevol", "cecnd", "sfcnd", "sfnml")
+
+
+class Case:
+    """One mesh + IC + BCs set up identically on the checker and on the device solver."""
+
+    def __init__(self, b, name, order="morton", dt_scale=0.05):
+        from solvcon_b200 import meshgen
+        from solvcon_b200.mesh import TableMesh
+        from solvcon_b200.multidim import EulerCore
+        ndim, ndcrd, cltpn, clnds = md_mesh_case(name)
+        self.ndim = ndim
+        if b.have_ref():
+            rmesh = b.make_ref_mesh(ndim, ndcrd, cltpn, clnds)
+            tabs = rmesh.tables()
+            self.rmesh = rmesh
+        else:
+            pytest.skip("needs oracle/_ref (mesh tables come from the reference's StaticMesh)")
+        ng = tabs["fccls"][1]
+        nface = len(tabs["fccls"][0]) - ng
+        fccnd = tabs["fccnd"][0][tabs["fccnd"][1]:]
+        fccls = tabs["fccls"][0][ng:]
+        clcnd = tabs["clcnd"][0][tabs["clcnd"][1]:]
+        lo, hi = ndcrd.min(axis=0), ndcrd.max(axis=0)
+        self.groups = meshgen.boundary_groups(ndim, fccnd, fccls, nface, lo, hi)
+        inlet, outlet, wall = self.groups
+        h = (np.prod(hi - lo) / len(cltpn)) ** (1.0 / ndim)
+        dt = dt_scale * h
+        self.chk = b.PortEuler(tabs, ndim, dt)
+        self.chk.phase(b.MD_PREPARE_CE)
+        self.mesh = TableMesh(ndim, tabs)
+        self.dev = EulerCore(self.mesh, dt, order=order)
+        vel = [2.0, 0.0, 0.0][:ndim]
+        self.chk.init_solution(1.4, 1.4, vel, 1.0)
+        self.dev.init_solution(1.4, 1.4, vel, 1.0)
+        md_bump_ic(self.chk.body, clcnd, ndim)
+        md_bump_ic(lambda n: getattr(self.dev, n).body, clcnd, ndim)
+        inval = [1.4] + vel + [1.0, 1.4]
+        self.chk.add_bc(b.BC_INLET, inlet, inval)
+        self.chk.add_bc(b.BC_NONREFL, outlet)
+        self.chk.add_bc(b.BC_SLIPWALL, wall)
+        self.dev.add_inlet(inlet, inval)
+        self.dev.add_nonrefl(outlet)
+        self.dev.add_slipwall(wall)
+
+    def same(self, tag, names=STATE, strict=True):
+        for n in names:
+            a, c = getattr(self.dev, n).ndarray, self.chk.arr(n)
+            if strict:
+                assert np.array_equal(a, c), f"{tag}: {n} differs, max abs {np.abs(a - c).max()}"
+            else:
+                scale = np.abs(c).max() + 1e-300
+                assert np.abs(a - c).max() / scale < 1e-10, f"{tag}: {n}"
+
+
+def _strict(gpu):
+    return bool(gpu.load().scg_build_is_strict())
+
+
+@pytest.mark.parametrize("name", MESHES)
+def test_md_geometry_and_phases(gpu, bridge, name):
+    """prepare_ce and every phase of three substeps, like the reference's per-phase tests
+    (tests/test_multidim.py:632-770) but against the checker's arrays, bit for bit."""
+    b = bridge
+    c = Case(b, name)
+    strict = _strict(gpu)
+    c.same("prepare_ce", GEOM, strict)
+    c.chk.phase(b.MD_BC_SOLN)
+    c.chk.phase(b.MD_BC_DSOLN)
+    c.dev.bc_soln()
+    c.dev.bc_dsoln()
+    c.same("prime", STATE, strict)
+    calls = (("update", b.MD_UPDATE), ("calc_solt", b.MD_SOLT), ("calc_soln", b.MD_SOLN), ("bc_soln", b.MD_BC_SOLN),
+             ("calc_cfl", b.MD_CFL), ("calc_dsoln", b.MD_DSOLN), ("bc_dsoln", b.MD_BC_DSOLN))
+    for it in range(3):
+        for fn, ph in calls:
+            c.chk.phase(ph)
+            getattr(c.dev, fn)()
+            c.same(f"substep {it} {fn}", STATE, strict)
+    assert np.abs(c.dev.so1n.body).max() > 1e-3
+
+
+@pytest.mark.parametrize("name", ["mixed2d", "step2d", "mixed3d", "hex3d"])
+@pytest.mark.parametrize("order", ["none", "morton", "rcm"])
+@pytest.mark.parametrize("fused", [True, False])
+def test_md_march_matches(gpu, bridge, name, order, fused):
+    """march(N) with every cell ordering, fused and per-phase kernels: identical to the checker."""
+    b = bridge
+    c = Case(b, name, order=order)
+    strict = _strict(gpu)
+    c.dev.set_fused(fused)
+    for s in (c.chk,):
+        s.phase(b.MD_BC_SOLN)
+        s.phase(b.MD_BC_DSOLN)
+    c.dev.bc_soln()
+    c.dev.bc_dsoln()
+    n = 25
+    c.chk.march(n)
+    c.dev.march(n)
+    c.same(f"march({n}) order={order} fused={fused}", STATE, strict)
+    assert np.isfinite(c.dev.so0n.ndarray).all()
+    # conserved totals equal to round-off
+    vol = c.mesh.clvol.body
+    tot_d = (c.dev.so0n.body * vol[:, None]).sum(axis=0)
+    tot_c = (c.chk.body("so0n") * vol[:, None]).sum(axis=0)
+    assert np.allclose(tot_d, tot_c, rtol=1e-13, atol=1e-13)
+
+
+def test_md_substep_and_swap(gpu, bridge):
+    """march_substep swaps the current/next buffers on both sides (euler.hpp:123-127)."""
+    b = bridge
+    c = Case(b, "mixed2d")
+    c.dev.bc_soln(); c.dev.bc_dsoln()
+    c.chk.phase(b.MD_BC_SOLN); c.chk.phase(b.MD_BC_DSOLN)
+    view_n = c.dev.so0n.ndarray
+    for it in range(3):
+        c.chk.phase(b.MD_SUBSTEP)
+        c.dev.march_substep()
+        c.same(f"march_substep {it}", STATE, _strict(gpu))
+    # three swaps later the old so0n buffer is the current one
+    assert view_n is c.dev.so0c.ndarray
+
+
+def test_md_reduce_resident_and_params(gpu, bridge):
+    b = bridge
+    c = Case(b, "mixed3d")
+    c.dev.sigma0, c.dev.taumin, c.dev.tauscale = 2.0, 0.1, 0.7
+    c.chk.set_params(2.0, 0.1, 0.7)
+    c.chk.phase(b.MD_BC_SOLN); c.chk.phase(b.MD_BC_DSOLN)
+    c.dev.bc_soln(); c.dev.bc_dsoln()
+    c.dev.resident(True)
+    c.dev.march(4)
+    mn, mx, mass = c.dev.reduce(c.mesh.clvol.ndarray)
+    c.dev.sync_to_host()
+    c.chk.march(4)
+    c.same("resident march(4) with sigma0=2, taumin=.1, tauscale=.7", STATE, _strict(gpu))
+    cflo = c.dev.cflo.body
+    assert mn == cflo.min() and mx == cflo.max()
+    ref_mass = (c.dev.so0n.body[:, 0] * c.mesh.clvol.body).sum()
+    assert abs(mass - ref_mass) <= 1e-12 * abs(ref_mass)
+    assert c.dev.algorithmic_bytes() > 0
+
+
+def test_md_bc_validation_and_normal_matrix(gpu, bridge):
+    b = bridge
+    c = Case(b, "hex3d")
+    inlet, outlet, wall = c.groups
+    interior = int(np.nonzero(c.mesh.fccls.body[:, 1] >= 0)[0][0])
+    with pytest.raises(ValueError, match="is not a boundary face"):
+        c.dev.add_slipwall([interior])
+    with pytest.raises(ValueError, match="out of range"):
+        c.dev.add_nonrefl([c.mesh.nface])
+    with pytest.raises(ValueError, match="inlet value size"):
+        c.dev.add_inlet(inlet, [1.0, 2.0])
+    with pytest.raises(ValueError, match="gamma .* must be > 1"):
+        c.dev.init_solution(1.0, 1.0, [0, 0, 0], 1.0)
+    with pytest.raises(ValueError, match="velocity size"):
+        c.dev.init_solution(1.4, 1.0, [0, 0], 1.0)
+    with pytest.raises(IndexError):
+        c.dev.get_normal_matrix(c.mesh.nface)
+    for ifc in list(wall[:4]) + list(inlet[:2]):
+        out = np.zeros((3, 3))
+        nv = np.ascontiguousarray(c.mesh.fcnml.body[ifc])
+        b.port_lib().orc_normal_matrix(3, b._p(nv), b._p(out))
+        assert np.array_equal(np.array(c.dev.get_normal_matrix(int(ifc))), out)
+
+
+def test_md_overlapping_bc_last_wins(gpu, bridge):
+    """Boundaries apply in registration order; a face listed twice is overwritten by the later one."""
+    b = bridge
+    c = Case(b, "mixed2d")
+    inlet, outlet, wall = c.groups
+    extra = wall[: len(wall) // 2]
+    c.chk.add_bc(b.BC_NONREFL, extra)
+    c.dev.add_nonrefl(extra)
+    c.chk.phase(b.MD_BC_SOLN); c.chk.phase(b.MD_BC_DSOLN)
+    c.dev.bc_soln(); c.dev.bc_dsoln()
+    c.chk.march(5)
+    c.dev.march(5)
+    c.same("overlapping bc", STATE, _strict(gpu))
+    c.dev.clear_bc(); c.chk.clear_bc()
+    c.chk.march(2)
+    c.dev.march(2)
+    c.same("no bc", STATE, _strict(gpu))
