@@ -108,6 +108,29 @@ SCG_API int scg_e1d_phase(scg_e1d * s, int phase, int odd_plane, int alpha);
 SCG_API int scg_e1d_march(scg_e1d * s, int alpha, int64_t steps);
 SCG_API int scg_e1d_reduce(scg_e1d * s, double * cfl_min, double * cfl_max, double * mass);
 
+/* ------------------------------------------------------------- host mesh
+ * native twin of solvcon::StaticMesh (cpp/solvcon/mesh/StaticMesh.hpp:270-455): the table builder
+ * behind the unchanged `StaticMesh(ndim, nnode, nface, ncell)` / build_interior / add_bc /
+ * build_boundary / build_ghost sequence (mesh/pymod/wrap_StaticMesh.cpp:61-175).  Host code only.
+ */
+typedef struct scg_hmesh scg_hmesh;
+
+SCG_API int scg_hmesh_create(scg_hmesh ** out, int ndim, int64_t nnode, int64_t nface, int64_t ncell);
+SCG_API int scg_hmesh_destroy(scg_hmesh * m);
+/* which: 0 ndim 1 nnode 2 nface 3 ncell 4 nbound 5 ngstnode 6 ngstface 7 ngstcell 8 nedge 9 nbcs */
+SCG_API int scg_hmesh_count(scg_hmesh * m, int which, int64_t * out);
+/* zero-copy access to a table by name (ndcrd fccnd fcnml fcara clcnd clvol fctpn cltpn clgrp fcnds fccls
+ * clnds clfcs ednds bndfcs): pointer to the first STORED row (ghost rows first), shape, ghost count.
+ * Pointers are invalidated by build_interior / build_boundary / build_ghost. */
+SCG_API int scg_hmesh_table(scg_hmesh * m, const char * name, void ** ptr, int64_t * rows, int64_t * cols,
+                            int64_t * nghost, int * is_real, int * one_d);
+SCG_API int scg_hmesh_build_interior(scg_hmesh * m, int do_metric, int do_edge); /* StaticMesh.hpp:363-374 */
+SCG_API int scg_hmesh_build_edge(scg_hmesh * m);                                  /* StaticMesh_interior.cpp:566-609 */
+SCG_API int scg_hmesh_add_bc(scg_hmesh * m, const char * name, const int32_t * faces, int64_t n); /* StaticMesh_boundary.cpp:14-78 */
+SCG_API int scg_hmesh_bc(scg_hmesh * m, int64_t ibc, const char ** name, int32_t ** facn, int64_t * nbound);
+SCG_API int scg_hmesh_build_boundary(scg_hmesh * m); /* StaticMesh_boundary.cpp:103-182 */
+SCG_API int scg_hmesh_build_ghost(scg_hmesh * m);    /* StaticMesh_boundary.cpp:185-627 */
+
 /* ---------------------------------------------------------- multidim Euler
  * replaces EulerCore over StaticMesh (cpp/solvcon/multidim/euler.hpp:56-211,
  * euler_{ce,march,solution,gradient,bc}.cpp, GradientElement.cpp).

@@ -65,6 +65,18 @@ _SIGNATURES = {
     "scg_e1d_phase": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "scg_e1d_march": (C.c_int, [C.c_void_p, C.c_int, C.c_int64]),
     "scg_e1d_reduce": (C.c_int, [C.c_void_p, DP, DP, DP]),
+    # host mesh
+    "scg_hmesh_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int64, C.c_int64, C.c_int64]),
+    "scg_hmesh_destroy": (C.c_int, [C.c_void_p]),
+    "scg_hmesh_count": (C.c_int, [C.c_void_p, C.c_int, I64P]),
+    "scg_hmesh_table": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p), I64P, I64P, I64P,
+                                   C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "scg_hmesh_build_interior": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "scg_hmesh_build_edge": (C.c_int, [C.c_void_p]),
+    "scg_hmesh_add_bc": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]),
+    "scg_hmesh_bc": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_char_p), C.POINTER(C.c_void_p), I64P]),
+    "scg_hmesh_build_boundary": (C.c_int, [C.c_void_p]),
+    "scg_hmesh_build_ghost": (C.c_int, [C.c_void_p]),
     # multidim
     "scg_mesh_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                    C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -36,3 +36,157 @@ class TableMesh:
         if name in t:
             return t[name]
         raise AttributeError(name)
+
+
+# --------------------------------------------------------------------------------------------------
+# StaticMesh: native table builder (csrc/scg_hmesh.cpp) behind the reference's binding surface
+# --------------------------------------------------------------------------------------------------
+import ctypes as _C
+
+from . import _lib as _libmod
+
+(_C_NDIM, _C_NNODE, _C_NFACE, _C_NCELL, _C_NBOUND, _C_NGSTNODE, _C_NGSTFACE, _C_NGSTCELL, _C_NEDGE, _C_NBCS) = range(10)
+
+
+class StaticMeshBc:
+    """Mirror of ``StaticMeshBc`` (``StaticMesh.hpp:146-246``): ``name``, ``nbound``, ``facn`` [n,3]."""
+
+    def __init__(self, name, facn):
+        self.name = name
+        self.facn = facn
+
+    def __len__(self):
+        return self.nbound
+
+    @property
+    def nbound(self):
+        return self.facn.shape[0]
+
+
+class StaticMesh:
+    """Host mesh with the reference's surface (``mesh/pymod/wrap_StaticMesh.cpp:61-175``):
+    ``StaticMesh(ndim, nnode, nface=0, ncell=0)``; fill ``ndcrd``, ``cltpn``, ``clnds`` through the array
+    views; ``build_interior(do_metric, build_edge)``, ``add_bc(name, faces)``, ``build_boundary()``,
+    ``build_ghost()``; the 15 tables as SimpleArrays (zero-copy views of the native storage)."""
+
+    FCMND, CLMND, CLMFC, FCREL, BFREL = 4, 8, 6, 4, 3
+    NONCELLTYPE, POINT, LINE, QUADRILATERAL, TRIANGLE, HEXAHEDRON, TETRAHEDRON, PRISM, PYRAMID = range(9)
+
+    def __init__(self, ndim, nnode, nface=0, ncell=0):
+        self._lib = _libmod.load()
+        self._h = _C.c_void_p()
+        if self._lib.scg_hmesh_create(_C.byref(self._h), int(ndim), int(nnode), int(nface), int(ncell)):
+            raise ValueError(self._lib.scg_last_error().decode())
+        self._cache = {}
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            self._lib.scg_hmesh_destroy(h)
+            self._h = None
+
+    def _count(self, which):
+        v = _C.c_int64()
+        _libmod.check(self._lib.scg_hmesh_count(self._h, which, _C.byref(v)))
+        return int(v.value)
+
+    ndim = property(lambda s: s._count(_C_NDIM))
+    nnode = property(lambda s: s._count(_C_NNODE))
+    nface = property(lambda s: s._count(_C_NFACE))
+    ncell = property(lambda s: s._count(_C_NCELL))
+    nbound = property(lambda s: s._count(_C_NBOUND))
+    ngstnode = property(lambda s: s._count(_C_NGSTNODE))
+    ngstface = property(lambda s: s._count(_C_NGSTFACE))
+    ngstcell = property(lambda s: s._count(_C_NGSTCELL))
+    nedge = property(lambda s: s._count(_C_NEDGE))
+    nbcs = property(lambda s: s._count(_C_NBCS))
+
+    def _table(self, name):
+        if name in self._cache:
+            return self._cache[name]
+        ptr = _C.c_void_p()
+        rows, cols, ngh = _C.c_int64(), _C.c_int64(), _C.c_int64()
+        real, one_d = _C.c_int(), _C.c_int()
+        _libmod.check(self._lib.scg_hmesh_table(self._h, name.encode(), _C.byref(ptr), _C.byref(rows), _C.byref(cols),
+                                                _C.byref(ngh), _C.byref(real), _C.byref(one_d)))
+        dtype = np.float64 if real.value else np.int32
+        shape = (rows.value,) if one_d.value else (rows.value, cols.value)
+        n = rows.value * (1 if one_d.value else cols.value)
+        if n == 0 or not ptr.value:
+            a = np.zeros(shape, dtype=dtype)
+        else:
+            ctype = _C.c_double if real.value else _C.c_int32
+            a = np.ctypeslib.as_array(_C.cast(ptr, _C.POINTER(ctype)), shape=(n,)).reshape(shape)
+        sa = SimpleArray(array=a, nghost=int(ngh.value))
+        sa._owner = self  # keep the native storage alive as long as the view is
+        self._cache[name] = sa
+        return sa
+
+    def __getattr__(self, name):
+        if name in TABLES:
+            return self._table(name)
+        raise AttributeError(name)
+
+    def _check(self, rc, exc=ValueError):
+        if rc:
+            msg = self._lib.scg_last_error().decode()
+            if "already built" in msg:
+                exc = RuntimeError
+            raise exc(msg)
+        self._cache = {}  # the native arrays may have been re-allocated
+
+    def build_interior(self, do_metric=True, build_edge=True, _do_metric=None):
+        self._check(self._lib.scg_hmesh_build_interior(self._h, int(bool(do_metric)), int(bool(build_edge))))
+
+    def build_edge(self):
+        self._check(self._lib.scg_hmesh_build_edge(self._h))
+
+    def build_boundary(self):
+        self._check(self._lib.scg_hmesh_build_boundary(self._h))
+
+    def build_ghost(self):
+        self._check(self._lib.scg_hmesh_build_ghost(self._h))
+
+    def add_bc(self, name, faces):
+        f = np.ascontiguousarray(faces, dtype=np.int32)
+        self._check(self._lib.scg_hmesh_add_bc(self._h, str(name).encode(), _libmod.ptr(f) if len(f) else None, len(f)))
+        return self.bc(self.nbcs - 1)
+
+    def bc(self, key):
+        if isinstance(key, str):
+            for i in range(self.nbcs):
+                b = self.bc(i)
+                if b.name == key:
+                    return b
+            raise KeyError(key)
+        name, facn, n = _C.c_char_p(), _C.c_void_p(), _C.c_int64()
+        if self._lib.scg_hmesh_bc(self._h, int(key), _C.byref(name), _C.byref(facn), _C.byref(n)):
+            raise IndexError(self._lib.scg_last_error().decode())
+        if n.value:
+            a = np.ctypeslib.as_array(_C.cast(facn, _C.POINTER(_C.c_int32)), shape=(n.value * 3,)).reshape(n.value, 3)
+        else:
+            a = np.zeros((0, 3), dtype=np.int32)
+        return StaticMeshBc(name.value.decode(), a)
+
+    @property
+    def bcs(self):
+        return [self.bc(i) for i in range(self.nbcs)]
+
+    def tables(self):
+        """Deep copies of all tables: ``{name: (array incl. ghost rows, nghost)}``."""
+        return {n: (self._table(n).ndarray.copy(), self._table(n).nghost) for n in TABLES}
+
+
+def make_mesh(ndim, ndcrd, cltpn, clnds, bcs=(), build_edge=False):
+    """Nodes + cells -> a fully built StaticMesh (interior, boundary, ghost)."""
+    ndcrd = np.asarray(ndcrd, dtype=np.float64)
+    m = StaticMesh(ndim, len(ndcrd), 0, len(cltpn))
+    m.ndcrd.ndarray[...] = ndcrd
+    m.cltpn.ndarray[...] = cltpn
+    m.clnds.ndarray[...] = clnds
+    m.build_interior(True, build_edge)
+    for name, faces in bcs:
+        m.add_bc(name, faces)
+    m.build_boundary()
+    m.build_ghost()
+    return m

@@ -21,7 +21,7 @@ import numpy as np
 
 
 class SimpleArray:
-    __slots__ = ("_a", "_nghost")
+    __slots__ = ("_a", "_nghost", "_owner")
 
     def __init__(self, shape=None, value=None, dtype=np.float64, array=None, nghost=0):
         if array is not None:
