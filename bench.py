@@ -269,6 +269,7 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("SCG_BENCH_WORKLOAD", "e1d"))
     ap.add_argument("--size", type=int, default=0, help="points / cells per GPU (0 = workload default)")
     ap.add_argument("--chunk", type=int, default=5, help="time steps per march() call (one bench step)")
+    ap.add_argument("--order", default="morton", help="multidim cell ordering: none | morton | rcm")
     ap.add_argument("--ref-budget", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -318,6 +319,8 @@ def main():
     # ---- end-to-end arm through the public class with host arrays
     e2e = None
     if not args.no_e2e:
+        if hasattr(wl.dev, "materialise"):
+            wl.dev.materialise()
         wl.dev.resident(False)
         wl.e2e_step()
         n_e2e = max(1, min(args.steps, 3))

@@ -1,0 +1,170 @@
+"""Multidim benchmark workloads for bench.py: 3D Euler CESE on the synthetic mixed tet/hex/prism stepped
+channel (BASELINE.json configs[3]/[4]) and 2D Euler on the mixed tri/quad forward-facing step (configs[2]).
+
+Everything here is product code (mesh generator -> native StaticMesh builder -> device EulerCore); the CPU
+reference arm (``cpu_run``) is the only place that touches ``oracle/`` and only bench.py calls it.
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+
+from . import meshgen
+from .mesh import make_mesh
+from .multidim import EulerCore
+
+UNIT = "updates/s"
+
+
+def dims_3d(ncell_target):
+    """Box counts (nx, ny, nz, x1, z1) of the stepped channel with ~ncell_target cells, one third
+    hexahedra / prisms / tetrahedra by cell count: hex boxes a*c*V, prisms 2(1-a)c*V, tets 6(1-a)(1-c)V
+    with a = x1/nx = 2/3, c = z1/nz = 3/4 -> 1.5 V cells."""
+    v = ncell_target / 1.5
+    u = (v / (4 * 3 * 3)) ** (1.0 / 3.0)  # aspect 4:3:3, divisible by 3 (x) and 4 (z)
+    nx = max(3, int(round(4 * u / 3.0)) * 3)
+    nz = max(4, int(round(3 * u / 4.0)) * 4)
+    ny = max(2, int(round(v / (nx * nz))))
+    return nx, ny, nz, 2 * nx // 3, 3 * nz // 4
+
+
+def build_case_3d(ncell_target, order="morton", kinds="hpt", log=None):
+    t0 = time.perf_counter()
+    nx, ny, nz, x1, z1 = dims_3d(ncell_target)
+    h = 1.0 / ny
+    ndcrd, cltpn, clnds = meshgen.mixed_3d(nx, ny, nz, lx=nx * h, ly=1.0, lz=nz * h, x1=x1, z1=z1, kinds=kinds,
+                                           jitter=0.1)
+    t1 = time.perf_counter()
+    mesh = make_mesh(3, ndcrd, cltpn, clnds)
+    t2 = time.perf_counter()
+    lo, hi = ndcrd.min(axis=0), ndcrd.max(axis=0)
+    inlet, outlet, wall = meshgen.boundary_groups(3, mesh.fccnd.body, mesh.fccls.body, mesh.nface, lo, hi)
+    dt = 0.05 * h
+    svr = EulerCore(mesh, dt, order=order)
+    t3 = time.perf_counter()
+    # IC / BC of SURVEY.md 8d config 4: Mach-3 stream, inlet / non-reflective outlet / slip walls
+    svr.resident(True)
+    svr.init_solution(1.4, 1.4, [3.0, 0.0, 0.0], 1.0)
+    svr.add_inlet(inlet, [1.4, 3.0, 0.0, 0.0, 1.0, 1.4])
+    svr.add_nonrefl(outlet)
+    svr.add_slipwall(wall)
+    svr.bc_soln()
+    svr.bc_dsoln()
+    info = {"boxes": [nx, ny, nz], "x1": x1, "z1": z1, "h": h, "dt": dt, "ncell": int(mesh.ncell),
+            "nface": int(mesh.nface), "ngstcell": int(mesh.ngstcell),
+            "cells_by_type": {"hex": int((cltpn == 5).sum()), "tet": int((cltpn == 6).sum()),
+                              "prism": int((cltpn == 7).sum())},
+            "setup_s": {"generate": round(t1 - t0, 2), "tables": round(t2 - t1, 2), "device": round(t3 - t2, 2)}}
+    if log:
+        log(info)
+    return mesh, svr, info
+
+
+class MD3DWorkload:
+    name = "md3d"
+    dtype = "f64"
+    dominant_kernel = "md_substep_kernel<hex|prism|tet> (+ md_solt_kernel, boundary kernels: one substep)"
+
+    def __init__(self, ncell, chunk, order="morton", kinds="hpt"):
+        self.ncell_target = int(ncell)
+        self.chunk = chunk
+        self.order = order
+        self.kinds = kinds
+
+    def build_device(self):
+        self.mesh, self.dev, self.info = build_case_3d(self.ncell_target, self.order, self.kinds)
+        self.ncell = self.info["ncell"]
+        self.balg_substep = self.dev.algorithmic_bytes()
+        return self.dev
+
+    def describe(self, world):
+        d = {"workload": f"3D Euler CESE (multidim EulerCore.march), synthetic mixed tet/hex/prism stepped channel, "
+                         f"{self.ncell} cells per GPU ({self.info['cells_by_type']}), Mach-3 inlet / nonrefl outlet / "
+                         f"slip walls, march({self.chunk}) per step, {self.order} cell ordering",
+             "cells_per_gpu": self.ncell, "chunk_steps": self.chunk, "ordering": self.order,
+             "alg_bytes_per_cell_substep": self.balg_substep / self.ncell,
+             "l2_policy": "inputs larger than L2 (%.1f GB streamed per substep)" % (self.balg_substep / 1e9),
+             "decomposition": "none" if world == 1 else "independent replicas per GPU (halo exchange: see DESIGN.md)",
+             "mesh": self.info}
+        return d
+
+    def updates_per_step(self):
+        return 2 * self.chunk * self.ncell
+
+    def launches_per_step(self):
+        return 2 * self.chunk  # substeps
+
+    def alg_bytes_per_launch(self):
+        return float(self.balg_substep)
+
+    def resident_begin(self):
+        self.dev.resident(True)
+
+    def resident_step(self):
+        self.dev.march(self.chunk)
+
+    def e2e_step(self):
+        self.dev.march(self.chunk)
+
+    def e2e_bytes(self):
+        T = self.ncell + self.info["ngstcell"]
+        nd = 3
+        neq = nd + 2
+        per_row = 8 * (3 * neq + 2 * neq * nd + 3)
+        return T * per_row, T * per_row
+
+    def result_check(self):
+        return float(self.dev.so0n.body[:, 0].sum())
+
+    def cpu_run(self, budget_s=15.0):
+        return cpu_reference_3d(budget_s, self.kinds)
+
+
+def cpu_reference_3d(budget_s=15.0, kinds="hpt", ncell_target=60000):
+    """The reference's own EulerCore.march (oracle/_ref, else the pinned C port) on the same generator at a
+    size that finishes in seconds, single thread (the reference is single-threaded)."""
+    from oracle import bridge as b
+    nx, ny, nz, x1, z1 = dims_3d(ncell_target)
+    h = 1.0 / ny
+    ndcrd, cltpn, clnds = meshgen.mixed_3d(nx, ny, nz, lx=nx * h, ly=1.0, lz=nz * h, x1=x1, z1=z1, kinds=kinds, jitter=0.1)
+    dt = 0.05 * h
+    if b.have_ref():
+        mesh = b.make_ref_mesh(3, ndcrd, cltpn, clnds)
+        svr = b.RefEuler(mesh, dt)
+        fccnd, fccls, nface = mesh.body("fccnd"), mesh.body("fccls"), mesh.nface
+        kind = "reference"
+    else:
+        pm = make_mesh(3, ndcrd, cltpn, clnds)
+        svr = b.PortEuler(pm.tables(), 3, dt)
+        svr.phase(b.MD_PREPARE_CE)
+        fccnd, fccls, nface = pm.fccnd.body, pm.fccls.body, pm.nface
+        kind = "port"
+    lo, hi = ndcrd.min(axis=0), ndcrd.max(axis=0)
+    inlet, outlet, wall = meshgen.boundary_groups(3, fccnd, fccls, nface, lo, hi)
+    svr.init_solution(1.4, 1.4, [3.0, 0.0, 0.0], 1.0)
+    svr.add_bc(b.BC_INLET, inlet, [1.4, 3.0, 0.0, 0.0, 1.0, 1.4])
+    svr.add_bc(b.BC_NONREFL, outlet)
+    svr.add_bc(b.BC_SLIPWALL, wall)
+    svr.phase(b.MD_BC_SOLN)
+    svr.phase(b.MD_BC_DSOLN)
+    svr.march(1)
+    ncell = len(cltpn)
+    t0 = time.perf_counter()
+    steps = 0
+    while True:
+        svr.march(1)
+        steps += 1
+        el = time.perf_counter() - t0
+        if el > budget_s or steps >= 200:
+            break
+    upd = 2 * steps * ncell
+    return ({"value": upd / el, "unit": UNIT, "cores": 1, "kind": kind,
+             "sample": f"3D Euler mixed tet/hex/prism channel, {ncell} cells, march({steps}) in {el:.2f} s, single "
+                       f"thread (the reference is single-threaded)"}, upd, el)
+
+
+def make(args):
+    if args.workload == "md3d":
+        return MD3DWorkload(args.size or 50_000_000, args.chunk, order=getattr(args, "order", "morton"))
+    raise SystemExit(f"workload {args.workload} not available")

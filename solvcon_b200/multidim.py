@@ -102,24 +102,32 @@ class EulerCore:
         if self._lib.scg_md_create(C.byref(self._h), dm._h, self._dt):
             _raise(_lib.ScgError)
         T, nd, neq, nc, ng = self._ncell + self._ngst, self._ndim, self._neq, self._ncell, self._ngst
-
-        def arr(shape, nghost):
-            return SimpleArray(shape, 0.0, nghost=nghost)
-
-        # allocation shapes: euler_ce.cpp:31-60, euler_solution.cpp:19-41
-        self._a = {
-            "cevol": arr((T, CLMFC + 1), ng), "cecnd": arr((T, (CLMFC + 1) * nd), ng),
-            "sfcnd": arr((nc, CLMFC * FCMND, nd), 0), "sfnml": arr((nc, CLMFC * FCMND, nd), 0),
-            "so0c": arr((T, neq), ng), "so0n": arr((T, neq), ng), "so0t": arr((T, neq), ng),
-            "so1c": arr((T, neq, nd), ng), "so1n": arr((T, neq, nd), ng), "stm": arr((T, neq), ng),
-            "cflo": arr((T,), ng), "cflc": arr((T,), ng), "gamma": arr((T,), ng),
+        # allocation shapes: euler_ce.cpp:31-60, euler_solution.cpp:19-41.  Host arrays are materialised
+        # on first access (a 10^8-cell mesh never needs the padded host geometry unless the caller asks).
+        self._shapes = {
+            "cevol": ((T, CLMFC + 1), ng), "cecnd": ((T, (CLMFC + 1) * nd), ng),
+            "sfcnd": ((nc, CLMFC * FCMND, nd), 0), "sfnml": ((nc, CLMFC * FCMND, nd), 0),
+            "so0c": ((T, neq), ng), "so0n": ((T, neq), ng), "so0t": ((T, neq), ng),
+            "so1c": ((T, neq, nd), ng), "so1n": ((T, neq, nd), ng), "stm": ((T, neq), ng),
+            "cflo": ((T,), ng), "cflc": ((T,), ng), "gamma": ((T,), ng),
         }
+        self._a = {}
         self._sigma0, self._taumin, self._tauscale = 3.0, 0.0, 1.0  # euler.hpp:184-188
         self._resident = False
         self._geo_seen = {}
-        self._pull(_GEOMETRY)
-        for n in _GEOMETRY:
-            self._geo_seen[n] = self._a[n].ndarray.copy()
+
+    def _get(self, name):
+        """The host SimpleArray of ``name``; on first access it is allocated and filled from the device."""
+        a = self._a.get(name)
+        if a is None:
+            shape, ng = self._shapes[name]
+            a = SimpleArray(shape, 0.0, nghost=ng)
+            self._a[name] = a
+            if name in ARRAY_IDS:
+                _lib.check(self._lib.scg_md_download(self._h, ARRAY_IDS[name], _lib.ptr(a.ndarray)))
+            if name in _GEOMETRY:
+                self._geo_seen[name] = a.ndarray.copy()
+        return a
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -144,30 +152,33 @@ class EulerCore:
     tauscale = property(lambda self: self._tauscale, lambda self, v: self._set_param("_tauscale", v))
 
     # -- arrays ------------------------------------------------------------------------------------
-    cevol = property(lambda self: self._a["cevol"])
-    cecnd = property(lambda self: self._a["cecnd"])
-    sfcnd = property(lambda self: self._a["sfcnd"])
-    sfnml = property(lambda self: self._a["sfnml"])
-    so0c = property(lambda self: self._a["so0c"])
-    so0n = property(lambda self: self._a["so0n"])
-    so0t = property(lambda self: self._a["so0t"])
-    so1c = property(lambda self: self._a["so1c"])
-    so1n = property(lambda self: self._a["so1n"])
-    stm = property(lambda self: self._a["stm"])
-    cflo = property(lambda self: self._a["cflo"])
-    cflc = property(lambda self: self._a["cflc"])
-    gamma = property(lambda self: self._a["gamma"])
+    cevol = property(lambda self: self._get("cevol"))
+    cecnd = property(lambda self: self._get("cecnd"))
+    sfcnd = property(lambda self: self._get("sfcnd"))
+    sfnml = property(lambda self: self._get("sfnml"))
+    so0c = property(lambda self: self._get("so0c"))
+    so0n = property(lambda self: self._get("so0n"))
+    so0t = property(lambda self: self._get("so0t"))
+    so1c = property(lambda self: self._get("so1c"))
+    so1n = property(lambda self: self._get("so1n"))
+    stm = property(lambda self: self._get("stm"))
+    cflo = property(lambda self: self._get("cflo"))
+    cflc = property(lambda self: self._get("cflc"))
+    gamma = property(lambda self: self._get("gamma"))
 
     # -- coherence ---------------------------------------------------------------------------------
     def _push(self, names=_STATE, force=False):
         if self._resident and not force:
             return
         for n in names:
-            _lib.check(self._lib.scg_md_upload(self._h, ARRAY_IDS[n], _lib.ptr(self._a[n].ndarray)))
+            if n in self._a:
+                _lib.check(self._lib.scg_md_upload(self._h, ARRAY_IDS[n], _lib.ptr(self._a[n].ndarray)))
         # the CE geometry only travels when the caller wrote into it
         for n in _GEOMETRY:
+            if n not in self._a:
+                continue
             cur = self._a[n].ndarray
-            if n in self._geo_seen and not np.array_equal(cur, self._geo_seen[n]):
+            if not np.array_equal(cur, self._geo_seen[n]):
                 _lib.check(self._lib.scg_md_upload(self._h, ARRAY_IDS[n], _lib.ptr(cur)))
                 self._geo_seen[n] = cur.copy()
 
@@ -175,7 +186,8 @@ class EulerCore:
         if self._resident and not force:
             return
         for n in names:
-            _lib.check(self._lib.scg_md_download(self._h, ARRAY_IDS[n], _lib.ptr(self._a[n].ndarray)))
+            if n in self._a:
+                _lib.check(self._lib.scg_md_download(self._h, ARRAY_IDS[n], _lib.ptr(self._a[n].ndarray)))
 
     def resident(self, flag=True):
         """Keep the field on the device between calls (uploads once now)."""
@@ -191,8 +203,14 @@ class EulerCore:
 
     def _swap_host(self):
         a = self._a
-        a["so0c"], a["so0n"] = a["so0n"], a["so0c"]
-        a["so1c"], a["so1n"] = a["so1n"], a["so1c"]
+        for c, n in (("so0c", "so0n"), ("so1c", "so1n")):
+            a[c], a[n] = a[n], a[c]
+
+    def materialise(self, names=_STATE):
+        """Allocate (and fill from the device) the named host arrays now."""
+        for n in names:
+            self._get(n)
+        return self
 
     def _phase(self, phase):
         self._push()
@@ -207,7 +225,8 @@ class EulerCore:
             _raise()
         self._pull(_GEOMETRY, force=True)
         for n in _GEOMETRY:
-            self._geo_seen[n] = self._a[n].ndarray.copy()
+            if n in self._a:
+                self._geo_seen[n] = self._a[n].ndarray.copy()
 
     def init_solution(self, gamma, rho, v, p):
         v = list(v)
@@ -227,6 +246,7 @@ class EulerCore:
         self._pull()
 
     def march_substep(self):
+        self.materialise(("so0c", "so0n", "so1c", "so1n"))
         self._push()
         if self._lib.scg_md_phase(self._h, MD_SUBSTEP):
             _raise()
@@ -235,6 +255,7 @@ class EulerCore:
 
     def update(self):
         # pointer swap on both sides (euler.hpp:123-127): views taken earlier alias the other buffer
+        self.materialise(("so0c", "so0n", "so1c", "so1n"))
         _lib.check(self._lib.scg_md_phase(self._h, MD_UPDATE))
         self._swap_host()
 
