@@ -42,6 +42,9 @@ def build_case_3d(ncell_target, order="morton", kinds="hpt", log=None):
     inlet, outlet, wall = meshgen.boundary_groups(3, mesh.fccnd.body, mesh.fccls.body, mesh.nface, lo, hi)
     dt = 0.05 * h
     svr = EulerCore(mesh, dt, order=order)
+    import os
+    if os.environ.get("SCG_MD_FUSED"):
+        svr.set_fused(int(os.environ["SCG_MD_FUSED"]))
     t3 = time.perf_counter()
     # IC / BC of SURVEY.md 8d config 4: Mach-3 stream, inlet / non-reflective outlet / slip walls
     svr.resident(True)

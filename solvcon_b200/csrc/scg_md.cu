@@ -286,6 +286,288 @@ __global__ void __launch_bounds__(128) md_substep_kernel(MdField const F, MdGeo 
     }
 }
 
+// Split substep, kernel 1: calc_soln -> (raw energy for the ghosts) -> calc_cfl, one thread per cell.
+template <int TYPE>
+__global__ void __launch_bounds__(128) md_solncfl_kernel(MdField const F, MdGeo const G, double * eraw)
+{
+    constexpr int ND = ct_ndim(TYPE);
+    constexpr int NEQ = ND + 2;
+    constexpr int NFC = ct_nfc(TYPE);
+    int32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= G.n) { return; }
+    int64_t const k = G.beg + i;
+    double un[NEQ];
+    cell_soln<TYPE>(F, G, i, un);
+#pragma unroll
+    for (int f = 0; f < NFC; ++f)
+    {
+        int32_t const j = G.nbr[f * int64_t(G.n) + i];
+        if (j >= F.ncell) { eraw[j - F.ncell] = un[NEQ - 1]; }
+    }
+    double cflo, cflc;
+    cell_cfl<TYPE>(F, G, i, un, cflo, cflc);
+    F.cflo[k] = cflo;
+    F.cflc[k] = cflc;
+#pragma unroll
+    for (int e = 0; e < NEQ; ++e) { F.so0n[e * F.S + k] = un[e]; }
+}
+
+// GradientElementTypeGroup tables for run-time lane -> face lookups (0-based local faces)
+__constant__ int8_t c_fge[9][8][3] = {
+    {{0}}, {{0}}, {{0}},
+    /* 3 quadrilateral */ {{0, 1, 0}, {1, 2, 0}, {2, 3, 0}, {3, 0, 0}},
+    /* 4 triangle      */ {{0, 1, 0}, {1, 2, 0}, {2, 0, 0}},
+    /* 5 hexahedron    */ {{1, 2, 4}, {5, 2, 1}, {3, 2, 5}, {4, 2, 3}, {4, 0, 1}, {1, 0, 5}, {5, 0, 3}, {3, 0, 4}},
+    /* 6 tetrahedron   */ {{2, 0, 1}, {1, 0, 3}, {3, 0, 2}, {1, 3, 2}},
+    /* 7 prism         */ {{4, 1, 3}, {2, 1, 4}, {3, 1, 2}, {3, 0, 4}, {4, 0, 2}, {2, 0, 3}},
+    /* 8 pyramid       */ {{0, 4, 1}, {1, 4, 2}, {2, 4, 3}, {3, 4, 0}, {0, 2, 3}, {2, 0, 1}},
+};
+
+// Split substep, kernel 2: calc_dsoln (euler_gradient.cpp:23-130) with a GROUP of NFGE lanes per cell.
+//
+// One thread per cell needs ~200 live doubles here (every FGE gradient must exist before the W-3/4
+// limiter can run), which caps the SM at 8 warps and unrolls into >150 KB of straight-line code that
+// misses the instruction cache.  Instead lane t of a cell's group owns local face t (t < nfc) and
+// gradient element t: faces evaluate the displaced points and the Taylor differences, gradient elements
+// solve their ndim x ndim system for all equations, and everything that the reference sums in a fixed
+// order (centroid, weight totals, the weighted gradient) is parked in shared memory and summed in that
+// same order by whichever lanes need it.  Same operations, same order, same rounding -- just spread
+// over 3..8 lanes, so registers drop to ~1/3 and the code to ~1/8.
+template <int TYPE>
+struct Coop
+{
+    static constexpr int ND = ct_ndim(TYPE);
+    static constexpr int NEQ = ND + 2;
+    static constexpr int NFC = ct_nfc(TYPE);
+    static constexpr int NFGE = ct_nfge(TYPE);
+    static constexpr int GS = NFGE;       // lanes per cell
+    static constexpr int CPW = 32 / GS;   // cells per warp
+    static constexpr int WARPS = 4;
+    // shared-memory map of one cell (doubles)
+    static constexpr int O_GP = 0;                          // [NFC][ND]
+    static constexpr int O_FGE = O_GP + NFC * ND;           // [NFGE][ND+1]: vob, subcnd*vob
+    static constexpr int O_FACE = O_FGE + NFGE * (ND + 1);  // [NFC][ND+NEQ]: idis, udf
+    static constexpr int O_END1 = O_FACE + NFC * (ND + NEQ);
+    static constexpr int O_TERM = 0;                        // [NEQ*ND][NFGE], aliases the above (dead by then)
+    static constexpr int O_END2 = NEQ * ND * NFGE;
+    static constexpr int O_W = (O_END1 > O_END2 ? O_END1 : O_END2); // [NEQ][NFGE]
+    static constexpr int O_SIG = O_W + NEQ * NFGE;          // [NEQ]
+    static constexpr int SZ = (O_SIG + NEQ) | 1;            // odd stride: spreads the cells over the banks
+};
+
+template <int TYPE>
+__global__ void __launch_bounds__(128) md_dsoln_coop_kernel(MdField const F, MdGeo const G)
+{
+    using C = Coop<TYPE>;
+    constexpr int ND = C::ND, NEQ = C::NEQ, NFC = C::NFC, NFGE = C::NFGE, GS = C::GS, CPW = C::CPW;
+    __shared__ double smem[C::WARPS * CPW * C::SZ];
+    int const lane = threadIdx.x & 31;
+    int const warp = threadIdx.x >> 5;
+    int const c = lane / GS;
+    int const t = lane - c * GS;
+    bool const valid = c < CPW;
+    int64_t const n = G.n;
+    int64_t const S = F.S;
+    int64_t icell = (static_cast<int64_t>(blockIdx.x) * C::WARPS + warp) * CPW + (valid ? c : 0);
+    bool const live = valid && icell < n;
+    if (icell >= n) { icell = n - 1; } // idle lanes shadow a real cell: loads stay in range, nothing is stored
+    int64_t const i = icell;
+    int64_t const k = G.beg + i;
+    double * const sm = smem + (warp * CPW + (valid ? c : 0)) * C::SZ;
+    unsigned const FULL = 0xffffffffu;
+
+    double const hdt = F.dt * 0.5;
+    double const cflc = F.cflc[k];
+    double const acfl = fabs(cflc);
+    double const sgm0 = F.sigma0 / acfl;
+    double const tau = F.taumin + acfl * F.tauscale;
+    double const ofg1 = 1.0 / NFGE;
+    bool const is_face = t < NFC;
+    int const f = is_face ? t : 0;
+
+    // ---- phase 1: displaced points of the faces (GradientElement.cpp:166-180)
+    int64_t const j = G.nbr[f * n + i];
+    double gp[ND], jd[ND], icecnd[ND];
+#pragma unroll
+    for (int d = 0; d < ND; ++d)
+    {
+        double const mid = G.cecnd[(f * ND + d) * n + i];
+        double const jce = F.solpt[d * S + j];
+        icecnd[d] = F.solpt[d * S + k];
+        gp[d] = mid + tau * (jce - mid);
+        jd[d] = gp[d] - jce;
+        if (valid && is_face) { sm[C::O_GP + f * ND + d] = gp[d]; }
+    }
+    __syncwarp(FULL);
+
+    // ---- phase 2: centroid of the gradient element (GradientElement.cpp:81-133)
+    double avg[ND];
+#pragma unroll
+    for (int d = 0; d < ND; ++d) { avg[d] = 0.0; }
+#pragma unroll
+    for (int q = 0; q < NFC; ++q)
+    {
+#pragma unroll
+        for (int d = 0; d < ND; ++d) { avg[d] += sm[C::O_GP + q * ND + d]; }
+    }
+#pragma unroll
+    for (int d = 0; d < ND; ++d) { avg[d] /= NFC; }
+    int fl[ND]; // the faces of this lane's gradient element
+#pragma unroll
+    for (int v = 0; v < ND; ++v) { fl[v] = c_fge[TYPE][t][v]; }
+    {
+        double subcnd[ND], dst[ND][ND];
+#pragma unroll
+        for (int d = 0; d < ND; ++d) { subcnd[d] = avg[d]; }
+#pragma unroll
+        for (int v = 0; v < ND; ++v)
+        {
+#pragma unroll
+            for (int d = 0; d < ND; ++d)
+            {
+                double const g = sm[C::O_GP + fl[v] * ND + d];
+                subcnd[d] += g;
+                dst[v][d] = g - avg[d];
+            }
+        }
+#pragma unroll
+        for (int d = 0; d < ND; ++d) { subcnd[d] /= static_cast<double>(ND + 1); }
+        double const vob = det_n<ND>(dst);
+        if (valid)
+        {
+            sm[C::O_FGE + t * (ND + 1)] = vob;
+#pragma unroll
+            for (int d = 0; d < ND; ++d) { sm[C::O_FGE + t * (ND + 1) + 1 + d] = subcnd[d] * vob; }
+        }
+    }
+    __syncwarp(FULL);
+    double cnd[ND];
+    {
+        double voc = 0.0;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) { cnd[d] = 0.0; }
+#pragma unroll
+        for (int q = 0; q < NFGE; ++q)
+        {
+            voc += sm[C::O_FGE + q * (ND + 1)];
+#pragma unroll
+            for (int d = 0; d < ND; ++d) { cnd[d] += sm[C::O_FGE + q * (ND + 1) + 1 + d]; }
+        }
+#pragma unroll
+        for (int d = 0; d < ND; ++d) { cnd[d] /= voc; }
+    }
+
+    // ---- phase 3: per-face displacement and Taylor difference (euler_gradient.cpp:60-72)
+    {
+        double jdis[ND];
+#pragma unroll
+        for (int d = 0; d < ND; ++d)
+        {
+            double const idis = gp[d] - cnd[d];
+            jdis[d] = jd[d] + icecnd[d] - cnd[d];
+            if (valid && is_face) { sm[C::O_FACE + f * (ND + NEQ) + d] = idis; }
+        }
+#pragma unroll
+        for (int e = 0; e < NEQ; ++e)
+        {
+            double val = F.so0c[e * S + j] + hdt * F.so0t[e * S + j] - F.so0n[e * S + k];
+#pragma unroll
+            for (int d = 0; d < ND; ++d) { val += jdis[d] * F.so1c[(e * ND + d) * S + j]; }
+            if (valid && is_face) { sm[C::O_FACE + f * (ND + NEQ) + ND + e] = val; }
+        }
+    }
+    __syncwarp(FULL);
+
+    // ---- phase 4: this lane's gradient element: adj(D), det(D), gradients and W-1/2 weights
+    double grad[NEQ][ND], w[NEQ];
+    {
+        double dst[ND][ND], adj[ND][ND];
+#pragma unroll
+        for (int v = 0; v < ND; ++v)
+        {
+#pragma unroll
+            for (int d = 0; d < ND; ++d) { dst[v][d] = sm[C::O_FACE + fl[v] * (ND + NEQ) + d]; }
+        }
+        adj_n<ND>(dst, adj);
+        double const det = det_n<ND>(dst);
+#pragma unroll
+        for (int e = 0; e < NEQ; ++e)
+        {
+            double u[ND];
+#pragma unroll
+            for (int b = 0; b < ND; ++b) { u[b] = sm[C::O_FACE + fl[b] * (ND + NEQ) + ND + e]; }
+            double sq = 0.0;
+#pragma unroll
+            for (int a = 0; a < ND; ++a)
+            {
+                double r = 0.0;
+#pragma unroll
+                for (int b = 0; b < ND; ++b) { r += adj[a][b] * u[b]; }
+                grad[e][a] = r / det;
+            }
+#pragma unroll
+            for (int d = 0; d < ND; ++d) { sq += grad[e][d] * grad[e][d]; }
+            w[e] = 1.0 / sqrt(sq + MD_ALMOST_ZERO);
+            if (valid) { sm[C::O_W + e * NFGE + t] = w[e]; }
+        }
+    }
+    __syncwarp(FULL);
+    // weight totals in FGE order, then this lane's normalised weights (euler_gradient.cpp:90-100)
+#pragma unroll
+    for (int e = 0; e < NEQ; ++e)
+    {
+        double wacc = 0.0;
+#pragma unroll
+        for (int q = 0; q < NFGE; ++q) { wacc += sm[C::O_W + e * NFGE + q]; }
+        w[e] = w[e] / wacc - ofg1;
+    }
+    __syncwarp(FULL);
+    if (valid)
+    {
+#pragma unroll
+        for (int e = 0; e < NEQ; ++e) { sm[C::O_W + e * NFGE + t] = w[e]; }
+    }
+    __syncwarp(FULL);
+
+    // ---- phase 5: W-3/4 limiter, one lane per equation (euler_gradient.cpp:101-110)
+    for (int e = t; e < NEQ; e += GS)
+    {
+        double wmax = 0.0, wmin = 0.0;
+#pragma unroll
+        for (int q = 0; q < NFGE; ++q)
+        {
+            double const wq = sm[C::O_W + e * NFGE + q];
+            wmax = fmax(wmax, wq);
+            wmin = fmin(wmin, wq);
+        }
+        double const smx = fmin((1.0 - ofg1) / (wmax + MD_ALMOST_ZERO), -ofg1 / (wmin - MD_ALMOST_ZERO));
+        if (valid) { sm[C::O_SIG + e] = fmin(smx, sgm0); }
+    }
+    __syncwarp(FULL);
+
+    // ---- phase 6: weighted gradients of this lane's element (euler_gradient.cpp:112-128)
+    if (valid)
+    {
+#pragma unroll
+        for (int e = 0; e < NEQ; ++e)
+        {
+            double const wgt = ofg1 + sm[C::O_SIG + e] * w[e];
+#pragma unroll
+            for (int d = 0; d < ND; ++d) { sm[C::O_TERM + (e * ND + d) * NFGE + t] = wgt * grad[e][d]; }
+        }
+    }
+    __syncwarp(FULL);
+
+    // ---- phase 7: sum over the elements in FGE order and store so1n
+    for (int q = t; q < NEQ * ND; q += GS)
+    {
+        double o = 0.0;
+#pragma unroll
+        for (int r = 0; r < NFGE; ++r) { o += sm[C::O_TERM + q * NFGE + r]; }
+        if (live) { F.so1n[q * S + k] = o; }
+    }
+}
+
 // ================================================================================================
 // boundary conditions: one thread per (deduplicated) boundary face
 // ================================================================================================
@@ -656,7 +938,7 @@ struct scg_md
     int cur = 0;                                               // so0[cur] is so0c, so0[1-cur] is so0n
     DevBuf<double> so0[2], so1[2], so0t, gamma, cflo, cflc, solpt, geo, eraw, stage, red, clvol;
     bool have_clvol = false;
-    bool fused = true;
+    int fused = 2; // 0: one kernel per reference phase, 1: one fused thread-per-cell kernel, 2: soln+cfl kernel + cooperative dsoln kernel
     std::vector<BcReg> regs;
     bool bc_dirty = true;
     int32_t nbc = 0;
@@ -721,6 +1003,8 @@ enum CellPhase
     CP_CFL,
     CP_DSOLN,
     CP_SUBSTEP,
+    CP_SOLNCFL,
+    CP_DSOLN_COOP,
 };
 
 template <int TYPE>
@@ -749,6 +1033,13 @@ void launch_cell_phase_t(scg_md * s, MeshGroup const & g, CellPhase ph)
     case CP_CFL: md_cfl_kernel<TYPE><<<grid, 128, 0, stream()>>>(F, G); break;
     case CP_DSOLN: md_dsoln_kernel<TYPE><<<grid, 128, 0, stream()>>>(F, G); break;
     case CP_SUBSTEP: md_substep_kernel<TYPE><<<grid, 128, 0, stream()>>>(F, G, s->eraw.p); break;
+    case CP_SOLNCFL: md_solncfl_kernel<TYPE><<<grid, 128, 0, stream()>>>(F, G, s->eraw.p); break;
+    case CP_DSOLN_COOP:
+    {
+        int64_t const cells_per_block = int64_t(Coop<TYPE>::WARPS) * Coop<TYPE>::CPW;
+        md_dsoln_coop_kernel<TYPE><<<static_cast<unsigned>(ceil_div(g.n, cells_per_block)), 128, 0, stream()>>>(F, G);
+        break;
+    }
     }
     count_launch();
 }
@@ -913,7 +1204,13 @@ int substep(scg_md * s)
 {
     s->cur ^= 1; // update(): swap so0c<->so0n, so1c<->so1n (euler.hpp:123-127)
     launch_solt(s);
-    if (s->fused)
+    if (2 == s->fused)
+    {
+        launch_cell_phase(s, CP_SOLNCFL);
+        if (int rc = launch_bc_soln(s, true)) { return rc; }
+        launch_cell_phase(s, CP_DSOLN_COOP);
+    }
+    else if (1 == s->fused)
     {
         launch_cell_phase(s, CP_SUBSTEP);
         if (int rc = launch_bc_soln(s, true)) { return rc; }
@@ -1082,7 +1379,8 @@ int scg_md_set_time_increment(scg_md * s, double time_increment)
 int scg_md_set_fused(scg_md * s, int fused)
 {
     SCG_REQUIRE(s, "scg_md_set_fused: null solver");
-    s->fused = fused != 0;
+    SCG_REQUIRE(fused >= 0 && fused <= 2, "scg_md_set_fused: mode must be 0, 1 or 2");
+    s->fused = fused;
     return 0;
 }
 

@@ -308,9 +308,10 @@ class EulerCore:
         return out.tolist()
 
     # -- additive API -----------------------------------------------------------------------------------
-    def set_fused(self, flag):
-        """march() with the fused soln+cfl+dsoln kernel (default) or one kernel per reference phase."""
-        _lib.check(self._lib.scg_md_set_fused(self._h, int(bool(flag))))
+    def set_fused(self, mode):
+        """march() kernels: 2 (default) soln+cfl kernel + cooperative dsoln kernel, 1 one fused
+        thread-per-cell kernel, 0 one kernel per reference phase (bit-identical results)."""
+        _lib.check(self._lib.scg_md_set_fused(self._h, int(mode)))
 
     def reduce(self, clvol=None):
         """(cflo.min, cflo.max, sum(density*clvol)) over body cells on the device -- the callers' numpy

@@ -91,9 +91,9 @@ def test_md_geometry_and_phases(gpu, bridge, name):
     assert np.abs(c.dev.so1n.body).max() > 1e-3
 
 
-@pytest.mark.parametrize("name", ["mixed2d", "step2d", "mixed3d", "hex3d"])
+@pytest.mark.parametrize("name", ["mixed2d", "step2d", "mixed3d", "hex3d", "tet3d", "prism3d", "tri2d"])
 @pytest.mark.parametrize("order", ["none", "morton", "rcm"])
-@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("fused", [2, 1, 0])
 def test_md_march_matches(gpu, bridge, name, order, fused):
     """march(N) with every cell ordering, fused and per-phase kernels: identical to the checker."""
     b = bridge
