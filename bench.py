@@ -266,7 +266,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--workload", default=os.environ.get("SCG_BENCH_WORKLOAD", "e1d"))
+    ap.add_argument("--workload", default=os.environ.get("SCG_BENCH_WORKLOAD", "md3d"))
     ap.add_argument("--size", type=int, default=0, help="points / cells per GPU (0 = workload default)")
     ap.add_argument("--chunk", type=int, default=5, help="time steps per march() call (one bench step)")
     ap.add_argument("--order", default="morton", help="multidim cell ordering: none | morton | rcm")

@@ -21,6 +21,8 @@ I64P = C.POINTER(C.c_int64)
 def lib_path(strict: bool | None = None) -> str:
     """Path of the device library.  ``SCG_STRICT_FP=0`` selects the FMA-contracted speed
     variant (``libscg_cuda_fma.so``); the default is the bit-parity build."""
+    if os.environ.get("SCG_LIB"):
+        return os.path.join(HERE, os.environ["SCG_LIB"])
     if strict is None:
         strict = os.environ.get("SCG_STRICT_FP", "1") != "0"
     return os.path.join(HERE, "libscg_cuda.so" if strict else "libscg_cuda_fma.so")

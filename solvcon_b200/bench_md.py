@@ -67,7 +67,7 @@ def build_case_3d(ncell_target, order="morton", kinds="hpt", log=None):
 class MD3DWorkload:
     name = "md3d"
     dtype = "f64"
-    dominant_kernel = "md_substep_kernel<hex|prism|tet> (+ md_solt_kernel, boundary kernels: one substep)"
+    dominant_kernel = "one substep = md_solt + md_solncfl<hex|prism|tet> + md_dsoln_coop<hex|prism|tet> + boundary kernels"
 
     def __init__(self, ncell, chunk, order="morton", kinds="hpt"):
         self.ncell_target = int(ncell)

@@ -52,6 +52,10 @@ def build(force=False, fma_variant=True, verbose=False):
     variants = [("libscg_cuda.so", "strict", ["-fmad=false", "-DSCG_STRICT_FP"])]
     if fma_variant:
         variants.append(("libscg_cuda_fma.so", "fma", ["-fmad=true"]))
+    # experiment variants: SCG_EXTRA_VARIANTS="tag:-DFOO=1 -DBAR=2;tag2:..." -> libscg_cuda_<tag>.so (strict)
+    for spec in filter(None, os.environ.get("SCG_EXTRA_VARIANTS", "").split(";")):
+        tag, _, fl = spec.partition(":")
+        variants.append((f"libscg_cuda_{tag}.so", tag, ["-fmad=false", "-DSCG_STRICT_FP"] + fl.split()))
     jobs, built = [], []
     for name, tag, flags in variants:
         for s in SOURCES:

@@ -287,8 +287,11 @@ __global__ void __launch_bounds__(128) md_substep_kernel(MdField const F, MdGeo 
 }
 
 // Split substep, kernel 1: calc_soln -> (raw energy for the ghosts) -> calc_cfl, one thread per cell.
+#ifndef SCG_SOLN_MINBLOCKS
+#define SCG_SOLN_MINBLOCKS 3
+#endif
 template <int TYPE>
-__global__ void __launch_bounds__(128) md_solncfl_kernel(MdField const F, MdGeo const G, double * eraw)
+__global__ void __launch_bounds__(128, SCG_SOLN_MINBLOCKS) md_solncfl_kernel(MdField const F, MdGeo const G, double * eraw)
 {
     constexpr int ND = ct_ndim(TYPE);
     constexpr int NEQ = ND + 2;
@@ -344,14 +347,19 @@ struct Coop
     static constexpr int CPW = 32 / GS;   // cells per warp
     static constexpr int WARPS = 4;
     // shared-memory map of one cell (doubles)
+    // row strides are odd so that the lanes of a group (one row each) fall into different banks
+    static constexpr int R_FGE = (ND + 1) | 1;              // vob, subcnd*vob
+    static constexpr int R_FACE = (ND + NEQ) | 1;           // idis, udf
+    static constexpr int R_TERM = NFGE | 1;
+    static constexpr int R_W = NFGE | 1;
     static constexpr int O_GP = 0;                          // [NFC][ND]
-    static constexpr int O_FGE = O_GP + NFC * ND;           // [NFGE][ND+1]: vob, subcnd*vob
-    static constexpr int O_FACE = O_FGE + NFGE * (ND + 1);  // [NFC][ND+NEQ]: idis, udf
-    static constexpr int O_END1 = O_FACE + NFC * (ND + NEQ);
-    static constexpr int O_TERM = 0;                        // [NEQ*ND][NFGE], aliases the above (dead by then)
-    static constexpr int O_END2 = NEQ * ND * NFGE;
-    static constexpr int O_W = (O_END1 > O_END2 ? O_END1 : O_END2); // [NEQ][NFGE]
-    static constexpr int O_SIG = O_W + NEQ * NFGE;          // [NEQ]
+    static constexpr int O_FGE = O_GP + NFC * ND;           // [NFGE][R_FGE]
+    static constexpr int O_FACE = O_FGE + NFGE * R_FGE;     // [NFC][R_FACE]
+    static constexpr int O_END1 = O_FACE + NFC * R_FACE;
+    static constexpr int O_TERM = 0;                        // [NEQ*ND][R_TERM], aliases the above (dead by then)
+    static constexpr int O_END2 = NEQ * ND * R_TERM;
+    static constexpr int O_W = (O_END1 > O_END2 ? O_END1 : O_END2); // [NEQ][R_W]
+    static constexpr int O_SIG = O_W + NEQ * R_W;           // [NEQ]
     static constexpr int SZ = (O_SIG + NEQ) | 1;            // odd stride: spreads the cells over the banks
 };
 
@@ -387,6 +395,15 @@ __global__ void __launch_bounds__(128) md_dsoln_coop_kernel(MdField const F, MdG
 
     // ---- phase 1: displaced points of the faces (GradientElement.cpp:166-180)
     int64_t const j = G.nbr[f * n + i];
+    // the neighbour state is needed in phase 3; start pulling it towards the SM now
+#pragma unroll
+    for (int e = 0; e < NEQ; ++e)
+    {
+        prefetch_l1(&F.so0c[e * S + j]);
+        prefetch_l1(&F.so0t[e * S + j]);
+#pragma unroll
+        for (int d = 0; d < ND; ++d) { prefetch_l1(&F.so1c[(e * ND + d) * S + j]); }
+    }
     double gp[ND], jd[ND], icecnd[ND];
 #pragma unroll
     for (int d = 0; d < ND; ++d)
@@ -435,9 +452,9 @@ __global__ void __launch_bounds__(128) md_dsoln_coop_kernel(MdField const F, MdG
         double const vob = det_n<ND>(dst);
         if (valid)
         {
-            sm[C::O_FGE + t * (ND + 1)] = vob;
+            sm[C::O_FGE + t * C::R_FGE] = vob;
 #pragma unroll
-            for (int d = 0; d < ND; ++d) { sm[C::O_FGE + t * (ND + 1) + 1 + d] = subcnd[d] * vob; }
+            for (int d = 0; d < ND; ++d) { sm[C::O_FGE + t * C::R_FGE + 1 + d] = subcnd[d] * vob; }
         }
     }
     __syncwarp(FULL);
@@ -449,9 +466,9 @@ __global__ void __launch_bounds__(128) md_dsoln_coop_kernel(MdField const F, MdG
 #pragma unroll
         for (int q = 0; q < NFGE; ++q)
         {
-            voc += sm[C::O_FGE + q * (ND + 1)];
+            voc += sm[C::O_FGE + q * C::R_FGE];
 #pragma unroll
-            for (int d = 0; d < ND; ++d) { cnd[d] += sm[C::O_FGE + q * (ND + 1) + 1 + d]; }
+            for (int d = 0; d < ND; ++d) { cnd[d] += sm[C::O_FGE + q * C::R_FGE + 1 + d]; }
         }
 #pragma unroll
         for (int d = 0; d < ND; ++d) { cnd[d] /= voc; }
@@ -465,7 +482,7 @@ __global__ void __launch_bounds__(128) md_dsoln_coop_kernel(MdField const F, MdG
         {
             double const idis = gp[d] - cnd[d];
             jdis[d] = jd[d] + icecnd[d] - cnd[d];
-            if (valid && is_face) { sm[C::O_FACE + f * (ND + NEQ) + d] = idis; }
+            if (valid && is_face) { sm[C::O_FACE + f * C::R_FACE + d] = idis; }
         }
 #pragma unroll
         for (int e = 0; e < NEQ; ++e)
@@ -473,7 +490,7 @@ __global__ void __launch_bounds__(128) md_dsoln_coop_kernel(MdField const F, MdG
             double val = F.so0c[e * S + j] + hdt * F.so0t[e * S + j] - F.so0n[e * S + k];
 #pragma unroll
             for (int d = 0; d < ND; ++d) { val += jdis[d] * F.so1c[(e * ND + d) * S + j]; }
-            if (valid && is_face) { sm[C::O_FACE + f * (ND + NEQ) + ND + e] = val; }
+            if (valid && is_face) { sm[C::O_FACE + f * C::R_FACE + ND + e] = val; }
         }
     }
     __syncwarp(FULL);
@@ -486,7 +503,7 @@ __global__ void __launch_bounds__(128) md_dsoln_coop_kernel(MdField const F, MdG
         for (int v = 0; v < ND; ++v)
         {
 #pragma unroll
-            for (int d = 0; d < ND; ++d) { dst[v][d] = sm[C::O_FACE + fl[v] * (ND + NEQ) + d]; }
+            for (int d = 0; d < ND; ++d) { dst[v][d] = sm[C::O_FACE + fl[v] * C::R_FACE + d]; }
         }
         adj_n<ND>(dst, adj);
         double const det = det_n<ND>(dst);
@@ -495,7 +512,7 @@ __global__ void __launch_bounds__(128) md_dsoln_coop_kernel(MdField const F, MdG
         {
             double u[ND];
 #pragma unroll
-            for (int b = 0; b < ND; ++b) { u[b] = sm[C::O_FACE + fl[b] * (ND + NEQ) + ND + e]; }
+            for (int b = 0; b < ND; ++b) { u[b] = sm[C::O_FACE + fl[b] * C::R_FACE + ND + e]; }
             double sq = 0.0;
 #pragma unroll
             for (int a = 0; a < ND; ++a)
@@ -508,7 +525,7 @@ __global__ void __launch_bounds__(128) md_dsoln_coop_kernel(MdField const F, MdG
 #pragma unroll
             for (int d = 0; d < ND; ++d) { sq += grad[e][d] * grad[e][d]; }
             w[e] = 1.0 / sqrt(sq + MD_ALMOST_ZERO);
-            if (valid) { sm[C::O_W + e * NFGE + t] = w[e]; }
+            if (valid) { sm[C::O_W + e * C::R_W + t] = w[e]; }
         }
     }
     __syncwarp(FULL);
@@ -518,14 +535,14 @@ __global__ void __launch_bounds__(128) md_dsoln_coop_kernel(MdField const F, MdG
     {
         double wacc = 0.0;
 #pragma unroll
-        for (int q = 0; q < NFGE; ++q) { wacc += sm[C::O_W + e * NFGE + q]; }
+        for (int q = 0; q < NFGE; ++q) { wacc += sm[C::O_W + e * C::R_W + q]; }
         w[e] = w[e] / wacc - ofg1;
     }
     __syncwarp(FULL);
     if (valid)
     {
 #pragma unroll
-        for (int e = 0; e < NEQ; ++e) { sm[C::O_W + e * NFGE + t] = w[e]; }
+        for (int e = 0; e < NEQ; ++e) { sm[C::O_W + e * C::R_W + t] = w[e]; }
     }
     __syncwarp(FULL);
 
@@ -536,7 +553,7 @@ __global__ void __launch_bounds__(128) md_dsoln_coop_kernel(MdField const F, MdG
 #pragma unroll
         for (int q = 0; q < NFGE; ++q)
         {
-            double const wq = sm[C::O_W + e * NFGE + q];
+            double const wq = sm[C::O_W + e * C::R_W + q];
             wmax = fmax(wmax, wq);
             wmin = fmin(wmin, wq);
         }
@@ -553,7 +570,7 @@ __global__ void __launch_bounds__(128) md_dsoln_coop_kernel(MdField const F, MdG
         {
             double const wgt = ofg1 + sm[C::O_SIG + e] * w[e];
 #pragma unroll
-            for (int d = 0; d < ND; ++d) { sm[C::O_TERM + (e * ND + d) * NFGE + t] = wgt * grad[e][d]; }
+            for (int d = 0; d < ND; ++d) { sm[C::O_TERM + (e * ND + d) * C::R_TERM + t] = wgt * grad[e][d]; }
         }
     }
     __syncwarp(FULL);
@@ -563,7 +580,7 @@ __global__ void __launch_bounds__(128) md_dsoln_coop_kernel(MdField const F, MdG
     {
         double o = 0.0;
 #pragma unroll
-        for (int r = 0; r < NFGE; ++r) { o += sm[C::O_TERM + q * NFGE + r]; }
+        for (int r = 0; r < NFGE; ++r) { o += sm[C::O_TERM + q * C::R_TERM + r]; }
         if (live) { F.so1n[q * S + k] = o; }
     }
 }

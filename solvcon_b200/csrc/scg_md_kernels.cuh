@@ -52,6 +52,14 @@ struct MdGeo // one cell-type group
     int32_t n;
 };
 
+// L1 / L2 prefetch of one address per lane (no register is tied up while the line is in flight)
+__device__ __forceinline__ void prefetch_l1(void const * p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(void const * p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+#ifndef SCG_SOLN_PREFETCH
+#define SCG_SOLN_PREFETCH 0
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // flux function and Jacobian, detail::EulerJacobian<2>/<3>::update (euler_march.cpp:35-81, 94-157)
 // ------------------------------------------------------------------------------------------------
@@ -278,10 +286,38 @@ __device__ __forceinline__ void cell_soln(MdField const & F, MdGeo const & G, in
 #pragma unroll
     for (int e = 0; e < NEQ; ++e) { acc[e] = 0.0; }
 
+    int64_t jnext = G.nbr[i];
 #pragma unroll 1
     for (int f = 0; f < NFC; ++f)
     {
-        int64_t const j = G.nbr[f * n + i];
+        int64_t const j = jnext;
+#if SCG_SOLN_PREFETCH
+        // The loop body is long (a Jacobian and up to four sub-face flux evaluations) and only a few
+        // warps fit on an SM, so the next face's neighbour gather and geometry are pulled towards the
+        // SM now and hit the cache when the next iteration asks for them.
+        if (f + 1 < NFC)
+        {
+            jnext = G.nbr[(f + 1) * n + i];
+#pragma unroll
+            for (int e = 0; e < NEQ; ++e)
+            {
+                prefetch_l1(&F.so0c[e * S + jnext]);
+                prefetch_l1(&F.so0t[e * S + jnext]);
+#pragma unroll
+                for (int d = 0; d < ND; ++d) { prefetch_l1(&F.so1c[(e * ND + d) * S + jnext]); }
+            }
+            prefetch_l1(&F.gamma[jnext]);
+#pragma unroll
+            for (int d = 0; d < ND; ++d)
+            {
+                prefetch_l1(&F.solpt[d * S + jnext]);
+                prefetch_l1(&G.cecnd[((f + 1) * ND + d) * n + i]);
+            }
+            prefetch_l1(&G.cevol[(f + 2) * n + i]);
+        }
+#else
+        if (f + 1 < NFC) { jnext = G.nbr[(f + 1) * n + i]; }
+#endif
         double jc[ND], bc[ND];
 #pragma unroll
         for (int d = 0; d < ND; ++d)
