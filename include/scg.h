@@ -52,6 +52,10 @@ SCG_API int scg_flush_l2(int64_t bytes);
 /* pinned host memory for the end-to-end path */
 SCG_API int scg_host_alloc(void ** ptr, int64_t bytes);
 SCG_API int scg_host_free(void * ptr);
+/* raw device scratch and an async copy on the library stream (halo staging between partitions) */
+SCG_API int scg_dev_alloc(void ** ptr, int64_t bytes);
+SCG_API int scg_dev_free(void * ptr);
+SCG_API int scg_dev_copy(void * dst, const void * src, int64_t bytes);
 
 /* --------------------------------------------------------------- 1D scalar
  * replaces spacetime::SolverBase<...> for LinearScalar / InviscidBurgers
@@ -156,6 +160,16 @@ SCG_API int scg_mesh_create(scg_mesh ** out, int ndim,
                             const int32_t * cltpn, const int32_t * clfcs, const int32_t * fccls,
                             const int32_t * fcnds, const double * ndcrd, const double * fccnd,
                             const double * fcnml, const double * clcnd, int order);
+/* The mesh of one PARTITION (domain decomposition, one process per GPU): as above plus owned[ncell]
+ * (1 = this partition updates the cell, 0 = halo copy of a cell owned by another partition, refreshed by
+ * scg_md_halo_unpack).  Halo copies are ordinary body cells of the local StaticMesh; they are stored
+ * after the owned cells of their type group and skipped by the march kernels.  owned may be NULL. */
+SCG_API int scg_mesh_create_part(scg_mesh ** out, int ndim,
+                                 int64_t nnode, int64_t nface, int64_t ncell,
+                                 int64_t ngstnode, int64_t ngstface, int64_t ngstcell,
+                                 const int32_t * cltpn, const int32_t * clfcs, const int32_t * fccls,
+                                 const int32_t * fcnds, const double * ndcrd, const double * fccnd,
+                                 const double * fcnml, const double * clcnd, int order, const int8_t * owned);
 SCG_API int scg_mesh_destroy(scg_mesh * m);
 /* device order <-> reference order permutation: perm[k] = reference cell id stored at device slot k */
 SCG_API int scg_mesh_perm(scg_mesh * m, int32_t * perm /* ncell */);
@@ -217,14 +231,14 @@ SCG_API int scg_md_algorithmic_bytes(scg_md * s, int64_t * bytes_per_substep);
 SCG_API int scg_md_normal_matrix(scg_md * s, int32_t ifc, double * out);
 
 /* halo exchange support for domain decomposition (one process per GPU; the caller moves the packed
- * buffers with NCCL send/recv, see solvcon_b200/decomp.py).  A partition is a StaticMesh of the owned
- * cells whose interface faces are boundary faces; the ghost cell of an interface face is the HALO copy
- * of the remote neighbour.  send_cells are local reference cell ids, recv_ghosts local ghost indices g
- * (reference index -(g+1)).  what = 0: the new state so0n+so1n, neq*(1+ndim) doubles per cell, every
- * substep;  what = 1: solution point + gamma, ndim+1 doubles per cell, once at setup (the halo's
- * solution point is the remote CE centroid, euler_march.cpp:229-234, not the mirrored centroid).
- * Buffers are component-major: buf[c * ncells + i]. */
-SCG_API int scg_md_halo_set(scg_md * s, const int32_t * send_cells, int64_t nsend, const int32_t * recv_ghosts, int64_t nrecv);
+ * buffers with NCCL send/recv, see solvcon_b200/decomp.py).  A partition is a StaticMesh of the owned cells
+ * plus one layer of HALO copies of the remote face neighbours (scg_mesh_create_part).  send_cells /
+ * recv_cells are local reference cell ids, in the order both sides agreed on.  what = 0: the new state
+ * so0n+so1n, neq*(1+ndim) doubles per cell, after every substep;  what = 1: solution point + gamma,
+ * ndim+1 doubles per cell, once at setup (a halo copy's CE centroid cannot be computed locally: its own
+ * outer neighbours are missing).  Buffers are cell-major, buf[i * width + c], so the cells of one neighbour
+ * rank (a contiguous range of the lists) form one contiguous message. */
+SCG_API int scg_md_halo_set(scg_md * s, const int32_t * send_cells, int64_t nsend, const int32_t * recv_cells, int64_t nrecv);
 SCG_API int scg_md_halo_pack(scg_md * s, int what, double ** dev_buffer, int64_t * ndouble);
 SCG_API int scg_md_halo_unpack(scg_md * s, int what, const double * dev_buffer);
 

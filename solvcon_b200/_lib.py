@@ -47,6 +47,9 @@ _SIGNATURES = {
     "scg_flush_l2": (C.c_int, [C.c_int64]),
     "scg_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
     "scg_host_free": (C.c_int, [C.c_void_p]),
+    "scg_dev_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
+    "scg_dev_free": (C.c_int, [C.c_void_p]),
+    "scg_dev_copy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     # 1D scalar
     "scg_st_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int64, C.c_double]),
     "scg_st_destroy": (C.c_int, [C.c_void_p]),
@@ -83,6 +86,9 @@ _SIGNATURES = {
     "scg_mesh_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                    C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "scg_mesh_create_part": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                                        C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "scg_mesh_destroy": (C.c_int, [C.c_void_p]),
     "scg_mesh_perm": (C.c_int, [C.c_void_p, C.c_void_p]),
     "scg_md_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_double]),

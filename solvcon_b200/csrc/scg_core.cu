@@ -193,6 +193,26 @@ int scg_host_alloc(void ** ptr, int64_t bytes)
     return 0;
 }
 
+int scg_dev_alloc(void ** ptr, int64_t bytes)
+{
+    if (int rc = ensure_init()) { return rc; }
+    SCG_CUDA(cudaMalloc(ptr, static_cast<size_t>(bytes > 0 ? bytes : 1)));
+    return 0;
+}
+
+int scg_dev_free(void * ptr)
+{
+    if (ptr) { SCG_CUDA(cudaFree(ptr)); }
+    return 0;
+}
+
+int scg_dev_copy(void * dst, const void * src, int64_t bytes)
+{
+    if (int rc = ensure_init()) { return rc; }
+    SCG_CUDA(cudaMemcpyAsync(dst, src, static_cast<size_t>(bytes), cudaMemcpyDefault, g_stream));
+    return 0;
+}
+
 int scg_host_free(void * ptr)
 {
     if (ptr) { SCG_CUDA(cudaFreeHost(ptr)); }

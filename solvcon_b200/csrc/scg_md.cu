@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(128) md_soln_kernel(MdField const F, MdGeo con
 {
     constexpr int NEQ = ct_ndim(TYPE) + 2;
     int32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= G.n) { return; }
+    if (i >= G.nact) { return; }
     double un[NEQ];
     cell_soln<TYPE>(F, G, i, un);
     int64_t const k = G.beg + i;
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(128) md_cfl_kernel(MdField const F, MdGeo cons
 {
     constexpr int NEQ = ct_ndim(TYPE) + 2;
     int32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= G.n) { return; }
+    if (i >= G.nact) { return; }
     int64_t const k = G.beg + i;
     double un[NEQ];
 #pragma unroll
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(128) md_dsoln_kernel(MdField const F, MdGeo co
     constexpr int ND = ct_ndim(TYPE);
     constexpr int NEQ = ND + 2;
     int32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= G.n) { return; }
+    if (i >= G.nact) { return; }
     int64_t const k = G.beg + i;
     double un[NEQ];
 #pragma unroll
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(128) md_substep_kernel(MdField const F, MdGeo 
     constexpr int NEQ = ND + 2;
     constexpr int NFC = ct_nfc(TYPE);
     int32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= G.n) { return; }
+    if (i >= G.nact) { return; }
     int64_t const k = G.beg + i;
     int64_t const S = F.S;
     double un[NEQ];
@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(128, SCG_SOLN_MINBLOCKS) md_solncfl_kernel(MdF
     constexpr int NEQ = ND + 2;
     constexpr int NFC = ct_nfc(TYPE);
     int32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= G.n) { return; }
+    if (i >= G.nact) { return; }
     int64_t const k = G.beg + i;
     double un[NEQ];
     cell_soln<TYPE>(F, G, i, un);
@@ -377,8 +377,8 @@ __global__ void __launch_bounds__(128) md_dsoln_coop_kernel(MdField const F, MdG
     int64_t const n = G.n;
     int64_t const S = F.S;
     int64_t icell = (static_cast<int64_t>(blockIdx.x) * C::WARPS + warp) * CPW + (valid ? c : 0);
-    bool const live = valid && icell < n;
-    if (icell >= n) { icell = n - 1; } // idle lanes shadow a real cell: loads stay in range, nothing is stored
+    bool const live = valid && icell < G.nact;
+    if (icell >= G.nact) { icell = G.nact - 1; } // idle lanes shadow a real cell: loads stay in range, nothing is stored
     int64_t const i = icell;
     int64_t const k = G.beg + i;
     double * const sm = smem + (warp * CPW + (valid ? c : 0)) * C::SZ;
@@ -908,13 +908,15 @@ __global__ void md_halo_pack_kernel(double const * so0, double const * so1, doub
     int64_t const k = cells[t];
     if (0 == what)
     {
-        for (int e = 0; e < neq; ++e) { buf[e * ncells + t] = so0[e * S + k]; }
-        for (int c = 0; c < neq * ndim; ++c) { buf[(neq + c) * ncells + t] = so1[c * S + k]; }
+        int64_t const w = neq * (1 + ndim);
+        for (int e = 0; e < neq; ++e) { buf[t * w + e] = so0[e * S + k]; }
+        for (int c = 0; c < neq * ndim; ++c) { buf[t * w + neq + c] = so1[c * S + k]; }
     }
     else
     {
-        for (int d = 0; d < ndim; ++d) { buf[d * ncells + t] = solpt[d * S + k]; }
-        buf[ndim * ncells + t] = gamma[k];
+        int64_t const w = ndim + 1;
+        for (int d = 0; d < ndim; ++d) { buf[t * w + d] = solpt[d * S + k]; }
+        buf[t * w + ndim] = gamma[k];
     }
 }
 
@@ -926,13 +928,15 @@ __global__ void md_halo_unpack_kernel(double * so0, double * so1, double * solpt
     int64_t const k = ghosts[t];
     if (0 == what)
     {
-        for (int e = 0; e < neq; ++e) { so0[e * S + k] = buf[e * nghost + t]; }
-        for (int c = 0; c < neq * ndim; ++c) { so1[c * S + k] = buf[(neq + c) * nghost + t]; }
+        int64_t const w = neq * (1 + ndim);
+        for (int e = 0; e < neq; ++e) { so0[e * S + k] = buf[t * w + e]; }
+        for (int c = 0; c < neq * ndim; ++c) { so1[c * S + k] = buf[t * w + neq + c]; }
     }
     else
     {
-        for (int d = 0; d < ndim; ++d) { solpt[d * S + k] = buf[d * nghost + t]; }
-        gamma[k] = buf[ndim * nghost + t];
+        int64_t const w = ndim + 1;
+        for (int d = 0; d < ndim; ++d) { solpt[d * S + k] = buf[t * w + d]; }
+        gamma[k] = buf[t * w + ndim];
     }
 }
 
@@ -1002,6 +1006,7 @@ MdGeo geo_of(scg_md * s, MeshGroup const & g)
     G.sfnml = s->geo.p + g.geo_sfnml();
     G.beg = g.beg;
     G.n = g.n;
+    G.nact = g.nact;
     return G;
 }
 
@@ -1029,7 +1034,10 @@ void launch_cell_phase_t(scg_md * s, MeshGroup const & g, CellPhase ph)
 {
     MdField const F = field_of(s);
     MdGeo const G = geo_of(s, g);
-    unsigned const grid = static_cast<unsigned>(ceil_div(g.n, 128));
+    bool const all_cells = (CP_PREPARE == ph);
+    int64_t const ncl = all_cells ? g.n : g.nact;
+    if (0 == ncl) { return; }
+    unsigned const grid = static_cast<unsigned>(ceil_div(ncl, 128));
     switch (ph)
     {
     case CP_PREPARE:
@@ -1054,7 +1062,7 @@ void launch_cell_phase_t(scg_md * s, MeshGroup const & g, CellPhase ph)
     case CP_DSOLN_COOP:
     {
         int64_t const cells_per_block = int64_t(Coop<TYPE>::WARPS) * Coop<TYPE>::CPW;
-        md_dsoln_coop_kernel<TYPE><<<static_cast<unsigned>(ceil_div(g.n, cells_per_block)), 128, 0, stream()>>>(F, G);
+        md_dsoln_coop_kernel<TYPE><<<static_cast<unsigned>(ceil_div(g.nact, cells_per_block)), 128, 0, stream()>>>(F, G);
         break;
     }
     }
@@ -1539,19 +1547,24 @@ int scg_md_reduce(scg_md * s, const double * clvol_host_or_null, double * cfl_mi
         }
         s->have_clvol = true;
     }
-    int const nblk = 592; // 4 CTAs per SM
-    md_reduce_kernel<<<nblk, 256, 0, stream()>>>(s->cflo.p, s->so0[1 - s->cur].p, s->have_clvol ? s->clvol.p : nullptr, m->ncell,
-                                                 s->red.p);
-    count_launch();
-    std::vector<double> h(3 * nblk);
-    SCG_CUDA(cudaMemcpyAsync(h.data(), s->red.p, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, stream()));
-    SCG_CUDA(cudaStreamSynchronize(stream()));
+    // owned cells only, one launch per cell-type group (halo copies hold another partition's cells)
+    int const nblk = 296;
     double mn = DBL_MAX, mx = -DBL_MAX, sm = 0.0;
-    for (int b = 0; b < nblk; ++b)
+    std::vector<double> h(3 * nblk);
+    for (auto const & g : m->groups)
     {
-        mn = h[3 * b] < mn ? h[3 * b] : mn;
-        mx = h[3 * b + 1] > mx ? h[3 * b + 1] : mx;
-        sm += h[3 * b + 2];
+        if (0 == g.nact) { continue; }
+        md_reduce_kernel<<<nblk, 256, 0, stream()>>>(s->cflo.p + g.beg, s->so0[1 - s->cur].p + g.beg,
+                                                     s->have_clvol ? s->clvol.p + g.beg : nullptr, g.nact, s->red.p);
+        count_launch();
+        SCG_CUDA(cudaMemcpyAsync(h.data(), s->red.p, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, stream()));
+        SCG_CUDA(cudaStreamSynchronize(stream()));
+        for (int b = 0; b < nblk; ++b)
+        {
+            mn = h[3 * b] < mn ? h[3 * b] : mn;
+            mx = h[3 * b + 1] > mx ? h[3 * b + 1] : mx;
+            sm += h[3 * b + 2];
+        }
     }
     if (cfl_min) { *cfl_min = mn; }
     if (cfl_max) { *cfl_max = mx; }
@@ -1563,7 +1576,7 @@ int scg_md_algorithmic_bytes(scg_md * s, int64_t * bytes_per_substep)
 {
     SCG_REQUIRE(s && bytes_per_substep, "scg_md_algorithmic_bytes: null argument");
     int64_t b = 0;
-    for (auto const & g : s->mesh->groups) { b += int64_t(ct_balg(g.type)) * g.n; }
+    for (auto const & g : s->mesh->groups) { b += int64_t(ct_balg(g.type)) * g.nact; }
     *bytes_per_substep = b;
     return 0;
 }
@@ -1576,7 +1589,7 @@ int scg_md_normal_matrix(scg_md * s, int32_t ifc, double * out)
     return 0;
 }
 
-int scg_md_halo_set(scg_md * s, const int32_t * send_cells, int64_t nsend, const int32_t * recv_ghosts, int64_t nrecv)
+int scg_md_halo_set(scg_md * s, const int32_t * send_cells, int64_t nsend, const int32_t * recv_cells, int64_t nrecv)
 {
     SCG_REQUIRE(s, "scg_md_halo_set: null solver");
     scg_mesh * m = s->mesh;
@@ -1588,8 +1601,8 @@ int scg_md_halo_set(scg_md * s, const int32_t * send_cells, int64_t nsend, const
     }
     for (int64_t q = 0; q < nrecv; ++q)
     {
-        SCG_REQUIRE(recv_ghosts[q] >= 0 && recv_ghosts[q] < m->ngstcell, "scg_md_halo_set: ghost %d out of range", recv_ghosts[q]);
-        rcv[q] = static_cast<int32_t>(m->ncell + recv_ghosts[q]);
+        SCG_REQUIRE(recv_cells[q] >= 0 && recv_cells[q] < m->ncell, "scg_md_halo_set: halo cell %d out of range", recv_cells[q]);
+        rcv[q] = m->iperm[recv_cells[q]];
     }
     s->nsend = nsend;
     s->nrecv = nrecv;

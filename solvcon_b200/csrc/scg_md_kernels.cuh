@@ -49,7 +49,8 @@ struct MdGeo // one cell-type group
     double * sfcnd;      // [nsf*ndim][n]
     double * sfnml;      // [nsf*ndim][n]
     int32_t beg;
-    int32_t n;
+    int32_t n;    // cells in the group (array stride)
+    int32_t nact; // owned cells, stored first: the march kernels stop here
 };
 
 // L1 / L2 prefetch of one address per lane (no register is tied up while the line is in flight)

@@ -126,6 +126,15 @@ int scg_mesh_create(scg_mesh ** out, int ndim, int64_t nnode, int64_t nface, int
                     const int32_t * fccls, const int32_t * fcnds, const double * ndcrd, const double * fccnd,
                     const double * fcnml, const double * clcnd, int order)
 {
+    return scg_mesh_create_part(out, ndim, nnode, nface, ncell, ngstnode, ngstface, ngstcell, cltpn, clfcs, fccls, fcnds, ndcrd,
+                                fccnd, fcnml, clcnd, order, nullptr);
+}
+
+int scg_mesh_create_part(scg_mesh ** out, int ndim, int64_t nnode, int64_t nface, int64_t ncell, int64_t ngstnode,
+                         int64_t ngstface, int64_t ngstcell, const int32_t * cltpn, const int32_t * clfcs,
+                         const int32_t * fccls, const int32_t * fcnds, const double * ndcrd, const double * fccnd,
+                         const double * fcnml, const double * clcnd, int order, const int8_t * owned)
+{
     if (int rc = ensure_init()) { return rc; }
     SCG_REQUIRE(out != nullptr, "scg_mesh_create: null output");
     SCG_REQUIRE(2 == ndim || 3 == ndim, "scg_mesh_create: ndim must be 2 or 3");
@@ -170,14 +179,21 @@ int scg_mesh_create(scg_mesh ** out, int ndim, int64_t nnode, int64_t nface, int
     else if (SCG_ORDER_RCM == order) { rcm_rank(ncell, clfcs_b, fccls_b, key); }
     m->perm.resize(static_cast<size_t>(ncell));
     std::iota(m->perm.begin(), m->perm.end(), 0);
+    // primary key: cell type; then owned cells before halo copies; then the locality key
+    auto halo = [&](int32_t c) -> int { return (owned && !owned[c]) ? 1 : 0; };
     if (key.empty())
     {
-        std::stable_sort(m->perm.begin(), m->perm.end(), [&](int32_t a, int32_t b) { return cltpn_b[a] < cltpn_b[b]; });
+        std::stable_sort(m->perm.begin(), m->perm.end(), [&](int32_t a, int32_t b)
+                         { return cltpn_b[a] != cltpn_b[b] ? cltpn_b[a] < cltpn_b[b] : halo(a) < halo(b); });
     }
     else
     {
         std::stable_sort(m->perm.begin(), m->perm.end(), [&](int32_t a, int32_t b)
-                         { return cltpn_b[a] != cltpn_b[b] ? cltpn_b[a] < cltpn_b[b] : key[a] < key[b]; });
+                         {
+                             if (cltpn_b[a] != cltpn_b[b]) { return cltpn_b[a] < cltpn_b[b]; }
+                             if (halo(a) != halo(b)) { return halo(a) < halo(b); }
+                             return key[a] < key[b];
+                         });
     }
     m->iperm.resize(static_cast<size_t>(ncell));
     for (int64_t k = 0; k < ncell; ++k) { m->iperm[m->perm[k]] = static_cast<int32_t>(k); }
@@ -195,6 +211,8 @@ int scg_mesh_create(scg_mesh ** out, int ndim, int64_t nnode, int64_t nface, int
             g.type = t;
             g.beg = static_cast<int32_t>(k);
             g.n = static_cast<int32_t>(e - k);
+            g.nact = 0;
+            for (int64_t q = k; q < e; ++q) { g.nact += halo(m->perm[q]) ? 0 : 1; }
             g.off_nbr = off_nbr;
             g.off_geo = off_geo;
             off_nbr += int64_t(ct_nfc(t)) * g.n;

@@ -1,0 +1,300 @@
+"""Domain decomposition and halo exchange for the multidim march (one process per GPU).
+
+The reference has no decomposition; this is the B200-side addition that lets one mesh
+run on the 8 GPUs of a box.  The march is a pure gather, so a partition only needs, besides its own
+cells, one layer of *halo copies* of the remote face neighbours (refreshed every substep) and a second,
+passive layer behind it:
+
+* a partition is an ordinary ``StaticMesh`` built from the owned cells plus that halo layer, in
+  ascending GLOBAL cell order (so the owner cell of every face -- and with it the node order of the
+  face, the sub-face order and every rounding -- is the same as in the undecomposed mesh);
+* the second layer is never exchanged or read by an owned cell's update; it only exists so that every
+  face of a first-layer copy has both of its cells present -- then the face keeps its global owner and
+  node order, and the copy's mesh centroid ``clcnd`` (which the CE geometry of the owned interface cells
+  reads, ``euler_ce.cpp:96-101,214-216``) comes out with the same bits as in the undecomposed mesh;
+* the march kernels skip all copies (``owned`` mask, ``scg_mesh_create_part``);
+* after every substep each partition sends the new state (``so0n``+``so1n``) of the cells its
+  neighbours hold as halo copies (``scg_md_halo_pack/unpack``), in ascending global cell order on both
+  sides; ``so0t`` of a halo copy is recomputed locally;
+* once at setup the halo copies receive their solution point and gamma from the owner (a halo copy's
+  own CE centroid cannot be computed locally: its outer neighbours are missing).
+
+Results are bit-identical to the single-domain run for any number of parts
+(``tests/test_gpu_decomp.py``, ``tests/test_decomp_gloo.py``).
+
+Transport: :class:`LocalExchange` (all partitions in one process: tests, one GPU) or
+:class:`TorchExchange` (``torch.distributed``: NCCL send/recv of the packed device buffers between GPUs over
+NVLink, gloo for the CPU tests).  The halo of a 5e7-cell partition is ~2.5e5 cells x 160 B = 40 MB per
+neighbour per substep: ~50 us on NVLink against ~60 ms of compute, so the exchange is not overlapped.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import meshgen
+from .mesh import StaticMesh, make_mesh
+
+
+# ----------------------------------------------------------------------------- partitioning ---
+
+def rcb_partition(centroids, nparts):
+    """Recursive coordinate bisection of the cell centroids into ``nparts`` parts of (nearly) equal
+    size; deterministic (stable sorts), any ``nparts >= 1``.  Returns ``part[ncell]`` (int32)."""
+    n = len(centroids)
+    part = np.zeros(n, dtype=np.int32)
+
+    def split(idx, p0, np_):
+        if np_ == 1:
+            part[idx] = p0
+            return
+        c = centroids[idx]
+        axis = int(np.argmax(c.max(axis=0) - c.min(axis=0)))
+        order = np.argsort(c[:, axis], kind="stable")
+        nl = np_ // 2
+        cut = (len(idx) * nl) // np_
+        split(idx[order[:cut]], p0, nl)
+        split(idx[order[cut:]], p0 + nl, np_ - nl)
+
+    split(np.arange(n), 0, int(nparts))
+    return part
+
+
+@dataclass
+class Partition:
+    rank: int
+    ndim: int
+    ndcrd: np.ndarray          # local nodes
+    cltpn: np.ndarray          # local cells, ascending global id
+    clnds: np.ndarray
+    owned: np.ndarray          # int8 mask over the local cells
+    gid: np.ndarray            # global id of every local cell
+    send: dict = field(default_factory=dict)  # neighbour rank -> local cell ids (ascending global id)
+    recv: dict = field(default_factory=dict)  # neighbour rank -> local cell ids of the halo copies
+    mesh: StaticMesh = None
+
+    @property
+    def neighbours(self):
+        return sorted(set(self.send) | set(self.recv))
+
+    def build_mesh(self):
+        if self.mesh is None:
+            self.mesh = make_mesh(self.ndim, self.ndcrd, self.cltpn, self.clnds)
+        return self.mesh
+
+    def send_list(self):
+        return np.concatenate([self.send[q] for q in self.neighbours]) if self.send else np.zeros(0, np.int32)
+
+    def recv_list(self):
+        return np.concatenate([self.recv[q] for q in self.neighbours]) if self.recv else np.zeros(0, np.int32)
+
+    def physical_boundary_groups(self, lo, hi):
+        """(inlet, outlet, wall) boundary faces of OWNED cells; faces whose interior cell is a halo copy are
+        artefacts of the cut and get no boundary condition."""
+        m = self.build_mesh()
+        inlet, outlet, wall = meshgen.boundary_groups(self.ndim, m.fccnd.body, m.fccls.body, m.nface, lo, hi)
+        own = self.owned.astype(bool)
+        keep = lambda f: f[own[m.fccls.body[f, 0]]]  # noqa: E731
+        return keep(inlet), keep(outlet), keep(wall)
+
+
+def make_partitions(ndim, ndcrd, cltpn, clnds, part, ranks=None):
+    """Cut a global mesh (nodes + cells) into partitions with one halo layer.  ``part[ncell]`` assigns every
+    cell to a rank.  Returns ``{rank: Partition}`` for ``ranks`` (default: all)."""
+    ndcrd = np.asarray(ndcrd)
+    nparts = int(part.max()) + 1
+    g = StaticMesh(ndim, len(ndcrd), 0, len(cltpn))
+    g.ndcrd.ndarray[...] = ndcrd
+    g.cltpn.ndarray[...] = cltpn
+    g.clnds.ndarray[...] = clnds
+    g.build_interior(False, False)
+    fccls = g.fccls.ndarray[:, :2]
+    inner = fccls[fccls[:, 1] >= 0]
+    a, b = inner[:, 0], inner[:, 1]
+    cross = part[a] != part[b]
+    a, b = a[cross], b[cross]
+    out = {}
+    ia, ib = inner[:, 0], inner[:, 1]
+    for r in (range(nparts) if ranks is None else ranks):
+        # cells of other ranks that share a face with a cell of rank r, and the other way round
+        halo_of_r = np.unique(np.concatenate([b[part[a] == r], a[part[b] == r]]))
+        own = np.nonzero(part == r)[0]
+        # second (passive) layer: face neighbours of the first layer
+        in1 = np.zeros(len(cltpn), dtype=bool)
+        in1[halo_of_r] = True
+        layer2 = np.unique(np.concatenate([ib[in1[ia]], ia[in1[ib]]]))
+        local = np.union1d(np.union1d(own, halo_of_r), layer2)  # ascending global id
+        lid = np.full(len(cltpn), -1, dtype=np.int64)
+        lid[local] = np.arange(len(local))
+        lcl = clnds[local].copy()
+        valid = lcl[:, 1:] >= 0
+        nodes = np.unique(lcl[:, 1:][valid])
+        nmap = np.full(len(ndcrd), -1, dtype=np.int64)
+        nmap[nodes] = np.arange(len(nodes))
+        lcl[:, 1:][valid] = nmap[lcl[:, 1:][valid]]
+        p = Partition(rank=r, ndim=ndim, ndcrd=np.ascontiguousarray(ndcrd[nodes]), cltpn=cltpn[local].astype(np.int32),
+                      clnds=lcl.astype(np.int32), owned=(part[local] == r).astype(np.int8), gid=local)
+        for q in np.unique(part[halo_of_r]):
+            p.recv[int(q)] = lid[halo_of_r[part[halo_of_r] == q]].astype(np.int32)
+            # my cells that rank q holds as halo copies: owned by r, adjacent to a cell of q
+            mine = np.unique(np.concatenate([a[(part[a] == r) & (part[b] == q)], b[(part[b] == r) & (part[a] == q)]]))
+            p.send[int(q)] = lid[mine].astype(np.int32)
+        out[r] = p
+    return out
+
+
+def slab_partition_3d(rank, nparts, nx, ny_per_rank, nz, h, x1, z1, kinds="hpt", jitter=0.1):
+    """Partition ``rank`` of the weak-scaling stepped channel: the domain is
+    extended in y with the number of ranks (``ny = nparts * ny_per_rank`` boxes) and rank r owns the box
+    layers ``r*ny_per_rank <= j < (r+1)*ny_per_rank``.  Only the own layers plus two halo layers per side
+    (the exchanged one and the passive one) are generated, in global lattice coordinates, so no rank ever
+    holds the global mesh."""
+    ny = nparts * ny_per_rank
+    j0, j1 = rank * ny_per_rank, (rank + 1) * ny_per_rank
+    g0, g1 = max(0, j0 - 2), min(ny, j1 + 2)
+    ndcrd, cltpn, clnds, bj = meshgen.mixed_3d(nx, ny, nz, lx=nx * h, ly=ny * h, lz=nz * h, x1=x1, z1=z1, kinds=kinds,
+                                               jitter=jitter, j_range=(g0, g1), return_box_j=True)
+    owned = ((bj >= j0) & (bj < j1)).astype(np.int8)
+    ids = np.arange(len(cltpn), dtype=np.int32)
+    p = Partition(rank=rank, ndim=3, ndcrd=ndcrd, cltpn=cltpn, clnds=clnds, owned=owned, gid=ids.astype(np.int64))
+    # Every cell of a box touches the box's own y-faces?  No: only some cells of a box have a face on the
+    # slab interface, but every face neighbour across the interface lies in the adjacent box layer, so
+    # exchanging whole layers is a (slightly generous) superset and keeps both sides' lists trivially
+    # consistent: ascending local order == ascending global order on both ranks.
+    if rank > 0:
+        p.recv[rank - 1] = ids[bj == j0 - 1]
+        p.send[rank - 1] = ids[bj == j0]
+    if rank < nparts - 1:
+        p.recv[rank + 1] = ids[bj == j1]
+        p.send[rank + 1] = ids[bj == j1 - 1]
+    return p
+
+
+# ----------------------------------------------------------------------------------- transport ---
+
+class LocalExchange:
+    """All partitions live in this process (tests; several partitions on one GPU): a 'message' is the
+    sender's packed device buffer, read directly by the receiver's unpack kernel."""
+
+    def __init__(self, solvers):
+        self.solvers = solvers  # {rank: DistEulerCore}
+
+    def exchange(self, what):
+        packed = {}
+        for r, s in self.solvers.items():
+            ptr, n = s.core.halo_pack(what)
+            packed[r] = (ptr, s.send_offsets)
+        from . import _lib
+        _lib.sync()
+        for r, s in self.solvers.items():
+            w = s.core.halo_width(what)
+            # the receiver's unpack wants ONE buffer ordered like its recv list: gather the segments
+            segs = []
+            for q in s.part.neighbours:
+                ptr, offs = packed[q]
+                o0, o1 = offs[r]
+                segs.append((ptr + o0 * w * 8, (o1 - o0) * w))
+            s.unpack_segments(segs, what)
+
+
+class TorchExchange:
+    """``torch.distributed`` transport (NCCL between GPUs, gloo on the CPU): grouped isend/irecv of the
+    packed buffers with every neighbour rank."""
+
+    def __init__(self, solver, device):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.s, self.device = torch, dist, solver, device
+        self.recvbuf = {}
+
+    def _view(self, ptr, n):
+        class _Dev:
+            pass
+        d = _Dev()
+        d.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False), "version": 3}
+        return self.torch.as_tensor(d, device=self.device)
+
+    def exchange(self, what):
+        from . import _lib
+        torch, dist, s = self.torch, self.dist, self.s
+        w = s.core.halo_width(what)
+        ptr, n = s.core.halo_pack(what)
+        _lib.sync()  # the library packs on its own stream
+        ops, total = [], 0
+        key = what
+        if key not in self.recvbuf:
+            self.recvbuf[key] = torch.empty(max(1, s.nrecv * w), dtype=torch.float64, device=self.device)
+        rb = self.recvbuf[key]
+        sendall = self._view(ptr, max(1, n)) if n else None
+        ro = 0
+        for q in s.part.neighbours:
+            o0, o1 = s.send_offsets[q]
+            if o1 > o0:
+                ops.append(dist.P2POp(dist.isend, sendall[o0 * w:o1 * w], q))
+            nr = len(s.part.recv.get(q, ()))
+            if nr:
+                ops.append(dist.P2POp(dist.irecv, rb[ro * w:(ro + nr) * w], q))
+            ro += nr
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+            torch.cuda.synchronize(self.device)
+        if s.nrecv:
+            s.core.halo_unpack(rb.data_ptr(), what)
+
+
+# ------------------------------------------------------------------------------------- solver ---
+
+class DistEulerCore:
+    """``EulerCore`` of one partition: the device solver of the local mesh plus the halo bookkeeping.
+    ``march(steps)`` = per substep: local substep on the owned cells, then the halo exchange."""
+
+    def __init__(self, part: Partition, time_increment, order="morton"):
+        from .multidim import EulerCore
+        self.part = part
+        mesh = part.build_mesh()
+        self.core = EulerCore(mesh, time_increment, order=order, owned=part.owned)
+        self.core.resident(True)
+        snd, rcv = part.send_list(), part.recv_list()
+        self.nsend, self.nrecv = len(snd), len(rcv)
+        self.core.halo_set(snd, rcv)
+        self.send_offsets, o = {}, 0
+        for q in part.neighbours:
+            k = len(part.send.get(q, ()))
+            self.send_offsets[q] = (o, o + k)
+            o += k
+        self.transport = None
+        self._scratch = None
+
+    def unpack_segments(self, segs, what):
+        """LocalExchange helper: unpack from several source buffers (one per neighbour, in neighbour order)."""
+        import ctypes as C
+        from . import _lib
+        lib = _lib.load()
+        if len(segs) == 1:
+            self.core.halo_unpack(segs[0][0], what)
+            return
+        # more than one neighbour: stage the segments contiguously (device-to-device copies)
+        total = sum(n for _, n in segs)
+        if self._scratch is None or self._scratch[1] < total:
+            p = C.c_void_p()
+            _lib.check(lib.scg_dev_alloc(C.byref(p), total * 8))
+            self._scratch = (p.value, total)
+        o = 0
+        for ptr, n in segs:
+            _lib.check(lib.scg_dev_copy(C.c_void_p(self._scratch[0] + o * 8), C.c_void_p(ptr), n * 8))
+            o += n
+        self.core.halo_unpack(self._scratch[0], what)
+
+    def upload_state(self):
+        """Push host-side edits of the field (initial condition) to the device."""
+        self.core._push(force=True)
+
+    def download_state(self):
+        self.core.sync_to_host()
+
+    def march(self, steps):
+        for _ in range(2 * int(steps)):
+            self.core.substep_local()
+            self.transport.exchange(0)

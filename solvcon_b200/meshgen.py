@@ -99,14 +99,18 @@ for perm in ((0, 1, 2), (0, 2, 1), (1, 0, 2), (1, 2, 0), (2, 0, 1), (2, 1, 0)):
     _KUHN.append(path)
 
 
-def mixed_3d(nx, ny, nz, lx=None, ly=None, lz=None, x1=None, z1=None, kinds="hpt", jitter=0.0):
+def mixed_3d(nx, ny, nz, lx=None, ly=None, lz=None, x1=None, z1=None, kinds="hpt", jitter=0.0, j_range=None,
+             return_box_j=False):
     """Stepped channel of ``nx`` x ``ny`` x ``nz`` boxes: block A hexahedra
     (``i < x1, k < z1``), block B z-axis prisms (``i >= x1, k < z1``; each box split on its vertical
     ll-ur diagonal plane), block C tetrahedra (``i >= x1, k >= z1``; Kuhn split, 6 per box); the
     region ``i < x1, k >= z1`` is solid.  All interfaces conform without pyramids (hex|prism share
     quads at ``i = x1``, prism|tet share triangles at ``k = z1``).  ``kinds`` selects the blocks:
     ``"h"`` = hex box only (``x1 = nx, z1 = nz``), ``"hp"``, ``"hpt"``; ``"t"`` / ``"p"`` = one kind
-    everywhere.  Returns ``(ndcrd[nnode,3], cltpn, clnds)``."""
+    everywhere.  ``j_range=(j0, j1)`` generates only the boxes with ``j0 <= j < j1`` of the SAME global lattice
+    (coordinates, jitter and relative cell order are those of the full mesh -- used by the slab domain
+    decomposition); ``return_box_j`` also returns the global box index j of every cell.
+    Returns ``(ndcrd[nnode,3], cltpn, clnds)``."""
     lx = float(nx) if lx is None else lx
     ly = float(ny) if ly is None else ly
     lz = float(nz) if lz is None else lz
@@ -120,7 +124,8 @@ def mixed_3d(nx, ny, nz, lx=None, ly=None, lz=None, x1=None, z1=None, kinds="hpt
     else:
         x1 = nx // 2 if x1 is None else x1
         z1 = nz // 2 if z1 is None else z1
-    ii, jj, kk = np.meshgrid(np.arange(nx + 1), np.arange(ny + 1), np.arange(nz + 1), indexing="ij")
+    j0, j1 = (0, ny) if j_range is None else (max(0, int(j_range[0])), min(ny, int(j_range[1])))
+    ii, jj, kk = np.meshgrid(np.arange(nx + 1), np.arange(j0, j1 + 1), np.arange(nz + 1), indexing="ij")
     x = ii * (lx / nx)
     y = jj * (ly / ny)
     z = kk * (lz / nz)
@@ -130,8 +135,9 @@ def mixed_3d(nx, ny, nz, lx=None, ly=None, lz=None, x1=None, z1=None, kinds="hpt
         x = x + np.where(inner, jitter * np.sin(12.9898 * ii + 78.233 * jj + 37.719 * kk), 0.0) * (lx / nx)
         y = y + np.where(inner, jitter * np.cos(26.651 * ii + 41.347 * jj + 11.135 * kk), 0.0) * (ly / ny)
         z = z + np.where(inner, jitter * np.sin(63.7264 * ii + 10.873 * jj + 53.127 * kk), 0.0) * (lz / nz)
-    nid = ((ii * (ny + 1) + jj) * (nz + 1) + kk).astype(np.int64)
-    bi, bj, bk = [a.ravel() for a in np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")]
+    nyl = j1 - j0
+    nid = ((ii * (nyl + 1) + (jj - j0)) * (nz + 1) + kk).astype(np.int64)  # local lattice id, same relative order
+    bi, bj, bk = [a.ravel() for a in np.meshgrid(np.arange(nx), np.arange(nyl), np.arange(nz), indexing="ij")]
     solid = (bi < x1) & (bk >= z1)
     bi, bj, bk = bi[~solid], bj[~solid], bk[~solid]
     # box corners c = 4*dx + 2*dy + dz
@@ -175,6 +181,8 @@ def mixed_3d(nx, ny, nz, lx=None, ly=None, lz=None, x1=None, z1=None, kinds="hpt
         n[neg, 2], n[neg, 3] = n[neg, 3].copy(), n[neg, 2].copy()
         clnds[tets, 1:5] = n
     ndcrd, clnds = _compact_nodes(ndcrd, clnds)
+    if return_box_j:
+        return np.ascontiguousarray(ndcrd), cltpn, clnds, np.repeat(bj + j0, ncl)
     return np.ascontiguousarray(ndcrd), cltpn, clnds
 
 

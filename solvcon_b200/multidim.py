@@ -53,10 +53,11 @@ class DeviceMesh:
     """Device copy of the StaticMesh tables the march reads, in the reordered device layout
     (``scg_mesh_create``).  ``order``: ``"none" | "morton" | "rcm"``."""
 
-    def __init__(self, mesh, order="morton"):
+    def __init__(self, mesh, order="morton", owned=None):
         self._lib = _lib.load()
         self._h = C.c_void_p()
         self.order = _ORDERS[order]
+        own = None if owned is None else np.ascontiguousarray(owned, dtype=np.int8)
         self.ndim = int(mesh.ndim)
         self.ncell, self.nface, self.nnode = int(mesh.ncell), int(mesh.nface), int(mesh.nnode)
         self.ngstcell, self.ngstface, self.ngstnode = int(mesh.ngstcell), int(mesh.ngstface), int(mesh.ngstnode)
@@ -66,10 +67,11 @@ class DeviceMesh:
         for n in ("cltpn", "clfcs", "fccls", "fcnds"):
             if t[n].dtype != np.int32:
                 t[n] = t[n].astype(np.int32)
-        rc = self._lib.scg_mesh_create(
+        rc = self._lib.scg_mesh_create_part(
             C.byref(self._h), self.ndim, self.nnode, self.nface, self.ncell, self.ngstnode, self.ngstface,
             self.ngstcell, _lib.ptr(t["cltpn"]), _lib.ptr(t["clfcs"]), _lib.ptr(t["fccls"]), _lib.ptr(t["fcnds"]),
-            _lib.ptr(t["ndcrd"]), _lib.ptr(t["fccnd"]), _lib.ptr(t["fcnml"]), _lib.ptr(t["clcnd"]), self.order)
+            _lib.ptr(t["ndcrd"]), _lib.ptr(t["fccnd"]), _lib.ptr(t["fcnml"]), _lib.ptr(t["clcnd"]), self.order,
+            _lib.ptr(own))
         if rc:
             _raise(ValueError)
 
@@ -90,10 +92,10 @@ class DeviceMesh:
 class EulerCore:
     """Device twin of ``solvcon::EulerCore`` (``cpp/solvcon/multidim/euler.hpp:56-211``)."""
 
-    def __init__(self, mesh, time_increment, order="morton"):
+    def __init__(self, mesh, time_increment, order="morton", owned=None):
         self._lib = _lib.load()
         self._mesh = mesh
-        self._dmesh = mesh if isinstance(mesh, DeviceMesh) else DeviceMesh(mesh, order)
+        self._dmesh = mesh if isinstance(mesh, DeviceMesh) else DeviceMesh(mesh, order, owned)
         dm = self._dmesh
         self._ndim, self._ncell, self._ngst = dm.ndim, dm.ncell, dm.ngstcell
         self._neq = self._ndim + 2
@@ -323,6 +325,31 @@ class EulerCore:
         vol = None if clvol is None else np.ascontiguousarray(clvol, dtype=np.float64)
         _lib.check(self._lib.scg_md_reduce(self._h, _lib.ptr(vol), C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
+
+    # -- halo exchange of a partition (see solvcon_b200/decomp.py) ------------------------------------
+    def halo_set(self, send_cells, recv_cells):
+        snd = np.ascontiguousarray(send_cells, dtype=np.int32)
+        rcv = np.ascontiguousarray(recv_cells, dtype=np.int32)
+        self._nsend, self._nrecv = len(snd), len(rcv)
+        _lib.check(self._lib.scg_md_halo_set(self._h, _lib.ptr(snd) if len(snd) else None, len(snd),
+                                             _lib.ptr(rcv) if len(rcv) else None, len(rcv)))
+
+    def halo_width(self, what=0):
+        return self._neq * (1 + self._ndim) if what == 0 else self._ndim + 1
+
+    def halo_pack(self, what=0):
+        """Pack the send cells on the device; returns (device pointer, number of doubles)."""
+        p, n = C.c_void_p(), C.c_int64()
+        _lib.check(self._lib.scg_md_halo_pack(self._h, int(what), C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def halo_unpack(self, dev_ptr, what=0):
+        _lib.check(self._lib.scg_md_halo_unpack(self._h, int(what), C.c_void_p(dev_ptr)))
+
+    def substep_local(self):
+        """One march_substep of this partition without any host transfer (resident mode only)."""
+        if self._lib.scg_md_phase(self._h, MD_SUBSTEP):
+            _raise()
 
     def algorithmic_bytes(self):
         """Algorithmic bytes one substep moves on this mesh."""
