@@ -287,6 +287,7 @@ def main():
     wl = make_workload(args)
     wl.rank, wl.world, wl.dist, wl.local = rank, world, dist, local
     wl.build_device()
+    barrier(dist, local)
 
     # ---- device-resident arm
     wl.resident_begin()
@@ -321,7 +322,8 @@ def main():
     if not args.no_e2e:
         if hasattr(wl.dev, "materialise"):
             wl.dev.materialise()
-        wl.dev.resident(False)
+        if getattr(wl, "dist_svr", None) is None:
+            wl.dev.resident(False)
         wl.e2e_step()
         n_e2e = max(1, min(args.steps, 3))
         barrier(dist, local)

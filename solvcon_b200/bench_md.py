@@ -64,6 +64,44 @@ def build_case_3d(ncell_target, order="morton", kinds="hpt", log=None):
     return mesh, svr, info
 
 
+def build_case_3d_dist(ncell_target, rank, world, local_device, order="morton", kinds="hpt"):
+    """Weak-scaling case: the channel is extended in y with the number of ranks; rank r
+    owns ny box layers and builds only those plus two halo layers per side (solvcon_b200.decomp)."""
+    from .decomp import DistEulerCore, TorchExchange, slab_partition_3d
+    t0 = time.perf_counter()
+    nx, ny, nz, x1, z1 = dims_3d(ncell_target)
+    h = 1.0 / ny
+    part = slab_partition_3d(rank, world, nx, ny, nz, h, x1, z1, kinds=kinds, jitter=0.1)
+    t1 = time.perf_counter()
+    mesh = part.build_mesh()
+    t2 = time.perf_counter()
+    dt = 0.05 * h
+    svr = DistEulerCore(part, dt, order=order)
+    t3 = time.perf_counter()
+    lo = np.array([0.0, 0.0, 0.0])
+    hi = np.array([nx * h, world * ny * h, nz * h])
+    inlet, outlet, wall = part.physical_boundary_groups(lo, hi)
+    core = svr.core
+    core.init_solution(1.4, 1.4, [3.0, 0.0, 0.0], 1.0)
+    core.add_inlet(inlet, [1.4, 3.0, 0.0, 0.0, 1.0, 1.4])
+    core.add_nonrefl(outlet)
+    core.add_slipwall(wall)
+    core.bc_soln()
+    core.bc_dsoln()
+    svr.transport = TorchExchange(svr, f"cuda:{local_device}")
+    svr.transport.exchange(1)
+    svr.transport.exchange(0)
+    own = part.owned.astype(bool)
+    info = {"boxes_per_rank": [nx, ny, nz], "x1": x1, "z1": z1, "h": h, "dt": dt, "ncell": int(own.sum()),
+            "ncell_local_mesh": int(mesh.ncell), "halo_send_cells": int(svr.nsend), "halo_recv_cells": int(svr.nrecv),
+            "halo_bytes_per_substep": int(svr.nsend * core.halo_width(0) * 8),
+            "nface": int(mesh.nface), "ngstcell": int(mesh.ngstcell),
+            "cells_by_type": {"hex": int((part.cltpn[own] == 5).sum()), "tet": int((part.cltpn[own] == 6).sum()),
+                              "prism": int((part.cltpn[own] == 7).sum())},
+            "setup_s": {"generate": round(t1 - t0, 2), "tables": round(t2 - t1, 2), "device": round(t3 - t2, 2)}}
+    return mesh, svr, info
+
+
 class MD3DWorkload:
     name = "md3d"
     dtype = "f64"
@@ -76,7 +114,14 @@ class MD3DWorkload:
         self.kinds = kinds
 
     def build_device(self):
-        self.mesh, self.dev, self.info = build_case_3d(self.ncell_target, self.order, self.kinds)
+        world = getattr(self, "world", 1)
+        if world > 1:
+            self.mesh, self.dist_svr, self.info = build_case_3d_dist(self.ncell_target, self.rank, world, self.local,
+                                                                     self.order, self.kinds)
+            self.dev = self.dist_svr.core
+        else:
+            self.mesh, self.dev, self.info = build_case_3d(self.ncell_target, self.order, self.kinds)
+            self.dist_svr = None
         self.ncell = self.info["ncell"]
         self.balg_substep = self.dev.algorithmic_bytes()
         return self.dev
@@ -88,7 +133,9 @@ class MD3DWorkload:
              "cells_per_gpu": self.ncell, "chunk_steps": self.chunk, "ordering": self.order,
              "alg_bytes_per_cell_substep": self.balg_substep / self.ncell,
              "l2_policy": "inputs larger than L2 (%.1f GB streamed per substep)" % (self.balg_substep / 1e9),
-             "decomposition": "none" if world == 1 else "independent replicas per GPU (halo exchange: see DESIGN.md)",
+             "decomposition": "none" if world == 1 else
+             f"y-slabs, one per GPU, domain extended in y with the rank count; halo exchange of so0n+so1n after every "
+             f"substep by NCCL isend/irecv ({self.info.get('halo_bytes_per_substep', 0)} B sent per rank per substep)",
              "mesh": self.info}
         return d
 
@@ -105,10 +152,19 @@ class MD3DWorkload:
         self.dev.resident(True)
 
     def resident_step(self):
-        self.dev.march(self.chunk)
+        if self.dist_svr is not None:
+            self.dist_svr.march(self.chunk)
+        else:
+            self.dev.march(self.chunk)
 
     def e2e_step(self):
-        self.dev.march(self.chunk)
+        if self.dist_svr is not None:
+            # host arrays in, host arrays out, around the distributed march
+            self.dev._push(force=True)
+            self.dist_svr.march(self.chunk)
+            self.dev.sync_to_host()
+        else:
+            self.dev.march(self.chunk)
 
     def e2e_bytes(self):
         T = self.ncell + self.info["ngstcell"]
