@@ -287,6 +287,9 @@ __global__ void __launch_bounds__(128) md_substep_kernel(MdField const F, MdGeo 
 }
 
 // Split substep, kernel 1: calc_soln -> (raw energy for the ghosts) -> calc_cfl, one thread per cell.
+#ifndef SCG_SOLN_ROWS
+#define SCG_SOLN_ROWS 1
+#endif
 #ifndef SCG_SOLN_MINBLOCKS
 #define SCG_SOLN_MINBLOCKS 3
 #endif
@@ -300,7 +303,11 @@ __global__ void __launch_bounds__(128, SCG_SOLN_MINBLOCKS) md_solncfl_kernel(MdF
     if (i >= G.nact) { return; }
     int64_t const k = G.beg + i;
     double un[NEQ];
+#if SCG_SOLN_ROWS
+    cell_soln_rows<TYPE>(F, G, i, un);
+#else
     cell_soln<TYPE>(F, G, i, un);
+#endif
 #pragma unroll
     for (int f = 0; f < NFC; ++f)
     {

@@ -391,6 +391,115 @@ __device__ __forceinline__ void cell_soln(MdField const & F, MdGeo const & G, in
     for (int e = 0; e < NEQ; ++e) { out[e] = acc[e] / cvol; }
 }
 
+// calc_soln_impl for one cell, second formulation: identical terms and identical summation order per
+// equation, but organised for the memory system.  Everything a face needs -- the neighbour gather AND the
+// geometry of all of its sub-faces -- is requested in one batch at the top of the face iteration (one
+// exposed memory latency per face instead of one per sub-face), and the flux evaluation runs equation-outer /
+// sub-face-inner so only one Jacobian row is live at a time.  acc[e] still receives the spatial term and
+// then the sub-face terms in sub-face order, so every rounding is the one of euler_march.cpp:236-294.
+template <int TYPE>
+__device__ __forceinline__ void cell_soln_rows(MdField const & F, MdGeo const & G, int32_t i, double (&out)[ct_ndim(TYPE) + 2])
+{
+    constexpr int ND = ct_ndim(TYPE);
+    constexpr int NEQ = ND + 2;
+    constexpr int NFC = ct_nfc(TYPE);
+    constexpr int MSF = (ND == 2) ? 2 : ((TYPE == CT_TET) ? 3 : 4); // most sub-faces on one face
+    int64_t const n = G.n;
+    int64_t const S = F.S;
+    double const qdt = F.dt * 0.25;
+    double const hdt = F.dt * 0.5;
+    double acc[NEQ];
+#pragma unroll
+    for (int e = 0; e < NEQ; ++e) { acc[e] = 0.0; }
+
+    int64_t jnext = G.nbr[i];
+#pragma unroll 1
+    for (int f = 0; f < NFC; ++f)
+    {
+        int64_t const j = jnext;
+        if (f + 1 < NFC) { jnext = G.nbr[(f + 1) * n + i]; }
+        int const nsf = ct_fnnd(TYPE, f);
+        int const q0 = ct_sfoff(TYPE, f);
+        // ---- one batch of loads
+        double jc[ND], bc[ND];
+#pragma unroll
+        for (int d = 0; d < ND; ++d)
+        {
+            jc[d] = F.solpt[d * S + j];
+            bc[d] = G.cecnd[(f * ND + d) * n + i];
+        }
+        double const bvol = G.cevol[(f + 1) * n + i];
+        double ju[NEQ], jt[NEQ], jg[NEQ][ND];
+#pragma unroll
+        for (int e = 0; e < NEQ; ++e)
+        {
+            ju[e] = F.so0c[e * S + j];
+            jt[e] = F.so0t[e * S + j];
+#pragma unroll
+            for (int d = 0; d < ND; ++d) { jg[e][d] = F.so1c[(e * ND + d) * S + j]; }
+        }
+        double const ga = F.gamma[j];
+        double sc[MSF][ND], sn[MSF][ND];
+#pragma unroll
+        for (int s = 0; s < MSF; ++s)
+        {
+            int64_t const q = q0 + (s < nsf ? s : nsf - 1); // a triangle face of a prism/pyramid re-reads its last sub-face
+#pragma unroll
+            for (int d = 0; d < ND; ++d)
+            {
+                sc[s][d] = G.sfcnd[(q * ND + d) * n + i];
+                sn[s][d] = G.sfnml[(q * ND + d) * n + i];
+            }
+        }
+        // ---- spatial part over the basic CE (euler_march.cpp:236-249)
+#pragma unroll
+        for (int e = 0; e < NEQ; ++e)
+        {
+            double fusp = ju[e];
+#pragma unroll
+            for (int d = 0; d < ND; ++d) { fusp += (bc[d] - jc[d]) * jg[e][d]; }
+            acc[e] += fusp * bvol;
+        }
+        // ---- Taylor state on every sub-face (euler_march.cpp:268-280)
+        double usfc[MSF][NEQ];
+#pragma unroll
+        for (int s = 0; s < MSF; ++s)
+        {
+#pragma unroll
+            for (int e = 0; e < NEQ; ++e)
+            {
+                usfc[s][e] = qdt * jt[e];
+#pragma unroll
+                for (int d = 0; d < ND; ++d) { usfc[s][e] += (sc[s][d] - jc[d]) * jg[e][d]; }
+            }
+        }
+        Jaco<ND> J;
+        jaco_update<ND>(J, ga, ju);
+        // ---- temporal part, one equation (Jacobian row) at a time (euler_march.cpp:281-294)
+#pragma unroll
+        for (int e = 0; e < NEQ; ++e)
+        {
+#pragma unroll
+            for (int s = 0; s < MSF; ++s)
+            {
+                double dot = 0.0;
+#pragma unroll
+                for (int d2 = 0; d2 < ND; ++d2)
+                {
+                    double dfcn = J.fcn[e][d2];
+#pragma unroll
+                    for (int je = 0; je < NEQ; ++je) { SCG_JTERM(ND, J, e, je, d2, usfc[s][je], dfcn); }
+                    dot += dfcn * sn[s][d2];
+                }
+                if (s < nsf) { acc[e] -= hdt * dot; }
+            }
+        }
+    }
+    double const cvol = G.cevol[i];
+#pragma unroll
+    for (int e = 0; e < NEQ; ++e) { out[e] = acc[e] / cvol; }
+}
+
 // EulerCore::calc_cfl for one cell, euler_solution.cpp:106-160.  `u` is so0n of the cell; its energy
 // is rewritten in place; returns cflo / cflc.
 template <int TYPE>
