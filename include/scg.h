@@ -230,6 +230,11 @@ SCG_API int scg_md_algorithmic_bytes(scg_md * s, int64_t * bytes_per_substep);
 /* get_normal_matrix(ifc), euler_bc.cpp:391-425 (host-side helper, row-major ndim x ndim) */
 SCG_API int scg_md_normal_matrix(scg_md * s, int32_t ifc, double * out);
 
+/* self test of the shared-reciprocal division used inside the kernels (scg_md_kernels.cuh, DivBy): for every
+ * pair, out_fast = the shared-reciprocal quotient, ok = its range test, out_ref = the plain a / b.  Wherever
+ * ok is 1 the two must be bit-equal (tests/test_gpu_md.py). */
+SCG_API int scg_selftest_div(const double * a, const double * b, double * out_fast, double * out_ref, int32_t * ok, int64_t n);
+
 /* halo exchange support for domain decomposition (one process per GPU; the caller moves the packed
  * buffers with NCCL send/recv, see solvcon_b200/decomp.py).  A partition is a StaticMesh of the owned cells
  * plus one layer of HALO copies of the remote face neighbours (scg_mesh_create_part).  send_cells /

@@ -106,6 +106,7 @@ _SIGNATURES = {
     "scg_md_reduce": (C.c_int, [C.c_void_p, C.c_void_p, DP, DP, DP]),
     "scg_md_algorithmic_bytes": (C.c_int, [C.c_void_p, I64P]),
     "scg_md_normal_matrix": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "scg_selftest_div": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     "scg_md_halo_set": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]),
     "scg_md_halo_pack": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), I64P]),
     "scg_md_halo_unpack": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),

@@ -514,21 +514,49 @@ __global__ void __launch_bounds__(128) md_dsoln_coop_kernel(MdField const F, MdG
         }
         adj_n<ND>(dst, adj);
         double const det = det_n<ND>(dst);
+        double rr[NEQ][ND];
 #pragma unroll
         for (int e = 0; e < NEQ; ++e)
         {
             double u[ND];
 #pragma unroll
             for (int b = 0; b < ND; ++b) { u[b] = sm[C::O_FACE + fl[b] * C::R_FACE + ND + e]; }
-            double sq = 0.0;
 #pragma unroll
             for (int a = 0; a < ND; ++a)
             {
                 double r = 0.0;
 #pragma unroll
                 for (int b = 0; b < ND; ++b) { r += adj[a][b] * u[b]; }
-                grad[e][a] = r / det;
+                rr[e][a] = r;
             }
+        }
+        // neq*ndim quotients share det: one reciprocal refinement instead of fifteen (see DivBy)
+        bool fast_ok = false;
+#if SCG_SHARED_RCP
+        {
+            DivBy<true> by_det(det);
+#pragma unroll
+            for (int e = 0; e < NEQ; ++e)
+            {
+#pragma unroll
+                for (int a = 0; a < ND; ++a) { grad[e][a] = by_det(rr[e][a]); }
+            }
+            fast_ok = by_det.ok;
+        }
+#endif
+        if (!fast_ok)
+        {
+#pragma unroll
+            for (int e = 0; e < NEQ; ++e)
+            {
+#pragma unroll
+                for (int a = 0; a < ND; ++a) { grad[e][a] = rr[e][a] / det; }
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < NEQ; ++e)
+        {
+            double sq = 0.0;
 #pragma unroll
             for (int d = 0; d < ND; ++d) { sq += grad[e][d] * grad[e][d]; }
             w[e] = 1.0 / sqrt(sq + MD_ALMOST_ZERO);
@@ -945,6 +973,17 @@ __global__ void md_halo_unpack_kernel(double * so0, double * so1, double * solpt
         for (int d = 0; d < ndim; ++d) { solpt[d * S + k] = buf[t * w + d]; }
         gamma[k] = buf[t * w + ndim];
     }
+}
+
+// bit-exactness self test of DivBy: out_fast[i] = DivBy<true>(b[i])(a[i]) (0/1 flag in ok[i]), out_ref[i] = a[i] / b[i]
+__global__ void md_selftest_div_kernel(double const * a, double const * b, double * out_fast, double * out_ref, int * okf, int64_t n)
+{
+    int64_t const i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) { return; }
+    DivBy<true> d(b[i]);
+    out_fast[i] = d(a[i]);
+    okf[i] = d.ok ? 1 : 0;
+    out_ref[i] = a[i] / b[i];
 }
 
 struct BcReg
@@ -1593,6 +1632,27 @@ int scg_md_normal_matrix(scg_md * s, int32_t ifc, double * out)
     SCG_REQUIRE(s && out, "scg_md_normal_matrix: null argument");
     SCG_REQUIRE(ifc >= 0 && ifc < s->mesh->nface, "get_normal_matrix: face %d out of range", ifc);
     normal_matrix_host(s->ndim, &s->mesh->h_fcnml[static_cast<size_t>(ifc) * s->ndim], out);
+    return 0;
+}
+
+int scg_selftest_div(const double * a, const double * b, double * out_fast, double * out_ref, int32_t * ok, int64_t n)
+{
+    if (int rc = ensure_init()) { return rc; }
+    DevBuf<double> da, db, df, dr;
+    DevBuf<int> dk;
+    SCG_CUDA(da.alloc(n));
+    SCG_CUDA(db.alloc(n));
+    SCG_CUDA(df.alloc(n));
+    SCG_CUDA(dr.alloc(n));
+    SCG_CUDA(dk.alloc(n));
+    SCG_CUDA(cudaMemcpyAsync(da.p, a, sizeof(double) * n, cudaMemcpyHostToDevice, stream()));
+    SCG_CUDA(cudaMemcpyAsync(db.p, b, sizeof(double) * n, cudaMemcpyHostToDevice, stream()));
+    md_selftest_div_kernel<<<static_cast<unsigned>(ceil_div(n, 256)), 256, 0, stream()>>>(da.p, db.p, df.p, dr.p, dk.p, n);
+    count_launch();
+    SCG_CUDA(cudaMemcpyAsync(out_fast, df.p, sizeof(double) * n, cudaMemcpyDeviceToHost, stream()));
+    SCG_CUDA(cudaMemcpyAsync(out_ref, dr.p, sizeof(double) * n, cudaMemcpyDeviceToHost, stream()));
+    SCG_CUDA(cudaMemcpyAsync(ok, dk.p, sizeof(int) * n, cudaMemcpyDeviceToHost, stream()));
+    SCG_CUDA(cudaStreamSynchronize(stream()));
     return 0;
 }
 

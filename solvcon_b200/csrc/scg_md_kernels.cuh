@@ -57,6 +57,60 @@ struct MdGeo // one cell-type group
 __device__ __forceinline__ void prefetch_l1(void const * p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l2(void const * p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// ------------------------------------------------------------------------------------------------
+// IEEE division with a shared reciprocal.
+//
+// The march divides many numerators by the same denominator (9 per Jacobian, 15 per gradient element).
+// ptxas expands every `a / b` into: seed = MUFU.RCP64H(hi(b)) with low word 1, two Newton steps (5 DFMA),
+// then q0 = a*y, r = fma(-b, q0, a), q = fma(y, r, q0), a range test on hi(a) and hi(q), and a call to a
+// slow path when the test fails.  DivBy<true> runs EXACTLY that sequence (checked against the SASS of
+// `div.rn.f64` for sm_100a and, bit for bit, by scg_selftest_div) but refines the reciprocal once per
+// denominator, so each further quotient costs 3 fp64 instructions instead of 9.  `ok` records the range
+// test; when it fails the caller recomputes with DivBy<false>, i.e. the plain operator.
+// ------------------------------------------------------------------------------------------------
+template <bool FAST>
+struct DivBy
+{
+    double b;
+    double y;
+    int bhi;
+    bool ok;
+    __device__ __forceinline__ explicit DivBy(double denom)
+        : b(denom)
+        , y(0.0)
+        , bhi(0)
+        , ok(true)
+    {
+        if (FAST)
+        {
+            bhi = __double2hiint(denom);
+            double y0;
+            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(denom));
+            y0 = __hiloint2double(__double2hiint(y0), 1);
+            double e = __fma_rn(-denom, y0, 1.0);
+            e = __fma_rn(e, e, e);
+            double const y1 = __fma_rn(y0, e, y0);
+            double const e2 = __fma_rn(-denom, y1, 1.0);
+            y = __fma_rn(y1, e2, y1);
+        }
+    }
+    __device__ __forceinline__ double operator()(double a)
+    {
+        if (!FAST) { return a / b; }
+        double const q0 = __dmul_rn(a, y);
+        double const r = __fma_rn(-b, q0, a);
+        double const q = __fma_rn(y, r, q0);
+        float const ah = __int_as_float(__double2hiint(a));
+        float const t = __fmaf_rn(0.0f, __int_as_float(bhi), __int_as_float(__double2hiint(q)));
+        ok = ok && !(fabsf(ah) < 6.5827683646048100446e-37f) && (fabsf(t) > 1.469367938527859385e-39f);
+        return q;
+    }
+};
+
+#ifndef SCG_SHARED_RCP
+#define SCG_SHARED_RCP 1
+#endif
+
 #ifndef SCG_SOLN_PREFETCH
 #define SCG_SOLN_PREFETCH 0
 #endif
@@ -82,11 +136,20 @@ __host__ __device__ constexpr int jkind(int i, int j, int d)
     return (i == j || d == i - 1 || d == j - 1) ? 2 : 0;
 }
 
-template <int ND>
-__device__ __forceinline__ void jaco_update(Jaco<ND> & J, double ga, double const (&u)[ND + 2]);
+template <int ND, bool FAST>
+__device__ __forceinline__ bool jaco_update_impl(Jaco<ND> & J, double ga, double const (&u)[ND + 2]);
 
-template <>
-__device__ __forceinline__ void jaco_update<2>(Jaco<2> & J, double ga, double const (&u)[4])
+template <int ND>
+__device__ __forceinline__ void jaco_update(Jaco<ND> & J, double ga, double const (&u)[ND + 2])
+{
+#if SCG_SHARED_RCP
+    if (jaco_update_impl<ND, true>(J, ga, u)) { return; }
+#endif
+    jaco_update_impl<ND, false>(J, ga, u);
+}
+
+template <bool FAST>
+__device__ __forceinline__ bool jaco_update_2d(Jaco<2> & J, double ga, double const (&u)[4])
 {
     double const ga1 = ga - 1;
     double const ga3 = ga - 3;
@@ -96,15 +159,17 @@ __device__ __forceinline__ void jaco_update<2>(Jaco<2> & J, double ga, double co
     double const u3 = u[2];
     double const u4 = u[3];
     double const rho2 = u1 * u1;
-    double const v1 = u2 / u1;
+    DivBy<FAST> by_u1(u1);
+    DivBy<FAST> by_rho2(rho2);
+    double const v1 = by_u1(u2);
     double const v1o2 = v1 * v1;
-    double const v2 = u3 / u1;
+    double const v2 = by_u1(u3);
     double const v2o2 = v2 * v2;
-    double const ke2 = (u2 * u2 + u3 * u3) / u1;
+    double const ke2 = by_u1(u2 * u2 + u3 * u3);
     double const g1ke2 = ga1 * ke2;
-    double const vs = ke2 / u1;
+    double const vs = by_u1(ke2);
     double const gretot = ga * u4;
-    double const getot = gretot / u1;
+    double const getot = by_u1(gretot);
     double const pr = ga1 * u4 - ga1h * ke2;
 
     J.fcn[0][0] = u2;              J.fcn[0][1] = u3;
@@ -122,18 +187,19 @@ __device__ __forceinline__ void jaco_update<2>(Jaco<2> & J, double ga, double co
     J.jac[2][2][0] = v1;                 J.jac[2][2][1] = -ga3 * v2;
     J.jac[2][3][1] = ga1;
 
-    J.jac[3][0][0] = (-gretot + g1ke2) * u2 / rho2;
-    J.jac[3][0][1] = (-gretot + g1ke2) * u3 / rho2;
+    J.jac[3][0][0] = by_rho2((-gretot + g1ke2) * u2);
+    J.jac[3][0][1] = by_rho2((-gretot + g1ke2) * u3);
     J.jac[3][1][0] = getot - ga1h * (vs + 2 * v1o2);
     J.jac[3][1][1] = -ga1 * v1 * v2;
     J.jac[3][2][0] = -ga1 * v2 * v1;
     J.jac[3][2][1] = getot - ga1h * (vs + 2 * v2o2);
     J.jac[3][3][0] = ga * v1;
     J.jac[3][3][1] = ga * v2;
+    return by_u1.ok && by_rho2.ok;
 }
 
-template <>
-__device__ __forceinline__ void jaco_update<3>(Jaco<3> & J, double ga, double const (&u)[5])
+template <bool FAST>
+__device__ __forceinline__ bool jaco_update_3d(Jaco<3> & J, double ga, double const (&u)[5])
 {
     double const ga1 = ga - 1;
     double const ga3 = ga - 3;
@@ -144,17 +210,19 @@ __device__ __forceinline__ void jaco_update<3>(Jaco<3> & J, double ga, double co
     double const u4 = u[3];
     double const u5 = u[4];
     double const rho2 = u1 * u1;
-    double const v1 = u2 / u1;
+    DivBy<FAST> by_u1(u1);
+    DivBy<FAST> by_rho2(rho2);
+    double const v1 = by_u1(u2);
     double const v1o2 = v1 * v1;
-    double const v2 = u3 / u1;
+    double const v2 = by_u1(u3);
     double const v2o2 = v2 * v2;
-    double const v3 = u4 / u1;
+    double const v3 = by_u1(u4);
     double const v3o2 = v3 * v3;
-    double const ke2 = (u2 * u2 + u3 * u3 + u4 * u4) / u1;
+    double const ke2 = by_u1(u2 * u2 + u3 * u3 + u4 * u4);
     double const g1ke2 = ga1 * ke2;
-    double const vs = ke2 / u1;
+    double const vs = by_u1(ke2);
     double const gretot = ga * u5;
-    double const getot = gretot / u1;
+    double const getot = by_u1(gretot);
     double const pr = ga1 * u5 - ga1h * ke2;
 
     J.fcn[0][0] = u2;             J.fcn[0][1] = u3;             J.fcn[0][2] = u4;
@@ -181,14 +249,20 @@ __device__ __forceinline__ void jaco_update<3>(Jaco<3> & J, double ga, double co
     J.jac[3][3][0] = v1;       J.jac[3][3][1] = v2;       J.jac[3][3][2] = -ga3 * v3;
                                                           J.jac[3][4][2] = ga1;
 
-    J.jac[4][0][0] = (-gretot + g1ke2) * u2 / rho2;
-    J.jac[4][0][1] = (-gretot + g1ke2) * u3 / rho2;
-    J.jac[4][0][2] = (-gretot + g1ke2) * u4 / rho2;
+    J.jac[4][0][0] = by_rho2((-gretot + g1ke2) * u2);
+    J.jac[4][0][1] = by_rho2((-gretot + g1ke2) * u3);
+    J.jac[4][0][2] = by_rho2((-gretot + g1ke2) * u4);
     J.jac[4][1][0] = getot - ga1h * (vs + 2 * v1o2); J.jac[4][1][1] = -ga1 * v1 * v2; J.jac[4][1][2] = -ga1 * v1 * v3;
     J.jac[4][2][0] = -ga1 * v2 * v1; J.jac[4][2][1] = getot - ga1h * (vs + 2 * v2o2); J.jac[4][2][2] = -ga1 * v2 * v3;
     J.jac[4][3][0] = -ga1 * v3 * v1; J.jac[4][3][1] = -ga1 * v3 * v2; J.jac[4][3][2] = getot - ga1h * (vs + 2 * v3o2);
     J.jac[4][4][0] = ga * v1; J.jac[4][4][1] = ga * v2; J.jac[4][4][2] = ga * v3;
+    return by_u1.ok && by_rho2.ok;
 }
+
+template <> __device__ __forceinline__ bool jaco_update_impl<2, true>(Jaco<2> & J, double ga, double const (&u)[4]) { return jaco_update_2d<true>(J, ga, u); }
+template <> __device__ __forceinline__ bool jaco_update_impl<2, false>(Jaco<2> & J, double ga, double const (&u)[4]) { return jaco_update_2d<false>(J, ga, u); }
+template <> __device__ __forceinline__ bool jaco_update_impl<3, true>(Jaco<3> & J, double ga, double const (&u)[5]) { return jaco_update_3d<true>(J, ga, u); }
+template <> __device__ __forceinline__ bool jaco_update_impl<3, false>(Jaco<3> & J, double ga, double const (&u)[5]) { return jaco_update_3d<false>(J, ga, u); }
 
 // acc += jac[i][j][d] * x with the structural zeros skipped and the ones not multiplied
 #define SCG_JTERM(ND, J, i, j, d, x, acc)                   \
@@ -496,6 +570,12 @@ __device__ __forceinline__ void cell_soln_rows(MdField const & F, MdGeo const & 
         }
     }
     double const cvol = G.cevol[i];
+#if SCG_SHARED_RCP
+    DivBy<true> by_cvol(cvol);
+#pragma unroll
+    for (int e = 0; e < NEQ; ++e) { out[e] = by_cvol(acc[e]); }
+    if (by_cvol.ok) { return; }
+#endif
 #pragma unroll
     for (int e = 0; e < NEQ; ++e) { out[e] = acc[e] / cvol; }
 }

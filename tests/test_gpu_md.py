@@ -193,3 +193,29 @@ def test_md_overlapping_bc_last_wins(gpu, bridge):
     c.chk.march(2)
     c.dev.march(2)
     c.same("no bc", STATE, _strict(gpu))
+
+
+def test_shared_reciprocal_division_is_ieee(gpu):
+    """DivBy (scg_md_kernels.cuh) must return exactly a / b wherever its range test passes, and the range
+    test must pass for everything in the normal range."""
+    rng = np.random.RandomState(7)
+    n = 1 << 20
+    a = rng.standard_normal(n) * 10.0 ** rng.uniform(-30, 30, n)
+    b = rng.standard_normal(n) * 10.0 ** rng.uniform(-30, 30, n)
+    # hard cases: mantissas of all ones / near powers of two, exact quotients, tiny and huge operands, zeros
+    edge = np.array([1.0, 3.0, 1.0 / 3.0, np.nextafter(2.0, 0), np.nextafter(1.0, 2), 1e-300, 1e300, 4.9e-324,
+                     2.2250738585072014e-308, 1.7976931348623157e308, 0.0, -0.0, 7.0, 1e-160, 1e160])
+    ea, eb = np.meshgrid(edge, edge)
+    a = np.concatenate([a, ea.ravel(), -ea.ravel()])
+    b = np.concatenate([b, eb.ravel(), eb.ravel()])
+    n = len(a)
+    fast, ref = np.zeros(n), np.zeros(n)
+    ok = np.zeros(n, dtype=np.int32)
+    gpu.check(gpu.load().scg_selftest_div(gpu.ptr(a), gpu.ptr(b), gpu.ptr(fast), gpu.ptr(ref), ok.ctypes.data, n))
+    m = ok == 1
+    assert np.array_equal(fast[m].view(np.int64), ref[m].view(np.int64))
+    with np.errstate(all="ignore"):
+        host = a / b
+    fin = np.isfinite(host) & (host != 0)
+    assert np.array_equal(ref[fin].view(np.int64), host[fin].view(np.int64))   # device '/' is IEEE too
+    assert m[: 1 << 20].mean() > 0.999                                          # the fast path is the common path
