@@ -322,6 +322,66 @@ __global__ void __launch_bounds__(128, SCG_SOLN_MINBLOCKS) md_solncfl_kernel(MdF
     for (int e = 0; e < NEQ; ++e) { F.so0n[e * F.S + k] = un[e]; }
 }
 
+// Split substep, kernel 1, staged variant (march mode 3): same arithmetic as md_solncfl_kernel, with the
+// cell's geometry double-buffered through shared memory by cp.async and the neighbour gather of the next
+// face issued one face ahead (cell_soln_staged); calc_cfl's distance is taken from the staged cecnd rows
+// instead of a second pass over them.
+#ifndef SCG_STAGED_TB
+#define SCG_STAGED_TB 128
+#endif
+#ifndef SCG_STAGED_MINBLOCKS
+#define SCG_STAGED_MINBLOCKS 3
+#endif
+template <int TYPE>
+__global__ void __launch_bounds__(SCG_STAGED_TB, SCG_STAGED_MINBLOCKS) md_solncfl_staged_kernel(MdField const F, MdGeo const G, double * eraw)
+{
+    constexpr int ND = ct_ndim(TYPE);
+    constexpr int NEQ = ND + 2;
+    constexpr int NFC = ct_nfc(TYPE);
+    extern __shared__ double stage_smem[];
+    int32_t const i = blockIdx.x * SCG_STAGED_TB + threadIdx.x;
+    if (i >= G.nact) { return; }
+    int64_t const k = G.beg + i;
+    double un[NEQ];
+    double dist;
+    int32_t jmax;
+    cell_soln_staged<TYPE, SCG_STAGED_TB>(F, G, i, stage_smem + threadIdx.x, un, dist, jmax);
+    if (jmax >= F.ncell)
+    {
+#pragma unroll
+        for (int f = 0; f < NFC; ++f)
+        {
+            int32_t const j = G.nbr[f * int64_t(G.n) + i];
+            if (j >= F.ncell) { eraw[j - F.ncell] = un[NEQ - 1]; }
+        }
+    }
+    double cflo, cflc;
+    cfl_from_dist<ND>(F.dt / 2.0, F.gamma[k], dist, un, cflo, cflc);
+    F.cflo[k] = cflo;
+    F.cflc[k] = cflc;
+#pragma unroll
+    for (int e = 0; e < NEQ; ++e) { F.so0n[e * F.S + k] = un[e]; }
+}
+
+// Split substep, kernel 2, equation-outer variant (march mode 3): one thread per cell, adj(D)/det(D) of the
+// gradient elements parked in shared memory, then one equation at a time (cell_dsoln_eqo).
+template <int TYPE>
+struct EqoCfg
+{
+    static constexpr int TB = 64;
+    // resident CTAs per SM the register budget is sized for (shared memory allows at least as many)
+    static constexpr int MB = (TYPE == CT_HEX) ? 5 : (TYPE == CT_PRISM || TYPE == CT_PYRAMID) ? 6 : 8;
+};
+
+template <int TYPE>
+__global__ void __launch_bounds__(EqoCfg<TYPE>::TB, EqoCfg<TYPE>::MB) md_dsoln_eqo_kernel(MdField const F, MdGeo const G)
+{
+    extern __shared__ double eqo_smem[];
+    int32_t const i = blockIdx.x * EqoCfg<TYPE>::TB + threadIdx.x;
+    if (i >= G.nact) { return; }
+    cell_dsoln_eqo<TYPE, EqoCfg<TYPE>::TB>(F, G, i, eqo_smem + threadIdx.x);
+}
+
 // GradientElementTypeGroup tables for run-time lane -> face lookups (0-based local faces)
 __constant__ int8_t c_fge[9][8][3] = {
     {{0}}, {{0}}, {{0}},
@@ -1072,7 +1132,9 @@ enum CellPhase
     CP_DSOLN,
     CP_SUBSTEP,
     CP_SOLNCFL,
+    CP_SOLNCFL_STAGED,
     CP_DSOLN_COOP,
+    CP_DSOLN_EQO,
 };
 
 template <int TYPE>
@@ -1105,6 +1167,31 @@ void launch_cell_phase_t(scg_md * s, MeshGroup const & g, CellPhase ph)
     case CP_DSOLN: md_dsoln_kernel<TYPE><<<grid, 128, 0, stream()>>>(F, G); break;
     case CP_SUBSTEP: md_substep_kernel<TYPE><<<grid, 128, 0, stream()>>>(F, G, s->eraw.p); break;
     case CP_SOLNCFL: md_solncfl_kernel<TYPE><<<grid, 128, 0, stream()>>>(F, G, s->eraw.p); break;
+    case CP_SOLNCFL_STAGED:
+    {
+        constexpr int BYTES = SolnStage<TYPE, SCG_STAGED_TB>::BYTES;
+        static bool attr_set = false;
+        if (!attr_set)
+        {
+            cudaFuncSetAttribute(md_solncfl_staged_kernel<TYPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, BYTES);
+            attr_set = true;
+        }
+        md_solncfl_staged_kernel<TYPE><<<static_cast<unsigned>(ceil_div(ncl, SCG_STAGED_TB)), SCG_STAGED_TB, BYTES, stream()>>>(F, G, s->eraw.p);
+        break;
+    }
+    case CP_DSOLN_EQO:
+    {
+        constexpr int TB = EqoCfg<TYPE>::TB;
+        constexpr int BYTES = DsolnEqo<TYPE, TB>::BYTES;
+        static bool attr_set = false;
+        if (!attr_set)
+        {
+            cudaFuncSetAttribute(md_dsoln_eqo_kernel<TYPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, BYTES);
+            attr_set = true;
+        }
+        md_dsoln_eqo_kernel<TYPE><<<static_cast<unsigned>(ceil_div(ncl, TB)), TB, BYTES, stream()>>>(F, G);
+        break;
+    }
     case CP_DSOLN_COOP:
     {
         int64_t const cells_per_block = int64_t(Coop<TYPE>::WARPS) * Coop<TYPE>::CPW;
@@ -1275,11 +1362,11 @@ int substep(scg_md * s)
 {
     s->cur ^= 1; // update(): swap so0c<->so0n, so1c<->so1n (euler.hpp:123-127)
     launch_solt(s);
-    if (2 == s->fused)
+    if (2 == s->fused || 3 == s->fused)
     {
-        launch_cell_phase(s, CP_SOLNCFL);
+        launch_cell_phase(s, 3 == s->fused ? CP_SOLNCFL_STAGED : CP_SOLNCFL);
         if (int rc = launch_bc_soln(s, true)) { return rc; }
-        launch_cell_phase(s, CP_DSOLN_COOP);
+        launch_cell_phase(s, 3 == s->fused ? CP_DSOLN_EQO : CP_DSOLN_COOP);
     }
     else if (1 == s->fused)
     {
@@ -1450,7 +1537,7 @@ int scg_md_set_time_increment(scg_md * s, double time_increment)
 int scg_md_set_fused(scg_md * s, int fused)
 {
     SCG_REQUIRE(s, "scg_md_set_fused: null solver");
-    SCG_REQUIRE(fused >= 0 && fused <= 2, "scg_md_set_fused: mode must be 0, 1 or 2");
+    SCG_REQUIRE(fused >= 0 && fused <= 3, "scg_md_set_fused: mode must be 0, 1, 2 or 3");
     s->fused = fused;
     return 0;
 }

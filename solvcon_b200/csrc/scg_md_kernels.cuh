@@ -625,6 +625,374 @@ __device__ __forceinline__ void cell_cfl(MdField const & F, MdGeo const & G, int
     u[NEQ - 1] = pr_adj / ga1 + ke + MD_TINY;
 }
 
+// The thermodynamic half of calc_cfl (euler_solution.cpp:133-158) once `dist` is known.
+template <int ND>
+__device__ __forceinline__ void cfl_from_dist(double hdt, double ga, double dist, double (&u)[ND + 2], double & cflo, double & cflc)
+{
+    constexpr int NEQ = ND + 2;
+    double const ga1 = ga - 1.0;
+    double const density = u[0];
+    double momsq = 0.0;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) { momsq += u[1 + d] * u[1 + d]; }
+    double const ke = momsq / (2.0 * density);
+    double const energy = u[NEQ - 1];
+    double const pr = ga1 * (energy - ke);
+    double const pr_adj = (pr + fabs(pr)) / 2.0;
+    double const wspd = sqrt(ga * pr_adj / density) + sqrt(momsq) / density;
+    cflo = hdt * wspd / dist;
+    cflc = (cflo - 1.0) * pr_adj / (pr_adj + MD_TINY) + 1.0;
+    u[NEQ - 1] = pr_adj / ga1 + ke + MD_TINY;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Asynchronous global -> shared copies (LDGSTS).  Every thread copies the elements it will read itself,
+// so cp.async.wait_group is the only synchronisation needed -- no CTA barrier.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async8(double * smem_dst, double const * gsrc)
+{
+    unsigned const d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Jacobian in scalar form: the quantities every entry of EulerJacobian<ND>::update is built from
+// (euler_march.cpp:35-81, 94-157), and row<E>() which forms fcn[E][:] and jac[E][:][:] from them with the
+// very expressions of jaco_update_2d/3d.  Evaluating a row right where it is consumed keeps one row in
+// registers instead of the whole tensor (63 doubles in 3D).
+template <int ND>
+struct JacoS
+{
+    static constexpr int NEQ = ND + 2;
+    double ga, ga1, ga3, ga1h;
+    double m[ND];   // momenta u2..
+    double en;      // total energy
+    double v[ND];   // velocities
+    double vo2[ND]; // squared velocities
+    double vs, getot, pr;
+    double e0[ND];  // jac[NEQ-1][0][:]
+
+    template <bool FAST>
+    __device__ __forceinline__ bool set_impl(double ga_in, double const (&u)[NEQ])
+    {
+        ga = ga_in;
+        ga1 = ga - 1;
+        ga3 = ga - 3;
+        ga1h = ga1 / 2;
+        double const u1 = u[0] + MD_TINY;
+        double const rho2 = u1 * u1;
+        DivBy<FAST> by_u1(u1);
+        DivBy<FAST> by_rho2(rho2);
+        double msq = 0.0;
+#pragma unroll
+        for (int d = 0; d < ND; ++d)
+        {
+            m[d] = u[1 + d];
+            v[d] = by_u1(m[d]);
+            vo2[d] = v[d] * v[d];
+            msq = (0 == d) ? m[d] * m[d] : msq + m[d] * m[d];
+        }
+        en = u[NEQ - 1];
+        double const ke2 = by_u1(msq);
+        double const g1ke2 = ga1 * ke2;
+        vs = by_u1(ke2);
+        double const gretot = ga * en;
+        getot = by_u1(gretot);
+        pr = ga1 * en - ga1h * ke2;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) { e0[d] = by_rho2((-gretot + g1ke2) * m[d]); }
+        return by_u1.ok && by_rho2.ok;
+    }
+    __device__ __forceinline__ void set(double ga_in, double const (&u)[NEQ])
+    {
+#if SCG_SHARED_RCP
+        if (set_impl<true>(ga_in, u)) { return; }
+#endif
+        set_impl<false>(ga_in, u);
+    }
+    // fcn[E][d] and the general entries of jac[E][j][d] (structural zeros / ones are never read)
+    template <int E>
+    __device__ __forceinline__ void row(double (&fc)[ND], double (&jr)[NEQ][ND]) const
+    {
+        if (0 == E)
+        {
+#pragma unroll
+            for (int d = 0; d < ND; ++d) { fc[d] = m[d]; }
+        }
+        else if (NEQ - 1 == E)
+        {
+#pragma unroll
+            for (int d = 0; d < ND; ++d)
+            {
+                fc[d] = (pr + en) * v[d];
+                jr[0][d] = e0[d];
+                jr[NEQ - 1][d] = ga * v[d];
+#pragma unroll
+                for (int j = 1; j <= ND; ++j)
+                {
+                    jr[j][d] = (j - 1 == d) ? getot - ga1h * (vs + 2 * vo2[d]) : -ga1 * v[j - 1] * v[d];
+                }
+            }
+        }
+        else
+        {
+            constexpr int a = (E >= 1 && E <= ND) ? E - 1 : 0; // this row's momentum component
+#pragma unroll
+            for (int d = 0; d < ND; ++d)
+            {
+                fc[d] = (d == a) ? pr + m[a] * v[d] : m[a] * v[d];
+                jr[0][d] = (d == a) ? -vo2[a] + ga1h * vs : -v[a] * v[d];
+#pragma unroll
+                for (int j = 1; j <= ND; ++j)
+                {
+                    if (j - 1 == a) { jr[j][d] = (d == a) ? -ga3 * v[a] : v[d]; } // diagonal block
+                    else if (d == a) { jr[j][d] = -ga1 * v[j - 1]; }
+                    else if (d == j - 1) { jr[j][d] = v[a]; }
+                }
+                if (d == a) { jr[NEQ - 1][d] = ga1; }
+            }
+        }
+    }
+};
+
+// acc_e -= hdt * sum_d (fcn[E][d] + sum_j jac[E][j][d] * usfc[s][j]) * sn[s][d] over the sub-faces of one
+// face, in sub-face order (euler_march.cpp:281-294)
+template <int ND, int E, int MSF>
+__device__ __forceinline__ void flux_row(JacoS<ND> const & JS, double const (&usfc)[MSF][ND + 2], double const (&sn)[MSF][ND],
+                                         double hdt, int nsf, double & acc_e)
+{
+    constexpr int NEQ = ND + 2;
+    double fc[ND], jr[NEQ][ND];
+    JS.template row<E>(fc, jr);
+#pragma unroll
+    for (int s = 0; s < MSF; ++s)
+    {
+        double dot = 0.0;
+#pragma unroll
+        for (int d2 = 0; d2 < ND; ++d2)
+        {
+            double dfcn = fc[d2];
+#pragma unroll
+            for (int je = 0; je < NEQ; ++je)
+            {
+                if (2 == jkind<ND>(E, je, d2)) { dfcn += jr[je][d2] * usfc[s][je]; }
+                else if (1 == jkind<ND>(E, je, d2)) { dfcn += usfc[s][je]; }
+            }
+            dot += dfcn * sn[s][d2];
+        }
+        if (s < nsf) { acc_e -= hdt * dot; }
+    }
+}
+
+// calc_soln + the distance part of calc_cfl for one cell, third formulation ("staged"): the same terms
+// in the same order as cell_soln_rows, but no load of the face being evaluated is ever waited for.
+// Everything face f+1 needs travels global -> shared by cp.async while face f is being evaluated, into
+// three single buffers that are refilled as soon as their last reader of face f is done:
+//   N  the neighbour gather (solpt, so0c, so0t, so1c, gamma of the cell across the face)      29 rows in 3D
+//   A  cecnd, cevol of the face and sfcnd of its sub-faces                                    16 rows (hex)
+//   B  sfnml of its sub-faces                                                                 12 rows (hex)
+// N and A are consumed by the spatial term, the Taylor states and the Jacobian; they are refilled for
+// face f+1 before the flux evaluation of face f starts.  B is consumed by the flux evaluation and refilled
+// right after it.  `stage` points at this thread's column of the CTA buffer [ROWS][TB]; every thread reads
+// only what it copied itself, so cp.async.wait_group is the only synchronisation.
+template <int TYPE, int TB>
+struct SolnStage
+{
+    static constexpr int ND = ct_ndim(TYPE);
+    static constexpr int NEQ = ND + 2;
+    static constexpr int MSF = (ND == 2) ? 2 : ((TYPE == CT_TET) ? 3 : 4);
+    // N
+    static constexpr int R_JC = 0;                   // solpt[ND]
+    static constexpr int R_JU = R_JC + ND;           // so0c[NEQ]
+    static constexpr int R_JT = R_JU + NEQ;          // so0t[NEQ]
+    static constexpr int R_JG = R_JT + NEQ;          // so1c[NEQ][ND]
+    static constexpr int R_GA = R_JG + NEQ * ND;     // gamma
+    // A
+    static constexpr int R_BC = R_GA + 1;            // cecnd[f][ND]
+    static constexpr int R_VOL = R_BC + ND;          // cevol[f+1]
+    static constexpr int R_SC = R_VOL + 1;           // sfcnd[s][ND]
+    // B
+    static constexpr int R_SN = R_SC + MSF * ND;     // sfnml[s][ND]
+    static constexpr int ROWS = R_SN + MSF * ND;
+    static constexpr int BYTES = ROWS * TB * int(sizeof(double));
+};
+
+template <int TYPE, int TB>
+__device__ __forceinline__ void soln_stage_issue_an(MdField const & F, MdGeo const & G, int64_t i, int64_t j, int f, double * st)
+{
+    using L = SolnStage<TYPE, TB>;
+    constexpr int ND = L::ND, NEQ = L::NEQ;
+    int64_t const n = G.n;
+    int64_t const S = F.S;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) { cp_async8(st + (L::R_JC + d) * TB, &F.solpt[d * S + j]); }
+#pragma unroll
+    for (int e = 0; e < NEQ; ++e)
+    {
+        cp_async8(st + (L::R_JU + e) * TB, &F.so0c[e * S + j]);
+        cp_async8(st + (L::R_JT + e) * TB, &F.so0t[e * S + j]);
+#pragma unroll
+        for (int d = 0; d < ND; ++d) { cp_async8(st + (L::R_JG + e * ND + d) * TB, &F.so1c[(e * ND + d) * S + j]); }
+    }
+    cp_async8(st + L::R_GA * TB, &F.gamma[j]);
+    int const nsf = ct_fnnd(TYPE, f);
+    int const q0 = ct_sfoff(TYPE, f);
+#pragma unroll
+    for (int d = 0; d < ND; ++d) { cp_async8(st + (L::R_BC + d) * TB, &G.cecnd[(f * ND + d) * n + i]); }
+    cp_async8(st + L::R_VOL * TB, &G.cevol[(f + 1) * n + i]);
+#pragma unroll
+    for (int s = 0; s < L::MSF; ++s)
+    {
+        int64_t const q = q0 + (s < nsf ? s : nsf - 1); // a triangle face of a prism/pyramid re-reads its last sub-face
+#pragma unroll
+        for (int d = 0; d < ND; ++d) { cp_async8(st + (L::R_SC + s * ND + d) * TB, &G.sfcnd[(q * ND + d) * n + i]); }
+    }
+    cp_async_commit();
+}
+
+template <int TYPE, int TB>
+__device__ __forceinline__ void soln_stage_issue_b(MdGeo const & G, int64_t i, int f, double * st)
+{
+    using L = SolnStage<TYPE, TB>;
+    constexpr int ND = L::ND;
+    int64_t const n = G.n;
+    int const nsf = ct_fnnd(TYPE, f);
+    int const q0 = ct_sfoff(TYPE, f);
+#pragma unroll
+    for (int s = 0; s < L::MSF; ++s)
+    {
+        int64_t const q = q0 + (s < nsf ? s : nsf - 1);
+#pragma unroll
+        for (int d = 0; d < ND; ++d) { cp_async8(st + (L::R_SN + s * ND + d) * TB, &G.sfnml[(q * ND + d) * n + i]); }
+    }
+    cp_async_commit();
+}
+
+template <int TYPE, int TB>
+__device__ __forceinline__ void cell_soln_staged(MdField const & F, MdGeo const & G, int32_t i, double * st,
+                                                 double (&out)[ct_ndim(TYPE) + 2], double & dist, int32_t & jmax)
+{
+    using L = SolnStage<TYPE, TB>;
+    constexpr int ND = ct_ndim(TYPE);
+    constexpr int NEQ = ND + 2;
+    constexpr int NFC = ct_nfc(TYPE);
+    constexpr int MSF = L::MSF;
+    int64_t const n = G.n;
+    double const qdt = F.dt * 0.25;
+    double const hdt = F.dt * 0.5;
+    double acc[NEQ];
+#pragma unroll
+    for (int e = 0; e < NEQ; ++e) { acc[e] = 0.0; }
+
+    int32_t jn = G.nbr[i];
+    jmax = jn; // the largest neighbour index tells whether the cell touches a ghost
+    soln_stage_issue_an<TYPE, TB>(F, G, i, jn, 0, st);
+    soln_stage_issue_b<TYPE, TB>(G, i, 0, st);
+    jn = G.nbr[n + i]; // NFC >= 3
+    double cc[ND];
+#pragma unroll
+    for (int d = 0; d < ND; ++d) { cc[d] = F.solpt[d * F.S + G.beg + i]; }
+    dist = DBL_MAX;
+
+#pragma unroll 1
+    for (int f = 0; f < NFC; ++f)
+    {
+        int const nsf = ct_fnnd(TYPE, f);
+        double usfc[MSF][NEQ];
+        JacoS<ND> JS;
+        cp_async_wait<1>(); // N and A of this face have landed (B may still be in flight)
+        {
+            double jc[ND], ju[NEQ], jt[NEQ], jg[NEQ][ND];
+#pragma unroll
+            for (int d = 0; d < ND; ++d) { jc[d] = st[(L::R_JC + d) * TB]; }
+#pragma unroll
+            for (int e = 0; e < NEQ; ++e)
+            {
+                ju[e] = st[(L::R_JU + e) * TB];
+                jt[e] = st[(L::R_JT + e) * TB];
+#pragma unroll
+                for (int d = 0; d < ND; ++d) { jg[e][d] = st[(L::R_JG + e * ND + d) * TB]; }
+            }
+            double const ga = st[L::R_GA * TB];
+            // ---- spatial part over the basic CE (euler_march.cpp:236-249) and calc_cfl's distance
+            {
+                double bc[ND];
+#pragma unroll
+                for (int d = 0; d < ND; ++d) { bc[d] = st[(L::R_BC + d) * TB]; }
+                double const bvol = st[L::R_VOL * TB];
+#pragma unroll
+                for (int e = 0; e < NEQ; ++e)
+                {
+                    double fusp = ju[e];
+#pragma unroll
+                    for (int d = 0; d < ND; ++d) { fusp += (bc[d] - jc[d]) * jg[e][d]; }
+                    acc[e] += fusp * bvol;
+                }
+                double d2 = 0.0;
+#pragma unroll
+                for (int d = 0; d < ND; ++d)
+                {
+                    double const diff = bc[d] - cc[d];
+                    d2 += diff * diff;
+                }
+                double const r = sqrt(d2);
+                dist = (r < dist) ? r : dist; // std::min(dist, r), euler_solution.cpp:129
+            }
+            // ---- Taylor state on every sub-face (euler_march.cpp:268-280)
+#pragma unroll
+            for (int s = 0; s < MSF; ++s)
+            {
+                double sc[ND];
+#pragma unroll
+                for (int d = 0; d < ND; ++d) { sc[d] = st[(L::R_SC + s * ND + d) * TB] - jc[d]; }
+#pragma unroll
+                for (int e = 0; e < NEQ; ++e)
+                {
+                    usfc[s][e] = qdt * jt[e];
+#pragma unroll
+                    for (int d = 0; d < ND; ++d) { usfc[s][e] += sc[d] * jg[e][d]; }
+                }
+            }
+            JS.set(ga, ju);
+        }
+        // ---- N and A are free: start the copies of the next face
+        if (f + 1 < NFC)
+        {
+            soln_stage_issue_an<TYPE, TB>(F, G, i, jn, f + 1, st);
+            jmax = jn > jmax ? jn : jmax;
+            if (f + 2 < NFC) { jn = G.nbr[(f + 2) * n + i]; }
+            cp_async_wait<1>(); // B of this face has landed
+        }
+        else { cp_async_wait<0>(); }
+        double sn[MSF][ND];
+#pragma unroll
+        for (int s = 0; s < MSF; ++s)
+        {
+#pragma unroll
+            for (int d = 0; d < ND; ++d) { sn[s][d] = st[(L::R_SN + s * ND + d) * TB]; }
+        }
+        if (f + 1 < NFC) { soln_stage_issue_b<TYPE, TB>(G, i, f + 1, st); }
+        // ---- temporal part, one equation (Jacobian row) at a time (euler_march.cpp:281-294)
+        flux_row<ND, 0, MSF>(JS, usfc, sn, hdt, nsf, acc[0]);
+        flux_row<ND, 1, MSF>(JS, usfc, sn, hdt, nsf, acc[1]);
+        flux_row<ND, 2, MSF>(JS, usfc, sn, hdt, nsf, acc[2]);
+        flux_row<ND, 3, MSF>(JS, usfc, sn, hdt, nsf, acc[3]);
+        if (NEQ > 4) { flux_row<ND, (NEQ > 4 ? 4 : 0), MSF>(JS, usfc, sn, hdt, nsf, acc[NEQ - 1]); }
+    }
+    double const cvol = G.cevol[i];
+#if SCG_SHARED_RCP
+    DivBy<true> by_cvol(cvol);
+#pragma unroll
+    for (int e = 0; e < NEQ; ++e) { out[e] = by_cvol(acc[e]); }
+    if (by_cvol.ok) { return; }
+#endif
+#pragma unroll
+    for (int e = 0; e < NEQ; ++e) { out[e] = acc[e] / cvol; }
+}
+
+
 // EulerCore::calc_dsoln for one cell, euler_gradient.cpp:23-130, with the GradientElement constructor
 // (GradientElement.cpp:137-213) and calc_gge_centroid (:81-133) expanded in place.  `un` is the cell's
 // own so0n (energy already fixed by calc_cfl), `acfl_in` is cflc of the cell.
@@ -798,6 +1166,252 @@ __device__ __forceinline__ void cell_dsoln(MdField const & F, MdGeo const & G, i
         }
 #pragma unroll
         for (int d = 0; d < ND; ++d) { out[e][d] = o[d]; }
+    }
+}
+
+// EulerCore::calc_dsoln for one cell, equation-outer formulation (march mode 3).
+//
+// cell_dsoln keeps every FGE gradient of every equation alive until the limiter has run (about 200
+// doubles per cell).  The limiter only couples the gradients of ONE equation, so here the equation-
+// independent part of every gradient element -- adj(D) and det(D), euler_gradient.cpp:74-77 -- is formed
+// once and parked in shared memory (this thread's column of `sadj`, [NFGE][ND*ND+1][TB]); then one
+// equation at a time takes its Taylor differences (euler_gradient.cpp:60-72), solves the NFGE systems,
+// weighs and limits them (:79-128) and stores its ND gradient components.  Same operations on the same
+// operands in the same order as cell_dsoln; only the schedule differs.
+template <int TYPE, int TB>
+struct DsolnEqo
+{
+    static constexpr int ND = ct_ndim(TYPE);
+    static constexpr int NFGE = ct_nfge(TYPE);
+    static constexpr int RPF = ND * ND + 1; // rows per gradient element: adj, det
+    static constexpr int ROWS = NFGE * RPF;
+    static constexpr int BYTES = ROWS * TB * int(sizeof(double));
+};
+
+template <int TYPE, int TB>
+__device__ __forceinline__ void cell_dsoln_eqo(MdField const & F, MdGeo const & G, int32_t i, double * sadj)
+{
+    constexpr int ND = ct_ndim(TYPE);
+    constexpr int NEQ = ND + 2;
+    constexpr int NFC = ct_nfc(TYPE);
+    constexpr int NFGE = ct_nfge(TYPE);
+    constexpr int RPF = ND * ND + 1;
+    int64_t const n = G.n;
+    int64_t const S = F.S;
+    int64_t const k = G.beg + i;
+    double const hdt = F.dt * 0.5;
+    double const acfl = fabs(F.cflc[k]);
+    double const sgm0 = F.sigma0 / acfl;
+    double const tau = F.taumin + acfl * F.tauscale;
+    double const ofg1 = 1.0 / NFGE;
+
+    int32_t rcl[NFC];
+    double jdis[NFC][ND];
+    {
+        // ---- gradient element geometry (GradientElement.cpp:137-213, :81-133)
+        double icecnd[ND];
+#pragma unroll
+        for (int d = 0; d < ND; ++d) { icecnd[d] = F.solpt[d * S + k]; }
+        double gp[NFC][ND];
+#pragma unroll
+        for (int f = 0; f < NFC; ++f) { rcl[f] = G.nbr[f * n + i]; }
+#pragma unroll
+        for (int f = 0; f < NFC; ++f)
+        {
+            int64_t const j = rcl[f];
+#pragma unroll
+            for (int d = 0; d < ND; ++d)
+            {
+                double const mid = G.cecnd[(f * ND + d) * n + i];
+                double const jce = F.solpt[d * S + j];
+                gp[f][d] = mid + tau * (jce - mid);
+                jdis[f][d] = gp[f][d] - jce; // completed below: + icecnd - cnd
+            }
+        }
+        double avg[ND];
+#pragma unroll
+        for (int d = 0; d < ND; ++d) { avg[d] = 0.0; }
+#pragma unroll
+        for (int f = 0; f < NFC; ++f)
+        {
+#pragma unroll
+            for (int d = 0; d < ND; ++d) { avg[d] += gp[f][d]; }
+        }
+        {
+            double a2[ND];
+            DivBy<true> by_nfc(static_cast<double>(NFC));
+#pragma unroll
+            for (int d = 0; d < ND; ++d) { a2[d] = by_nfc(avg[d]); }
+            if (!by_nfc.ok)
+            {
+#pragma unroll
+                for (int d = 0; d < ND; ++d) { a2[d] = avg[d] / NFC; }
+            }
+#pragma unroll
+            for (int d = 0; d < ND; ++d) { avg[d] = a2[d]; }
+        }
+        double cnd[ND];
+#pragma unroll
+        for (int d = 0; d < ND; ++d) { cnd[d] = 0.0; }
+        double voc = 0.0;
+#pragma unroll
+        for (int isub = 0; isub < NFGE; ++isub)
+        {
+            double subcnd[ND];
+            double dst[ND][ND];
+#pragma unroll
+            for (int d = 0; d < ND; ++d) { subcnd[d] = avg[d]; }
+#pragma unroll
+            for (int ivx = 0; ivx < ND; ++ivx)
+            {
+                int const fl = fge_face(TYPE, isub, ivx);
+#pragma unroll
+                for (int d = 0; d < ND; ++d)
+                {
+                    subcnd[d] += gp[fl][d];
+                    dst[ivx][d] = gp[fl][d] - avg[d];
+                }
+            }
+#pragma unroll
+            for (int d = 0; d < ND; ++d) { subcnd[d] /= static_cast<double>(ND + 1); }
+            double const vob = det_n<ND>(dst);
+            voc += vob;
+#pragma unroll
+            for (int d = 0; d < ND; ++d) { cnd[d] += subcnd[d] * vob; }
+        }
+        {
+            double c2[ND];
+            DivBy<true> by_voc(voc);
+#pragma unroll
+            for (int d = 0; d < ND; ++d) { c2[d] = by_voc(cnd[d]); }
+            if (!by_voc.ok)
+            {
+#pragma unroll
+                for (int d = 0; d < ND; ++d) { c2[d] = cnd[d] / voc; }
+            }
+#pragma unroll
+            for (int d = 0; d < ND; ++d) { cnd[d] = c2[d]; }
+        }
+        // ---- displacements (GradientElement.cpp:196-211); idis replaces gp
+#pragma unroll
+        for (int f = 0; f < NFC; ++f)
+        {
+#pragma unroll
+            for (int d = 0; d < ND; ++d)
+            {
+                jdis[f][d] = jdis[f][d] + icecnd[d] - cnd[d];
+                gp[f][d] = gp[f][d] - cnd[d];
+            }
+        }
+        // ---- adj(D), det(D) of every gradient element -> shared memory
+#pragma unroll
+        for (int ifge = 0; ifge < NFGE; ++ifge)
+        {
+            double dst[ND][ND], adj[ND][ND];
+#pragma unroll
+            for (int ivx = 0; ivx < ND; ++ivx)
+            {
+                int const fl = fge_face(TYPE, ifge, ivx);
+#pragma unroll
+                for (int d = 0; d < ND; ++d) { dst[ivx][d] = gp[fl][d]; }
+            }
+            adj_n<ND>(dst, adj);
+            double const det = det_n<ND>(dst);
+#pragma unroll
+            for (int a = 0; a < ND; ++a)
+            {
+#pragma unroll
+                for (int b = 0; b < ND; ++b) { sadj[(ifge * RPF + a * ND + b) * TB] = adj[a][b]; }
+            }
+            sadj[(ifge * RPF + ND * ND) * TB] = det;
+        }
+    }
+
+    // ---- one equation at a time
+#pragma unroll 1
+    for (int e = 0; e < NEQ; ++e)
+    {
+        // adj/det are re-read from shared memory by every equation: without this barrier the compiler hoists
+        // the NFGE*(ND*ND+1) loop-invariant loads out of the loop and spills them
+        asm volatile("" ::: "memory");
+        double const un = F.so0n[e * S + k];
+        double udf[NFC];
+#pragma unroll
+        for (int f = 0; f < NFC; ++f)
+        {
+            int64_t const j = rcl[f];
+            double val = F.so0c[e * S + j] + hdt * F.so0t[e * S + j] - un;
+#pragma unroll
+            for (int d = 0; d < ND; ++d) { val += jdis[f][d] * F.so1c[(e * ND + d) * S + j]; }
+            udf[f] = val;
+        }
+        double grad[NFGE][ND], w[NFGE];
+        double wacc = 0.0;
+#pragma unroll
+        for (int ifge = 0; ifge < NFGE; ++ifge)
+        {
+            double rr[ND];
+#pragma unroll
+            for (int a = 0; a < ND; ++a)
+            {
+                double r = 0.0;
+#pragma unroll
+                for (int b = 0; b < ND; ++b) { r += sadj[(ifge * RPF + a * ND + b) * TB] * udf[fge_face(TYPE, ifge, b)]; }
+                rr[a] = r;
+            }
+            double const det = sadj[(ifge * RPF + ND * ND) * TB];
+            {
+                DivBy<true> by_det(det);
+#pragma unroll
+                for (int a = 0; a < ND; ++a) { grad[ifge][a] = by_det(rr[a]); }
+                if (!by_det.ok)
+                {
+#pragma unroll
+                    for (int a = 0; a < ND; ++a) { grad[ifge][a] = rr[a] / det; }
+                }
+            }
+            double sq = 0.0;
+#pragma unroll
+            for (int d = 0; d < ND; ++d) { sq += grad[ifge][d] * grad[ifge][d]; }
+            double const wgt = 1.0 / sqrt(sq + MD_ALMOST_ZERO);
+            wacc += wgt;
+            w[ifge] = wgt;
+        }
+        // ---- W-3/4 limiter (euler_gradient.cpp:90-128)
+        {
+            double q[NFGE];
+            DivBy<true> by_wacc(wacc);
+#pragma unroll
+            for (int ifge = 0; ifge < NFGE; ++ifge) { q[ifge] = by_wacc(w[ifge]); }
+            if (!by_wacc.ok)
+            {
+#pragma unroll
+                for (int ifge = 0; ifge < NFGE; ++ifge) { q[ifge] = w[ifge] / wacc; }
+            }
+#pragma unroll
+            for (int ifge = 0; ifge < NFGE; ++ifge) { w[ifge] = q[ifge] - ofg1; }
+        }
+        double wmax = 0.0, wmin = 0.0;
+#pragma unroll
+        for (int ifge = 0; ifge < NFGE; ++ifge)
+        {
+            wmax = fmax(wmax, w[ifge]);
+            wmin = fmin(wmin, w[ifge]);
+        }
+        double const sm = fmin((1.0 - ofg1) / (wmax + MD_ALMOST_ZERO), -ofg1 / (wmin - MD_ALMOST_ZERO));
+        double const sigma_max = fmin(sm, sgm0);
+        double o[ND];
+#pragma unroll
+        for (int d = 0; d < ND; ++d) { o[d] = 0.0; }
+#pragma unroll
+        for (int isub = 0; isub < NFGE; ++isub)
+        {
+            double const wgt = ofg1 + sigma_max * w[isub];
+#pragma unroll
+            for (int d = 0; d < ND; ++d) { o[d] += wgt * grad[isub][d]; }
+        }
+#pragma unroll
+        for (int d = 0; d < ND; ++d) { F.so1n[(e * ND + d) * S + k] = o[d]; }
     }
 }
 

@@ -93,7 +93,7 @@ def test_md_geometry_and_phases(gpu, bridge, name):
 
 @pytest.mark.parametrize("name", ["mixed2d", "step2d", "mixed3d", "hex3d", "tet3d", "prism3d", "tri2d"])
 @pytest.mark.parametrize("order", ["none", "morton", "rcm"])
-@pytest.mark.parametrize("fused", [2, 1, 0])
+@pytest.mark.parametrize("fused", [3, 2, 1, 0])
 def test_md_march_matches(gpu, bridge, name, order, fused):
     """march(N) with every cell ordering, fused and per-phase kernels: identical to the checker."""
     b = bridge
