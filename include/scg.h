@@ -208,8 +208,9 @@ SCG_API int scg_md_create(scg_md ** out, scg_mesh * mesh, double time_increment)
 SCG_API int scg_md_destroy(scg_md * s);
 SCG_API int scg_md_set_params(scg_md * s, double sigma0, double taumin, double tauscale); /* euler.hpp:99-104 */
 SCG_API int scg_md_set_time_increment(scg_md * s, double time_increment);
-/* march kernels: 2 (default) soln+cfl kernel + cooperative (lane-group per cell) dsoln kernel;
- * 1 one fused thread-per-cell kernel; 0 one kernel per reference phase.  All three are bit-identical. */
+/* march kernels: 3 (default) cp.async-staged soln+cfl kernel + equation-outer dsoln kernel;
+ * 2 soln+cfl kernel + cooperative (lane-group per cell) dsoln kernel; 1 one fused thread-per-cell kernel;
+ * 0 one kernel per reference phase.  All four are bit-identical. */
 SCG_API int scg_md_set_fused(scg_md * s, int fused);
 /* init_solution(gamma, rho, v, p), euler_solution.cpp:54-99 (v has 3 entries) */
 SCG_API int scg_md_init_solution(scg_md * s, double gamma, double rho, const double * v, double p);

@@ -105,7 +105,7 @@ def build_case_3d_dist(ncell_target, rank, world, local_device, order="morton", 
 class MD3DWorkload:
     name = "md3d"
     dtype = "f64"
-    dominant_kernel = "one substep = md_solt + md_solncfl<hex|prism|tet> + md_dsoln_coop<hex|prism|tet> + boundary kernels"
+    dominant_kernel = "one substep = md_solt + md_solncfl_staged<hex|prism|tet> + md_dsoln_eqo<hex|prism|tet> + boundary kernels"
 
     def __init__(self, ncell, chunk, order="morton", kinds="hpt"):
         self.ncell_target = int(ncell)

@@ -329,11 +329,21 @@ __global__ void __launch_bounds__(128, SCG_SOLN_MINBLOCKS) md_solncfl_kernel(MdF
 #ifndef SCG_STAGED_TB
 #define SCG_STAGED_TB 128
 #endif
-#ifndef SCG_STAGED_MINBLOCKS
-#define SCG_STAGED_MINBLOCKS 3
+// resident CTAs per SM the register budget is sized for: the 3D flux evaluation wants ~250 registers (two
+// CTAs); tetrahedra and the 2D types get by with 168 (three CTAs)
+#ifndef SCG_STAGED_MB_BIG
+#define SCG_STAGED_MB_BIG 2
+#endif
+#ifndef SCG_STAGED_MB_SMALL
+#define SCG_STAGED_MB_SMALL 3
 #endif
 template <int TYPE>
-__global__ void __launch_bounds__(SCG_STAGED_TB, SCG_STAGED_MINBLOCKS) md_solncfl_staged_kernel(MdField const F, MdGeo const G, double * eraw)
+struct StagedCfg
+{
+    static constexpr int MB = (TYPE == CT_HEX || TYPE == CT_PRISM || TYPE == CT_PYRAMID) ? SCG_STAGED_MB_BIG : SCG_STAGED_MB_SMALL;
+};
+template <int TYPE>
+__global__ void __launch_bounds__(SCG_STAGED_TB, StagedCfg<TYPE>::MB) md_solncfl_staged_kernel(MdField const F, MdGeo const G, double * eraw)
 {
     constexpr int ND = ct_ndim(TYPE);
     constexpr int NEQ = ND + 2;
@@ -365,12 +375,32 @@ __global__ void __launch_bounds__(SCG_STAGED_TB, SCG_STAGED_MINBLOCKS) md_solncf
 
 // Split substep, kernel 2, equation-outer variant (march mode 3): one thread per cell, adj(D)/det(D) of the
 // gradient elements parked in shared memory, then one equation at a time (cell_dsoln_eqo).
+#ifndef SCG_EQO_MB_HEX
+#define SCG_EQO_MB_HEX 4
+#endif
+#ifndef SCG_EQO_MB_PRISM
+#define SCG_EQO_MB_PRISM 6
+#endif
+#ifndef SCG_EQO_MB_TET
+#define SCG_EQO_MB_TET 8
+#endif
+#ifndef SCG_EQO_PF_HEX
+#define SCG_EQO_PF_HEX 1
+#endif
+#ifndef SCG_EQO_PF_PRISM
+#define SCG_EQO_PF_PRISM 0
+#endif
+#ifndef SCG_EQO_PF_TET
+#define SCG_EQO_PF_TET 0
+#endif
 template <int TYPE>
 struct EqoCfg
 {
+    // prefetch the next equation's neighbour gather into registers
+    static constexpr bool PF = (TYPE == CT_HEX) ? SCG_EQO_PF_HEX : (TYPE == CT_PRISM || TYPE == CT_PYRAMID) ? SCG_EQO_PF_PRISM : SCG_EQO_PF_TET;
     static constexpr int TB = 64;
     // resident CTAs per SM the register budget is sized for (shared memory allows at least as many)
-    static constexpr int MB = (TYPE == CT_HEX) ? 5 : (TYPE == CT_PRISM || TYPE == CT_PYRAMID) ? 6 : 8;
+    static constexpr int MB = (TYPE == CT_HEX) ? SCG_EQO_MB_HEX : (TYPE == CT_PRISM || TYPE == CT_PYRAMID) ? SCG_EQO_MB_PRISM : SCG_EQO_MB_TET;
 };
 
 template <int TYPE>
@@ -379,7 +409,7 @@ __global__ void __launch_bounds__(EqoCfg<TYPE>::TB, EqoCfg<TYPE>::MB) md_dsoln_e
     extern __shared__ double eqo_smem[];
     int32_t const i = blockIdx.x * EqoCfg<TYPE>::TB + threadIdx.x;
     if (i >= G.nact) { return; }
-    cell_dsoln_eqo<TYPE, EqoCfg<TYPE>::TB>(F, G, i, eqo_smem + threadIdx.x);
+    cell_dsoln_eqo<TYPE, EqoCfg<TYPE>::TB, EqoCfg<TYPE>::PF>(F, G, i, eqo_smem + threadIdx.x);
 }
 
 // GradientElementTypeGroup tables for run-time lane -> face lookups (0-based local faces)
@@ -1065,7 +1095,8 @@ struct scg_md
     int cur = 0;                                               // so0[cur] is so0c, so0[1-cur] is so0n
     DevBuf<double> so0[2], so1[2], so0t, gamma, cflo, cflc, solpt, geo, eraw, stage, red, clvol;
     bool have_clvol = false;
-    int fused = 2; // 0: one kernel per reference phase, 1: one fused thread-per-cell kernel, 2: soln+cfl kernel + cooperative dsoln kernel
+    int fused = 3; // 0: one kernel per reference phase, 1: one fused thread-per-cell kernel, 2: soln+cfl kernel + cooperative dsoln kernel,
+                   // 3: cp.async-staged soln+cfl kernel + equation-outer dsoln kernel
     std::vector<BcReg> regs;
     bool bc_dirty = true;
     int32_t nbc = 0;

@@ -1176,8 +1176,9 @@ __device__ __forceinline__ void cell_dsoln(MdField const & F, MdGeo const & G, i
 // independent part of every gradient element -- adj(D) and det(D), euler_gradient.cpp:74-77 -- is formed
 // once and parked in shared memory (this thread's column of `sadj`, [NFGE][ND*ND+1][TB]); then one
 // equation at a time takes its Taylor differences (euler_gradient.cpp:60-72), solves the NFGE systems,
-// weighs and limits them (:79-128) and stores its ND gradient components.  Same operations on the same
-// operands in the same order as cell_dsoln; only the schedule differs.
+// weighs and limits them (:79-128) and stores its ND gradient components.  The neighbour gather of
+// equation e+1 is issued into a second register set before the arithmetic of equation e starts.  Same
+// operations on the same operands in the same order as cell_dsoln; only the schedule differs.
 template <int TYPE, int TB>
 struct DsolnEqo
 {
@@ -1188,7 +1189,31 @@ struct DsolnEqo
     static constexpr int BYTES = ROWS * TB * int(sizeof(double));
 };
 
-template <int TYPE, int TB>
+// what one equation of calc_dsoln gathers through the neighbour indices (euler_gradient.cpp:66-69)
+template <int TYPE>
+struct EqoGather
+{
+    static constexpr int ND = ct_ndim(TYPE);
+    static constexpr int NFC = ct_nfc(TYPE);
+    double un;
+    double u[NFC], t[NFC], g[NFC][ND];
+    __device__ __forceinline__ void load(MdField const & F, int32_t const (&rcl)[NFC], int64_t k, int e)
+    {
+        int64_t const S = F.S;
+        un = F.so0n[e * S + k];
+#pragma unroll
+        for (int f = 0; f < NFC; ++f)
+        {
+            int64_t const j = rcl[f];
+            u[f] = F.so0c[e * S + j];
+            t[f] = F.so0t[e * S + j];
+#pragma unroll
+            for (int d = 0; d < ND; ++d) { g[f][d] = F.so1c[(e * ND + d) * S + j]; }
+        }
+    }
+};
+
+template <int TYPE, int TB, bool PF>
 __device__ __forceinline__ void cell_dsoln_eqo(MdField const & F, MdGeo const & G, int32_t i, double * sadj)
 {
     constexpr int ND = ct_ndim(TYPE);
@@ -1207,6 +1232,7 @@ __device__ __forceinline__ void cell_dsoln_eqo(MdField const & F, MdGeo const & 
 
     int32_t rcl[NFC];
     double jdis[NFC][ND];
+    EqoGather<TYPE> cur;
     {
         // ---- gradient element geometry (GradientElement.cpp:137-213, :81-133)
         double icecnd[ND];
@@ -1215,6 +1241,7 @@ __device__ __forceinline__ void cell_dsoln_eqo(MdField const & F, MdGeo const & 
         double gp[NFC][ND];
 #pragma unroll
         for (int f = 0; f < NFC; ++f) { rcl[f] = G.nbr[f * n + i]; }
+        if (PF) { cur.load(F, rcl, k, 0); } // the first equation's gather travels while the geometry is worked out
 #pragma unroll
         for (int f = 0; f < NFC; ++f)
         {
@@ -1245,7 +1272,7 @@ __device__ __forceinline__ void cell_dsoln_eqo(MdField const & F, MdGeo const & 
             if (!by_nfc.ok)
             {
 #pragma unroll
-                for (int d = 0; d < ND; ++d) { a2[d] = avg[d] / NFC; }
+                for (int d = 0; d < ND; ++d) { a2[d] = avg[d] / static_cast<double>(NFC); }
             }
 #pragma unroll
             for (int d = 0; d < ND; ++d) { avg[d] = a2[d]; }
@@ -1334,17 +1361,19 @@ __device__ __forceinline__ void cell_dsoln_eqo(MdField const & F, MdGeo const & 
         // adj/det are re-read from shared memory by every equation: without this barrier the compiler hoists
         // the NFGE*(ND*ND+1) loop-invariant loads out of the loop and spills them
         asm volatile("" ::: "memory");
-        double const un = F.so0n[e * S + k];
+        EqoGather<TYPE> nxt;
+        if (PF) { nxt.load(F, rcl, k, e + 1 < NEQ ? e + 1 : e); }
+        else { cur.load(F, rcl, k, e); }
         double udf[NFC];
 #pragma unroll
         for (int f = 0; f < NFC; ++f)
         {
-            int64_t const j = rcl[f];
-            double val = F.so0c[e * S + j] + hdt * F.so0t[e * S + j] - un;
+            double val = cur.u[f] + hdt * cur.t[f] - cur.un;
 #pragma unroll
-            for (int d = 0; d < ND; ++d) { val += jdis[f][d] * F.so1c[(e * ND + d) * S + j]; }
+            for (int d = 0; d < ND; ++d) { val += jdis[f][d] * cur.g[f][d]; }
             udf[f] = val;
         }
+        if (PF) { cur = nxt; }
         double grad[NFGE][ND], w[NFGE];
         double wacc = 0.0;
 #pragma unroll

@@ -311,8 +311,9 @@ class EulerCore:
 
     # -- additive API -----------------------------------------------------------------------------------
     def set_fused(self, mode):
-        """march() kernels: 2 (default) soln+cfl kernel + cooperative dsoln kernel, 1 one fused
-        thread-per-cell kernel, 0 one kernel per reference phase (bit-identical results)."""
+        """march() kernels: 3 (default) cp.async-staged soln+cfl kernel + equation-outer dsoln kernel,
+        2 soln+cfl kernel + cooperative dsoln kernel, 1 one fused thread-per-cell kernel, 0 one kernel per
+        reference phase (bit-identical results)."""
         _lib.check(self._lib.scg_md_set_fused(self._h, int(mode)))
 
     def reduce(self, clvol=None):
