@@ -350,6 +350,8 @@ def main():
                 "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
                 "strict_fp": bool(lib.scg_build_is_strict())}
         print(json.dumps(line))
+        if os.environ.get("SCG_TIMING") == "1":   # diagnostics: per-kernel device times to stderr
+            lib.scg_timing_dump()
     if dist is not None:
         dist.destroy_process_group()
 

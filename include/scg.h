@@ -44,6 +44,9 @@ SCG_API int scg_sync(void);
 SCG_API int scg_mem_info(int64_t * free_bytes, int64_t * total_bytes);
 /* kernels launched by this library since the last reset (for bench.py "gpu_launches") */
 SCG_API int64_t scg_launch_count(int reset);
+/* diagnostics: with SCG_TIMING=1 in the environment every multidim kernel launch is bracketed by events;
+ * this prints launches / average / share per kernel to stderr and clears the records */
+SCG_API int scg_timing_dump(void);
 /* CUDA-event timer on the library's work stream: start, stop -> elapsed ms */
 SCG_API int scg_timer_start(void);
 SCG_API int scg_timer_stop(double * elapsed_ms);
@@ -235,6 +238,11 @@ SCG_API int scg_md_normal_matrix(scg_md * s, int32_t ifc, double * out);
  * pair, out_fast = the shared-reciprocal quotient, ok = its range test, out_ref = the plain a / b.  Wherever
  * ok is 1 the two must be bit-equal (tests/test_gpu_md.py). */
 SCG_API int scg_selftest_div(const double * a, const double * b, double * out_fast, double * out_ref, int32_t * ok, int64_t n);
+
+/* self test of the deferred-range-test square root and reciprocal (scg_md_kernels.cuh, sqrt_fast / rcp_fast):
+ * out_fast[0:n] = sqrt_fast(x), out_fast[n:2n] = rcp_fast(x), ok likewise, out_ref = sqrt(x), 1.0 / x.  Wherever
+ * ok is 1 fast and ref must be bit-equal (tests/test_gpu_md.py). */
+SCG_API int scg_selftest_rsq(const double * x, double * out_fast, double * out_ref, int32_t * ok, int64_t n);
 
 /* halo exchange support for domain decomposition (one process per GPU; the caller moves the packed
  * buffers with NCCL send/recv, see solvcon_b200/decomp.py).  A partition is a StaticMesh of the owned cells

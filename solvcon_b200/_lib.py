@@ -42,6 +42,7 @@ _SIGNATURES = {
     "scg_sync": (C.c_int, []),
     "scg_mem_info": (C.c_int, [I64P, I64P]),
     "scg_launch_count": (C.c_int64, [C.c_int]),
+    "scg_timing_dump": (C.c_int, []),
     "scg_timer_start": (C.c_int, []),
     "scg_timer_stop": (C.c_int, [DP]),
     "scg_flush_l2": (C.c_int, [C.c_int64]),
@@ -107,6 +108,7 @@ _SIGNATURES = {
     "scg_md_algorithmic_bytes": (C.c_int, [C.c_void_p, I64P]),
     "scg_md_normal_matrix": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "scg_selftest_div": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
+    "scg_selftest_rsq": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     "scg_md_halo_set": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]),
     "scg_md_halo_pack": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), I64P]),
     "scg_md_halo_unpack": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),

@@ -40,6 +40,18 @@ int fail(char const * fmt, ...); // sets the error and returns -1
 cudaStream_t stream();   // the library's work stream (valid after scg_init)
 int ensure_init();       // lazily binds device 0 if scg_init was never called
 void count_launch(int n = 1);
+
+// Per-kernel device timing for diagnostics (SCG_TIMING=1 in the environment): a TimeScope around a launch
+// records two events on the work stream; scg_timing_dump() prints launches / average / total per key.
+bool timing_on();
+void timing_begin(char const * key);
+void timing_end();
+struct TimeScope
+{
+    bool on;
+    explicit TimeScope(char const * key) : on(timing_on()) { if (on) { timing_begin(key); } }
+    ~TimeScope() { if (on) { timing_end(); } }
+};
 int sm_count();
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

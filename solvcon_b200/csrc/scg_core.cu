@@ -2,6 +2,12 @@
 // CUDA-event timer, L2 flush, pinned host memory.
 #include "scg_common.cuh"
 
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <string>
+#include <vector>
+
 #include <atomic>
 #include <cstring>
 
@@ -41,6 +47,39 @@ int fail(char const * fmt, ...)
 
 cudaStream_t stream() { return g_stream; }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+namespace
+{
+struct TimingRec
+{
+    std::string key;
+    cudaEvent_t a, b;
+};
+std::vector<TimingRec> g_timing;
+int g_timing_state = -1;
+} // namespace
+
+bool timing_on()
+{
+    if (g_timing_state < 0)
+    {
+        char const * e = std::getenv("SCG_TIMING");
+        g_timing_state = (e && e[0] == '1') ? 1 : 0;
+    }
+    return 1 == g_timing_state;
+}
+
+void timing_begin(char const * key)
+{
+    TimingRec r;
+    r.key = key;
+    cudaEventCreate(&r.a);
+    cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, g_stream);
+    g_timing.push_back(r);
+}
+
+void timing_end() { cudaEventRecord(g_timing.back().b, g_stream); }
 int sm_count() { return g_sm_count; }
 
 static int init_device(int device)
@@ -141,6 +180,32 @@ int scg_mem_info(int64_t * free_bytes, int64_t * total_bytes)
     SCG_CUDA(cudaMemGetInfo(&f, &t));
     *free_bytes = static_cast<int64_t>(f);
     *total_bytes = static_cast<int64_t>(t);
+    return 0;
+}
+
+int scg_timing_dump(void)
+{
+    if (g_timing.empty()) { return 0; }
+    cudaStreamSynchronize(g_stream);
+    std::map<std::string, std::pair<int, double>> agg;
+    double total = 0.0;
+    for (auto & r : g_timing)
+    {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        auto & x = agg[r.key];
+        x.first += 1;
+        x.second += ms;
+        total += ms;
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    g_timing.clear();
+    for (auto const & kv : agg)
+    {
+        std::fprintf(stderr, "[scg timing] %-28s %6d x %10.1f us  %5.1f%%\n", kv.first.c_str(), kv.second.first,
+                     1e3 * kv.second.second / kv.second.first, 100.0 * kv.second.second / total);
+    }
     return 0;
 }
 

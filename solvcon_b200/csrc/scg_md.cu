@@ -5,6 +5,7 @@
 #include "scg_md_kernels.cuh"
 
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 
 using namespace scg;
@@ -1066,6 +1067,19 @@ __global__ void md_halo_unpack_kernel(double * so0, double * so1, double * solpt
 }
 
 // bit-exactness self test of DivBy: out_fast[i] = DivBy<true>(b[i])(a[i]) (0/1 flag in ok[i]), out_ref[i] = a[i] / b[i]
+__global__ void md_selftest_rsq_kernel(double const * x, double * out_fast, double * out_ref, int * okf, int64_t n)
+{
+    int64_t const i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) { return; }
+    bool oks = true, okr = true;
+    out_fast[i] = sqrt_fast(x[i], oks);
+    out_fast[n + i] = rcp_fast(x[i], okr);
+    okf[i] = oks ? 1 : 0;
+    okf[n + i] = okr ? 1 : 0;
+    out_ref[i] = sqrt(x[i]);
+    out_ref[n + i] = 1.0 / x[i];
+}
+
 __global__ void md_selftest_div_kernel(double const * a, double const * b, double * out_fast, double * out_ref, int * okf, int64_t n)
 {
     int64_t const i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -1177,6 +1191,10 @@ void launch_cell_phase_t(scg_md * s, MeshGroup const & g, CellPhase ph)
     int64_t const ncl = all_cells ? g.n : g.nact;
     if (0 == ncl) { return; }
     unsigned const grid = static_cast<unsigned>(ceil_div(ncl, 128));
+    static char const * const phase_name[] = {"prepare", "soln", "cfl", "dsoln", "substep", "solncfl", "solncfl_staged", "dsoln_coop", "dsoln_eqo"};
+    char key[48];
+    if (timing_on()) { std::snprintf(key, sizeof key, "%s<%d>", phase_name[ph], TYPE); }
+    TimeScope const ts(key);
     switch (ph)
     {
     case CP_PREPARE:
@@ -1254,6 +1272,7 @@ void launch_solt(scg_md * s)
 {
     MdField const F = field_of(s);
     unsigned const grid = static_cast<unsigned>(ceil_div(F.T, 256));
+    TimeScope const ts("solt");
     if (2 == s->ndim) { md_solt_kernel<2><<<grid, 256, 0, stream()>>>(F, 0, F.T); }
     else { md_solt_kernel<3><<<grid, 256, 0, stream()>>>(F, 0, F.T); }
     count_launch();
@@ -1770,6 +1789,25 @@ int scg_selftest_div(const double * a, const double * b, double * out_fast, doub
     SCG_CUDA(cudaMemcpyAsync(out_fast, df.p, sizeof(double) * n, cudaMemcpyDeviceToHost, stream()));
     SCG_CUDA(cudaMemcpyAsync(out_ref, dr.p, sizeof(double) * n, cudaMemcpyDeviceToHost, stream()));
     SCG_CUDA(cudaMemcpyAsync(ok, dk.p, sizeof(int) * n, cudaMemcpyDeviceToHost, stream()));
+    SCG_CUDA(cudaStreamSynchronize(stream()));
+    return 0;
+}
+
+int scg_selftest_rsq(const double * x, double * out_fast, double * out_ref, int32_t * ok, int64_t n)
+{
+    if (int rc = ensure_init()) { return rc; }
+    DevBuf<double> dx, df, dr;
+    DevBuf<int> dk;
+    SCG_CUDA(dx.alloc(n));
+    SCG_CUDA(df.alloc(2 * n));
+    SCG_CUDA(dr.alloc(2 * n));
+    SCG_CUDA(dk.alloc(2 * n));
+    SCG_CUDA(cudaMemcpyAsync(dx.p, x, sizeof(double) * n, cudaMemcpyHostToDevice, stream()));
+    md_selftest_rsq_kernel<<<static_cast<unsigned>(ceil_div(n, 256)), 256, 0, stream()>>>(dx.p, df.p, dr.p, dk.p, n);
+    count_launch();
+    SCG_CUDA(cudaMemcpyAsync(out_fast, df.p, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, stream()));
+    SCG_CUDA(cudaMemcpyAsync(out_ref, dr.p, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, stream()));
+    SCG_CUDA(cudaMemcpyAsync(ok, dk.p, sizeof(int) * 2 * n, cudaMemcpyDeviceToHost, stream()));
     SCG_CUDA(cudaStreamSynchronize(stream()));
     return 0;
 }

@@ -1189,6 +1189,118 @@ struct DsolnEqo
     static constexpr int BYTES = ROWS * TB * int(sizeof(double));
 };
 
+// ------------------------------------------------------------------------------------------------
+// IEEE square root and reciprocal with a deferred range test.
+//
+// ptxas expands sqrt.rn.f64 / rcp.rn.f64 into a MUFU seed, a fixed Newton sequence, a range test on the
+// high word of the argument and a call to a slow path when the test fails -- one basic block boundary per
+// operation, which keeps the scheduler from overlapping independent operations.  sqrt_fast / rcp_fast run
+// EXACTLY the fast sequences (read off the sm_100a SASS, including the odd low words of the seeds; checked
+// bit for bit by scg_selftest_rsq) and only record the test in `ok`; the caller redoes the work with the
+// plain operators when it is false.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double rcp_fast(double x, bool & ok)
+{
+    int const xh = __double2hiint(x);
+    int const lo = xh + 0x300402;
+    double s;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(s) : "d"(x));
+    double const y0 = __hiloint2double(__double2hiint(s), lo);
+    double e = __fma_rn(-x, y0, 1.0);
+    e = __fma_rn(e, e, e);
+    double const y1 = __fma_rn(y0, e, y0);
+    double const e2 = __fma_rn(-x, y1, 1.0);
+    ok = ok && !(fabsf(__int_as_float(lo)) < 5.8789094863358348022e-39f);
+    return __fma_rn(y1, e2, y1);
+}
+
+__device__ __forceinline__ double sqrt_fast(double x, bool & ok)
+{
+    int const xh = __double2hiint(x);
+    unsigned const lo = static_cast<unsigned>(xh) + 0xfcb00000u;
+    double s;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(s) : "d"(x));
+    double const y0 = __hiloint2double(__double2hiint(s), static_cast<int>(lo));
+    double const t = __dmul_rn(y0, y0);
+    double const e = __fma_rn(x, -t, 1.0);
+    double const c = __fma_rn(e, 0.375, 0.5);
+    double const ye = __dmul_rn(y0, e);
+    double const y1 = __fma_rn(c, ye, y0);
+    double const g = __dmul_rn(x, y1);
+    double const h = __hiloint2double(__double2hiint(y1) - 0x100000, __double2loint(y1));
+    double const r = __fma_rn(g, -g, x);
+    ok = ok && (lo < 0x7ca00000u);
+    return __fma_rn(r, h, g);
+}
+
+// The arithmetic of one equation of calc_dsoln after the Taylor differences (euler_gradient.cpp:74-110):
+// the NFGE gradients, their W-1/2 weights normalised and shifted, and sigma_max.  FAST: see above;
+// returns whether every range test passed.
+template <int TYPE, int TB, bool FAST>
+__device__ __forceinline__ bool eqo_solve(double const * sadj, double const (&udf)[ct_nfc(TYPE)], double ofg1, double sgm0,
+                                          double (&grad)[ct_nfge(TYPE)][ct_ndim(TYPE)], double (&w)[ct_nfge(TYPE)], double & sigma_max)
+{
+    constexpr int ND = ct_ndim(TYPE);
+    constexpr int NFGE = ct_nfge(TYPE);
+    constexpr int RPF = ND * ND + 1;
+    bool ok = true;
+#pragma unroll
+    for (int ifge = 0; ifge < NFGE; ++ifge)
+    {
+#pragma unroll
+        for (int a = 0; a < ND; ++a)
+        {
+            double r = 0.0;
+#pragma unroll
+            for (int b = 0; b < ND; ++b) { r += sadj[(ifge * RPF + a * ND + b) * TB] * udf[fge_face(TYPE, ifge, b)]; }
+            grad[ifge][a] = r;
+        }
+    }
+#pragma unroll
+    for (int ifge = 0; ifge < NFGE; ++ifge)
+    {
+        DivBy<FAST> by_det(sadj[(ifge * RPF + ND * ND) * TB]);
+#pragma unroll
+        for (int a = 0; a < ND; ++a) { grad[ifge][a] = by_det(grad[ifge][a]); }
+        ok = ok && by_det.ok;
+    }
+#pragma unroll
+    for (int ifge = 0; ifge < NFGE; ++ifge)
+    {
+        double sq = 0.0;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) { sq += grad[ifge][d] * grad[ifge][d]; }
+        w[ifge] = sq + MD_ALMOST_ZERO;
+    }
+#pragma unroll
+    for (int ifge = 0; ifge < NFGE; ++ifge) { w[ifge] = FAST ? sqrt_fast(w[ifge], ok) : sqrt(w[ifge]); }
+#pragma unroll
+    for (int ifge = 0; ifge < NFGE; ++ifge) { w[ifge] = FAST ? rcp_fast(w[ifge], ok) : 1.0 / w[ifge]; }
+    double wacc = 0.0;
+#pragma unroll
+    for (int ifge = 0; ifge < NFGE; ++ifge) { wacc += w[ifge]; }
+    // ---- W-3/4 limiter (euler_gradient.cpp:90-110)
+    {
+        DivBy<FAST> by_wacc(wacc);
+#pragma unroll
+        for (int ifge = 0; ifge < NFGE; ++ifge) { w[ifge] = by_wacc(w[ifge]) - ofg1; }
+        ok = ok && by_wacc.ok;
+    }
+    double wmax = 0.0, wmin = 0.0;
+#pragma unroll
+    for (int ifge = 0; ifge < NFGE; ++ifge)
+    {
+        wmax = fmax(wmax, w[ifge]);
+        wmin = fmin(wmin, w[ifge]);
+    }
+    DivBy<FAST> by_hi(wmax + MD_ALMOST_ZERO);
+    DivBy<FAST> by_lo(wmin - MD_ALMOST_ZERO);
+    double const sm = fmin(by_hi(1.0 - ofg1), by_lo(-ofg1));
+    ok = ok && by_hi.ok && by_lo.ok;
+    sigma_max = fmin(sm, sgm0);
+    return ok;
+}
+
 // what one equation of calc_dsoln gathers through the neighbour indices (euler_gradient.cpp:66-69)
 template <int TYPE>
 struct EqoGather
@@ -1375,60 +1487,14 @@ __device__ __forceinline__ void cell_dsoln_eqo(MdField const & F, MdGeo const & 
         }
         if (PF) { cur = nxt; }
         double grad[NFGE][ND], w[NFGE];
-        double wacc = 0.0;
-#pragma unroll
-        for (int ifge = 0; ifge < NFGE; ++ifge)
+        double sigma_max;
+        // every division, square root and reciprocal of the equation runs its inlined fast sequence with
+        // the range tests collected in one flag, so the hot path is one basic block; when any test fails the
+        // equation is redone with the plain operators (cold)
+        if (!eqo_solve<TYPE, TB, true>(sadj, udf, ofg1, sgm0, grad, w, sigma_max))
         {
-            double rr[ND];
-#pragma unroll
-            for (int a = 0; a < ND; ++a)
-            {
-                double r = 0.0;
-#pragma unroll
-                for (int b = 0; b < ND; ++b) { r += sadj[(ifge * RPF + a * ND + b) * TB] * udf[fge_face(TYPE, ifge, b)]; }
-                rr[a] = r;
-            }
-            double const det = sadj[(ifge * RPF + ND * ND) * TB];
-            {
-                DivBy<true> by_det(det);
-#pragma unroll
-                for (int a = 0; a < ND; ++a) { grad[ifge][a] = by_det(rr[a]); }
-                if (!by_det.ok)
-                {
-#pragma unroll
-                    for (int a = 0; a < ND; ++a) { grad[ifge][a] = rr[a] / det; }
-                }
-            }
-            double sq = 0.0;
-#pragma unroll
-            for (int d = 0; d < ND; ++d) { sq += grad[ifge][d] * grad[ifge][d]; }
-            double const wgt = 1.0 / sqrt(sq + MD_ALMOST_ZERO);
-            wacc += wgt;
-            w[ifge] = wgt;
+            eqo_solve<TYPE, TB, false>(sadj, udf, ofg1, sgm0, grad, w, sigma_max);
         }
-        // ---- W-3/4 limiter (euler_gradient.cpp:90-128)
-        {
-            double q[NFGE];
-            DivBy<true> by_wacc(wacc);
-#pragma unroll
-            for (int ifge = 0; ifge < NFGE; ++ifge) { q[ifge] = by_wacc(w[ifge]); }
-            if (!by_wacc.ok)
-            {
-#pragma unroll
-                for (int ifge = 0; ifge < NFGE; ++ifge) { q[ifge] = w[ifge] / wacc; }
-            }
-#pragma unroll
-            for (int ifge = 0; ifge < NFGE; ++ifge) { w[ifge] = q[ifge] - ofg1; }
-        }
-        double wmax = 0.0, wmin = 0.0;
-#pragma unroll
-        for (int ifge = 0; ifge < NFGE; ++ifge)
-        {
-            wmax = fmax(wmax, w[ifge]);
-            wmin = fmin(wmin, w[ifge]);
-        }
-        double const sm = fmin((1.0 - ofg1) / (wmax + MD_ALMOST_ZERO), -ofg1 / (wmin - MD_ALMOST_ZERO));
-        double const sigma_max = fmin(sm, sgm0);
         double o[ND];
 #pragma unroll
         for (int d = 0; d < ND; ++d) { o[d] = 0.0; }

@@ -219,3 +219,27 @@ def test_shared_reciprocal_division_is_ieee(gpu):
     fin = np.isfinite(host) & (host != 0)
     assert np.array_equal(ref[fin].view(np.int64), host[fin].view(np.int64))   # device '/' is IEEE too
     assert m[: 1 << 20].mean() > 0.999                                          # the fast path is the common path
+
+
+def test_fast_sqrt_and_reciprocal_are_ieee(gpu):
+    """sqrt_fast / rcp_fast (scg_md_kernels.cuh) must return exactly sqrt(x) / (1.0 / x) wherever their
+    range tests pass, the tests must pass over the whole normal range the march uses, and the device
+    operators themselves must agree with the host's IEEE results."""
+    rng = np.random.RandomState(11)
+    n0 = 1 << 20
+    x = np.abs(rng.standard_normal(n0)) * 10.0 ** rng.uniform(-250, 250, n0)
+    edge = np.array([1.0, 2.0, 3.0, 4.0, 1.0 / 3.0, np.nextafter(2.0, 0), np.nextafter(1.0, 2), np.nextafter(4.0, 0),
+                     1e-200, 1e-100, 1e-300, 1e300, 4.9e-324, 2.2250738585072014e-308, 1.7976931348623157e308,
+                     0.0, 7.0, 1e-160, 1e160, 0.25, 0.5, np.nextafter(0.5, 0)])
+    x = np.concatenate([x, edge, -edge])
+    n = len(x)
+    fast, ref = np.zeros(2 * n), np.zeros(2 * n)
+    ok = np.zeros(2 * n, dtype=np.int32)
+    gpu.check(gpu.load().scg_selftest_rsq(gpu.ptr(x), gpu.ptr(fast), gpu.ptr(ref), ok.ctypes.data, n))
+    m = ok == 1
+    assert np.array_equal(fast[m].view(np.int64), ref[m].view(np.int64))
+    with np.errstate(all="ignore"):
+        host = np.concatenate([np.sqrt(x), 1.0 / x])
+    fin = np.isfinite(host) & (host != 0) & (np.abs(host) > 1e-300)
+    assert np.array_equal(ref[fin].view(np.int64), host[fin].view(np.int64))
+    assert m[:n0].mean() > 0.999 and m[n:n + n0].mean() > 0.999

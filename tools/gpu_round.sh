@@ -13,7 +13,7 @@ ARGS="--workload md3d --size $NSZ --steps 1 --warmup 3 --chunk 1 --no-cpu --no-e
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_md3d.csv \
    python bench.py $ARGS "$@" > gpurun_out/ncu_list_md3d.log 2>&1
 python tools/ncu_list.py gpurun_out/launches_md3d.csv | grep -v "prepare\|fill\|init\|ghost"
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"md_solncfl|md_dsoln_coop" -s 12 -c 6 -f -o gpurun_out/prof_md3d \
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"md_solncfl|md_dsoln" -s 12 -c 6 -f -o gpurun_out/prof_md3d \
    python bench.py $ARGS "$@" > gpurun_out/ncu_full_md3d.log 2>&1
 tail -3 gpurun_out/ncu_full_md3d.log
 cat gpurun_out/host.txt
