@@ -124,6 +124,13 @@ class MD3DWorkload:
             self.dist_svr = None
         self.ncell = self.info["ncell"]
         self.balg_substep = self.dev.algorithmic_bytes()
+        # measured DRAM bytes per cell-substep from the committed ncu capture, scaled to this mesh
+        import json, os
+        tp = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "profiles", "traffic_md3d.json")
+        self.ncu_traffic = None
+        if os.path.exists(tp) and self.kinds == "hpt":
+            with open(tp) as f:
+                self.ncu_traffic = float(json.load(f)["bytes_per_cell_substep"]) * self.ncell
         return self.dev
 
     def describe(self, world):

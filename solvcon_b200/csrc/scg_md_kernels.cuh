@@ -75,15 +75,18 @@ struct DivBy
     double y;
     int bhi;
     bool ok;
+    bool bsane; // b is normal and 2^-900 < |b| < 2^900: the refined reciprocal is finite and normal
     __device__ __forceinline__ explicit DivBy(double denom)
         : b(denom)
         , y(0.0)
         , bhi(0)
         , ok(true)
+        , bsane(false)
     {
         if (FAST)
         {
             bhi = __double2hiint(denom);
+            bsane = (((static_cast<unsigned>(bhi) >> 20) & 0x7ffu) - 124u) < 1800u;
             double y0;
             asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(denom));
             y0 = __hiloint2double(__double2hiint(y0), 1);
@@ -94,18 +97,41 @@ struct DivBy
             y = __fma_rn(y1, e2, y1);
         }
     }
-    __device__ __forceinline__ double operator()(double a)
+    // ZMODE 0: a zero numerator fails the range test like in ptxas's own expansion.
+    // ZMODE 1: +-0 over a sane denominator passes and returns the IEEE result (a zero with the sign of a*b).
+    //          Uniform regions of a flow are full of exact zeros (transverse momentum, gradients); without this
+    //          every one of them would drop to the plain operator AND its slow path.
+    // ZMODE 2: as 1 but the sign of the returned zero is unspecified -- for callers that provably do not depend
+    //          on it (saves the select).
+    template <int ZMODE>
+    __device__ __forceinline__ double quot(double a)
     {
         if (!FAST) { return a / b; }
         double const q0 = __dmul_rn(a, y);
         double const r = __fma_rn(-b, q0, a);
         double const q = __fma_rn(y, r, q0);
-        float const ah = __int_as_float(__double2hiint(a));
+        int const ahi = __double2hiint(a);
+        float const ah = __int_as_float(ahi);
         float const t = __fmaf_rn(0.0f, __int_as_float(bhi), __int_as_float(__double2hiint(q)));
-        ok = ok && !(fabsf(ah) < 6.5827683646048100446e-37f) && (fabsf(t) > 1.469367938527859385e-39f);
-        return q;
+        bool const in_range = !(fabsf(ah) < 6.5827683646048100446e-37f) && (fabsf(t) > 1.469367938527859385e-39f);
+        if (0 == ZMODE)
+        {
+            ok = ok && in_range;
+            return q;
+        }
+        bool const a_zero = 0 == ((ahi & 0x7fffffff) | __double2loint(a));
+        ok = ok && (a_zero ? bsane : in_range);
+        if (2 == ZMODE) { return q; } // q is +-0 here when a is: y is finite
+        return a_zero ? __hiloint2double((ahi ^ bhi) & static_cast<int>(0x80000000u), 0) : q;
     }
+    __device__ __forceinline__ double operator()(double a) { return quot<1>(a); }
 };
+
+// zero-numerator mode of the gradient quotients in eqo_solve: the sign of a zero gradient cannot reach so1n
+// (grad*grad is +0 either way; o[d] starts at +0 and +0 + (+-0) is +0, x + (+-0) is x)
+#ifndef SCG_EQO_ZERO
+#define SCG_EQO_ZERO 2
+#endif
 
 #ifndef SCG_SHARED_RCP
 #define SCG_SHARED_RCP 1
@@ -1261,7 +1287,7 @@ __device__ __forceinline__ bool eqo_solve(double const * sadj, double const (&ud
     {
         DivBy<FAST> by_det(sadj[(ifge * RPF + ND * ND) * TB]);
 #pragma unroll
-        for (int a = 0; a < ND; ++a) { grad[ifge][a] = by_det(grad[ifge][a]); }
+        for (int a = 0; a < ND; ++a) { grad[ifge][a] = by_det.template quot<SCG_EQO_ZERO>(grad[ifge][a]); }
         ok = ok && by_det.ok;
     }
 #pragma unroll
@@ -1283,7 +1309,7 @@ __device__ __forceinline__ bool eqo_solve(double const * sadj, double const (&ud
     {
         DivBy<FAST> by_wacc(wacc);
 #pragma unroll
-        for (int ifge = 0; ifge < NFGE; ++ifge) { w[ifge] = by_wacc(w[ifge]) - ofg1; }
+        for (int ifge = 0; ifge < NFGE; ++ifge) { w[ifge] = by_wacc.template quot<0>(w[ifge]) - ofg1; }
         ok = ok && by_wacc.ok;
     }
     double wmax = 0.0, wmin = 0.0;
@@ -1295,7 +1321,7 @@ __device__ __forceinline__ bool eqo_solve(double const * sadj, double const (&ud
     }
     DivBy<FAST> by_hi(wmax + MD_ALMOST_ZERO);
     DivBy<FAST> by_lo(wmin - MD_ALMOST_ZERO);
-    double const sm = fmin(by_hi(1.0 - ofg1), by_lo(-ofg1));
+    double const sm = fmin(by_hi.template quot<0>(1.0 - ofg1), by_lo.template quot<0>(-ofg1));
     ok = ok && by_hi.ok && by_lo.ok;
     sigma_max = fmin(sm, sgm0);
     return ok;
@@ -1380,7 +1406,7 @@ __device__ __forceinline__ void cell_dsoln_eqo(MdField const & F, MdGeo const & 
             double a2[ND];
             DivBy<true> by_nfc(static_cast<double>(NFC));
 #pragma unroll
-            for (int d = 0; d < ND; ++d) { a2[d] = by_nfc(avg[d]); }
+            for (int d = 0; d < ND; ++d) { a2[d] = by_nfc.template quot<0>(avg[d]); }
             if (!by_nfc.ok)
             {
 #pragma unroll
@@ -1422,7 +1448,7 @@ __device__ __forceinline__ void cell_dsoln_eqo(MdField const & F, MdGeo const & 
             double c2[ND];
             DivBy<true> by_voc(voc);
 #pragma unroll
-            for (int d = 0; d < ND; ++d) { c2[d] = by_voc(cnd[d]); }
+            for (int d = 0; d < ND; ++d) { c2[d] = by_voc.template quot<0>(cnd[d]); }
             if (!by_voc.ok)
             {
 #pragma unroll

@@ -219,6 +219,9 @@ def test_shared_reciprocal_division_is_ieee(gpu):
     fin = np.isfinite(host) & (host != 0)
     assert np.array_equal(ref[fin].view(np.int64), host[fin].view(np.int64))   # device '/' is IEEE too
     assert m[: 1 << 20].mean() > 0.999                                          # the fast path is the common path
+    # exact zeros over a sane denominator are answered by the fast path too (uniform flow regions are full of them)
+    zs = (a == 0) & np.isfinite(b) & (np.abs(b) > 1e-250) & (np.abs(b) < 1e250)
+    assert zs.sum() > 10 and m[zs].all()
 
 
 def test_fast_sqrt_and_reciprocal_are_ieee(gpu):
