@@ -44,6 +44,9 @@ SCG_API int scg_sync(void);
 SCG_API int scg_mem_info(int64_t * free_bytes, int64_t * total_bytes);
 /* kernels launched by this library since the last reset (for bench.py "gpu_launches") */
 SCG_API int64_t scg_launch_count(int reset);
+/* the library's work stream (a cudaStream_t) so that a caller's communication library can order its own
+ * streams against it with events; valid after scg_init */
+SCG_API void * scg_stream_handle(void);
 /* diagnostics: with SCG_TIMING=1 in the environment every multidim kernel launch is bracketed by events;
  * this prints launches / average / share per kernel to stderr and clears the records */
 SCG_API int scg_timing_dump(void);
@@ -186,6 +189,11 @@ SCG_API int scg_mesh_perm(scg_mesh * m, int32_t * perm /* ncell */);
 #define SCG_MD_BC_DSOLN 6   /* bc_dsoln()                 euler_bc.cpp:219-320      */
 #define SCG_MD_PREPARE_CE 7 /* prepare_ce()               euler_ce.cpp:62-347       */
 #define SCG_MD_SUBSTEP 8    /* march_substep()            euler_march.cpp:339-348   */
+/* march_substep of one partition of a decomposed mesh in two stages (additive API): IFACE = update(), calc_solt,
+ * then soln/cfl/dsoln of the owned INTERFACE cells (owned[c] == 2 in scg_mesh_create_part) -- their state can be
+ * packed and sent right after; REST = the interior cells and the boundary kernels.  IFACE + REST == SUBSTEP. */
+#define SCG_MD_SUBSTEP_IFACE 9
+#define SCG_MD_SUBSTEP_REST 10
 
 #define SCG_BC_NONREFL 0  /* EulerBC::NonReflective euler.hpp:27-32 */
 #define SCG_BC_SLIPWALL 1

@@ -43,6 +43,7 @@ _SIGNATURES = {
     "scg_mem_info": (C.c_int, [I64P, I64P]),
     "scg_launch_count": (C.c_int64, [C.c_int]),
     "scg_timing_dump": (C.c_int, []),
+    "scg_stream_handle": (C.c_void_p, []),
     "scg_timer_start": (C.c_int, []),
     "scg_timer_stop": (C.c_int, [DP]),
     "scg_flush_l2": (C.c_int, [C.c_int64]),

@@ -230,7 +230,124 @@ def cpu_reference_3d(budget_s=15.0, kinds="hpt", ncell_target=60000):
                        f"thread (the reference is single-threaded)"}, upd, el)
 
 
+# ------------------------------------------------------------------------------------------ 2D ---
+
+def dims_2d(ncell_target):
+    """Box counts (nx, ny) of the forward-facing step domain [0,3]x[0,1] minus [0.6,3]x[0,0.2] (SURVEY.md 8d
+    config 3): 3 ny^2 boxes, 16 % removed, a quarter of the rest split into two triangles -> 3.15 ny^2 cells."""
+    ny = max(5, int(round((ncell_target / 3.15) ** 0.5 / 5.0)) * 5)
+    return 3 * ny, ny
+
+
+def build_case_2d(ncell_target, order="morton"):
+    t0 = time.perf_counter()
+    nx, ny = dims_2d(ncell_target)
+    h = 1.0 / ny
+    ndcrd, cltpn, clnds = meshgen.mixed_2d(nx, ny, lx=3.0, ly=1.0, tri_every=4, jitter=0.3, step=(0.6, 0.2))
+    t1 = time.perf_counter()
+    mesh = make_mesh(2, ndcrd, cltpn, clnds)
+    t2 = time.perf_counter()
+    lo, hi = ndcrd.min(axis=0), ndcrd.max(axis=0)
+    inlet, outlet, wall = meshgen.boundary_groups(2, mesh.fccnd.body, mesh.fccls.body, mesh.nface, lo, hi)
+    dt = 0.05 * h
+    svr = EulerCore(mesh, dt, order=order)
+    import os
+    if os.environ.get("SCG_MD_FUSED"):
+        svr.set_fused(int(os.environ["SCG_MD_FUSED"]))
+    t3 = time.perf_counter()
+    svr.resident(True)
+    svr.init_solution(1.4, 1.4, [3.0, 0.0], 1.0)
+    svr.add_inlet(inlet, [1.4, 3.0, 0.0, 1.0, 1.4])
+    svr.add_nonrefl(outlet)
+    svr.add_slipwall(wall)
+    svr.bc_soln()
+    svr.bc_dsoln()
+    info = {"boxes": [nx, ny], "h": h, "dt": dt, "ncell": int(mesh.ncell), "nface": int(mesh.nface),
+            "ngstcell": int(mesh.ngstcell),
+            "cells_by_type": {"quad": int((cltpn == 3).sum()), "tri": int((cltpn == 4).sum())},
+            "setup_s": {"generate": round(t1 - t0, 2), "tables": round(t2 - t1, 2), "device": round(t3 - t2, 2)}}
+    return mesh, svr, info
+
+
+class MD2DWorkload(MD3DWorkload):
+    name = "md2d"
+    dominant_kernel = "one substep = md_solt + md_solncfl_staged<quad|tri> + md_dsoln_eqo<quad|tri> + boundary kernels"
+
+    def build_device(self):
+        if getattr(self, "world", 1) > 1:
+            raise SystemExit("md2d: single-GPU workload (the multi-GPU arm is md3d)")
+        self.mesh, self.dev, self.info = build_case_2d(self.ncell_target, self.order)
+        self.dist_svr = None
+        self.ncell = self.info["ncell"]
+        self.balg_substep = self.dev.algorithmic_bytes()
+        self.ncu_traffic = None
+        return self.dev
+
+    def describe(self, world):
+        return {"workload": f"2D Euler CESE (multidim EulerCore.march), synthetic mixed tri/quad forward-facing step, "
+                            f"{self.ncell} cells ({self.info['cells_by_type']}), Mach-3 inlet / nonrefl outlet / slip walls, "
+                            f"march({self.chunk}) per step, {self.order} cell ordering",
+                "cells_per_gpu": self.ncell, "chunk_steps": self.chunk, "ordering": self.order,
+                "alg_bytes_per_cell_substep": self.balg_substep / self.ncell,
+                "l2_policy": "inputs larger than L2 (%.1f GB streamed per substep)" % (self.balg_substep / 1e9),
+                "decomposition": "none", "mesh": self.info}
+
+    def e2e_bytes(self):
+        T = self.ncell + self.info["ngstcell"]
+        nd = 2
+        neq = nd + 2
+        per_row = 8 * (3 * neq + 2 * neq * nd + 3)
+        return T * per_row, T * per_row
+
+    def cpu_run(self, budget_s=15.0):
+        return cpu_reference_2d(budget_s)
+
+
+def cpu_reference_2d(budget_s=15.0, ncell_target=120000):
+    """The reference's EulerCore.march on the same 2D generator at a size that finishes in seconds, single thread."""
+    from oracle import bridge as b
+    nx, ny = dims_2d(ncell_target)
+    h = 1.0 / ny
+    ndcrd, cltpn, clnds = meshgen.mixed_2d(nx, ny, lx=3.0, ly=1.0, tri_every=4, jitter=0.3, step=(0.6, 0.2))
+    dt = 0.05 * h
+    if b.have_ref():
+        mesh = b.make_ref_mesh(2, ndcrd, cltpn, clnds)
+        svr = b.RefEuler(mesh, dt)
+        fccnd, fccls, nface = mesh.body("fccnd"), mesh.body("fccls"), mesh.nface
+        kind = "reference"
+    else:
+        pm = make_mesh(2, ndcrd, cltpn, clnds)
+        svr = b.PortEuler(pm.tables(), 2, dt)
+        svr.phase(b.MD_PREPARE_CE)
+        fccnd, fccls, nface = pm.fccnd.body, pm.fccls.body, pm.nface
+        kind = "port"
+    lo, hi = ndcrd.min(axis=0), ndcrd.max(axis=0)
+    inlet, outlet, wall = meshgen.boundary_groups(2, fccnd, fccls, nface, lo, hi)
+    svr.init_solution(1.4, 1.4, [3.0, 0.0], 1.0)
+    svr.add_bc(b.BC_INLET, inlet, [1.4, 3.0, 0.0, 1.0, 1.4])
+    svr.add_bc(b.BC_NONREFL, outlet)
+    svr.add_bc(b.BC_SLIPWALL, wall)
+    svr.phase(b.MD_BC_SOLN)
+    svr.phase(b.MD_BC_DSOLN)
+    svr.march(1)
+    ncell = len(cltpn)
+    t0 = time.perf_counter()
+    steps = 0
+    while True:
+        svr.march(1)
+        steps += 1
+        el = time.perf_counter() - t0
+        if el > budget_s or steps >= 400:
+            break
+    upd = 2 * steps * ncell
+    return ({"value": upd / el, "unit": UNIT, "cores": 1, "kind": kind,
+             "sample": f"2D Euler mixed tri/quad forward step, {ncell} cells, march({steps}) in {el:.2f} s, single "
+                       f"thread (the reference is single-threaded)"}, upd, el)
+
+
 def make(args):
     if args.workload == "md3d":
         return MD3DWorkload(args.size or 50_000_000, args.chunk, order=getattr(args, "order", "morton"))
+    if args.workload == "md2d":
+        return MD2DWorkload(args.size or 20_000_000, args.chunk, order=getattr(args, "order", "morton"))
     raise SystemExit(f"workload {args.workload} not available")

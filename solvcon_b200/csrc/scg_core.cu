@@ -209,6 +209,8 @@ int scg_timing_dump(void)
     return 0;
 }
 
+void * scg_stream_handle(void) { return static_cast<void *>(g_stream); }
+
 int64_t scg_launch_count(int reset)
 {
     int64_t const v = g_launches.load();

@@ -332,16 +332,28 @@ __global__ void __launch_bounds__(128, SCG_SOLN_MINBLOCKS) md_solncfl_kernel(MdF
 #endif
 // resident CTAs per SM the register budget is sized for: the 3D flux evaluation wants ~250 registers (two
 // CTAs); tetrahedra and the 2D types get by with 168 (three CTAs)
-#ifndef SCG_STAGED_MB_BIG
-#define SCG_STAGED_MB_BIG 2
+#ifndef SCG_STAGED_MB_HEX
+#define SCG_STAGED_MB_HEX 2
 #endif
-#ifndef SCG_STAGED_MB_SMALL
-#define SCG_STAGED_MB_SMALL 3
+#ifndef SCG_STAGED_MB_PRISM
+#define SCG_STAGED_MB_PRISM 2
+#endif
+#ifndef SCG_STAGED_MB_TET
+#define SCG_STAGED_MB_TET 3
+#endif
+#ifndef SCG_STAGED_MB_QUAD
+#define SCG_STAGED_MB_QUAD 4
+#endif
+#ifndef SCG_STAGED_MB_TRI
+#define SCG_STAGED_MB_TRI 4
 #endif
 template <int TYPE>
 struct StagedCfg
 {
-    static constexpr int MB = (TYPE == CT_HEX || TYPE == CT_PRISM || TYPE == CT_PYRAMID) ? SCG_STAGED_MB_BIG : SCG_STAGED_MB_SMALL;
+    static constexpr int MB = (TYPE == CT_HEX) ? SCG_STAGED_MB_HEX
+                            : (TYPE == CT_PRISM || TYPE == CT_PYRAMID) ? SCG_STAGED_MB_PRISM
+                            : (TYPE == CT_TET) ? SCG_STAGED_MB_TET
+                            : (TYPE == CT_QUAD) ? SCG_STAGED_MB_QUAD : SCG_STAGED_MB_TRI;
 };
 template <int TYPE>
 __global__ void __launch_bounds__(SCG_STAGED_TB, StagedCfg<TYPE>::MB) md_solncfl_staged_kernel(MdField const F, MdGeo const G, double * eraw)
@@ -350,8 +362,8 @@ __global__ void __launch_bounds__(SCG_STAGED_TB, StagedCfg<TYPE>::MB) md_solncfl
     constexpr int NEQ = ND + 2;
     constexpr int NFC = ct_nfc(TYPE);
     extern __shared__ double stage_smem[];
-    int32_t const i = blockIdx.x * SCG_STAGED_TB + threadIdx.x;
-    if (i >= G.nact) { return; }
+    int32_t const i = G.ibeg + blockIdx.x * SCG_STAGED_TB + threadIdx.x;
+    if (i >= G.iend) { return; }
     int64_t const k = G.beg + i;
     double un[NEQ];
     double dist;
@@ -385,6 +397,12 @@ __global__ void __launch_bounds__(SCG_STAGED_TB, StagedCfg<TYPE>::MB) md_solncfl
 #ifndef SCG_EQO_MB_TET
 #define SCG_EQO_MB_TET 8
 #endif
+#ifndef SCG_EQO_MB_QUAD
+#define SCG_EQO_MB_QUAD 8
+#endif
+#ifndef SCG_EQO_MB_TRI
+#define SCG_EQO_MB_TRI 10
+#endif
 #ifndef SCG_EQO_PF_HEX
 #define SCG_EQO_PF_HEX 1
 #endif
@@ -394,22 +412,29 @@ __global__ void __launch_bounds__(SCG_STAGED_TB, StagedCfg<TYPE>::MB) md_solncfl
 #ifndef SCG_EQO_PF_TET
 #define SCG_EQO_PF_TET 0
 #endif
+#ifndef SCG_EQO_PF_2D
+#define SCG_EQO_PF_2D 0
+#endif
 template <int TYPE>
 struct EqoCfg
 {
     // prefetch the next equation's neighbour gather into registers
-    static constexpr bool PF = (TYPE == CT_HEX) ? SCG_EQO_PF_HEX : (TYPE == CT_PRISM || TYPE == CT_PYRAMID) ? SCG_EQO_PF_PRISM : SCG_EQO_PF_TET;
+    static constexpr bool PF = (TYPE == CT_HEX) ? SCG_EQO_PF_HEX : (TYPE == CT_PRISM || TYPE == CT_PYRAMID) ? SCG_EQO_PF_PRISM
+                             : (TYPE == CT_TET) ? SCG_EQO_PF_TET : SCG_EQO_PF_2D;
     static constexpr int TB = 64;
     // resident CTAs per SM the register budget is sized for (shared memory allows at least as many)
-    static constexpr int MB = (TYPE == CT_HEX) ? SCG_EQO_MB_HEX : (TYPE == CT_PRISM || TYPE == CT_PYRAMID) ? SCG_EQO_MB_PRISM : SCG_EQO_MB_TET;
+    static constexpr int MB = (TYPE == CT_HEX) ? SCG_EQO_MB_HEX
+                            : (TYPE == CT_PRISM || TYPE == CT_PYRAMID) ? SCG_EQO_MB_PRISM
+                            : (TYPE == CT_TET) ? SCG_EQO_MB_TET
+                            : (TYPE == CT_QUAD) ? SCG_EQO_MB_QUAD : SCG_EQO_MB_TRI;
 };
 
 template <int TYPE>
 __global__ void __launch_bounds__(EqoCfg<TYPE>::TB, EqoCfg<TYPE>::MB) md_dsoln_eqo_kernel(MdField const F, MdGeo const G)
 {
     extern __shared__ double eqo_smem[];
-    int32_t const i = blockIdx.x * EqoCfg<TYPE>::TB + threadIdx.x;
-    if (i >= G.nact) { return; }
+    int32_t const i = G.ibeg + blockIdx.x * EqoCfg<TYPE>::TB + threadIdx.x;
+    if (i >= G.iend) { return; }
     cell_dsoln_eqo<TYPE, EqoCfg<TYPE>::TB, EqoCfg<TYPE>::PF>(F, G, i, eqo_smem + threadIdx.x);
 }
 
@@ -1158,6 +1183,8 @@ MdGeo geo_of(scg_md * s, MeshGroup const & g)
     G.beg = g.beg;
     G.n = g.n;
     G.nact = g.nact;
+    G.ibeg = 0;
+    G.iend = g.nact;
     return G;
 }
 
@@ -1182,14 +1209,17 @@ enum CellPhase
     CP_DSOLN_EQO,
 };
 
+// part: 0 all owned cells, 1 the interface cells [0, nif), 2 the interior cells [nif, nact) (mode-3 kernels only)
 template <int TYPE>
-void launch_cell_phase_t(scg_md * s, MeshGroup const & g, CellPhase ph)
+void launch_cell_phase_t(scg_md * s, MeshGroup const & g, CellPhase ph, int part)
 {
     MdField const F = field_of(s);
-    MdGeo const G = geo_of(s, g);
+    MdGeo G = geo_of(s, g);
     bool const all_cells = (CP_PREPARE == ph);
-    int64_t const ncl = all_cells ? g.n : g.nact;
-    if (0 == ncl) { return; }
+    if (1 == part) { G.iend = g.nif; }
+    if (2 == part) { G.ibeg = g.nif; }
+    int64_t const ncl = all_cells ? g.n : (G.iend - G.ibeg);
+    if (ncl <= 0) { return; }
     unsigned const grid = static_cast<unsigned>(ceil_div(ncl, 128));
     static char const * const phase_name[] = {"prepare", "soln", "cfl", "dsoln", "substep", "solncfl", "solncfl_staged", "dsoln_coop", "dsoln_eqo"};
     char key[48];
@@ -1251,18 +1281,18 @@ void launch_cell_phase_t(scg_md * s, MeshGroup const & g, CellPhase ph)
     count_launch();
 }
 
-void launch_cell_phase(scg_md * s, CellPhase ph)
+void launch_cell_phase(scg_md * s, CellPhase ph, int part = 0)
 {
     for (auto const & g : s->mesh->groups)
     {
         switch (g.type)
         {
-        case CT_QUAD: launch_cell_phase_t<CT_QUAD>(s, g, ph); break;
-        case CT_TRI: launch_cell_phase_t<CT_TRI>(s, g, ph); break;
-        case CT_HEX: launch_cell_phase_t<CT_HEX>(s, g, ph); break;
-        case CT_TET: launch_cell_phase_t<CT_TET>(s, g, ph); break;
-        case CT_PRISM: launch_cell_phase_t<CT_PRISM>(s, g, ph); break;
-        case CT_PYRAMID: launch_cell_phase_t<CT_PYRAMID>(s, g, ph); break;
+        case CT_QUAD: launch_cell_phase_t<CT_QUAD>(s, g, ph, part); break;
+        case CT_TRI: launch_cell_phase_t<CT_TRI>(s, g, ph, part); break;
+        case CT_HEX: launch_cell_phase_t<CT_HEX>(s, g, ph, part); break;
+        case CT_TET: launch_cell_phase_t<CT_TET>(s, g, ph, part); break;
+        case CT_PRISM: launch_cell_phase_t<CT_PRISM>(s, g, ph, part); break;
+        case CT_PYRAMID: launch_cell_phase_t<CT_PYRAMID>(s, g, ph, part); break;
         default: break;
         }
     }
@@ -1405,6 +1435,27 @@ int launch_bc_dsoln(scg_md * s)
     else { md_bc_dsoln_kernel<3><<<grid, 128, 0, stream()>>>(F, B); }
     count_launch();
     return 0;
+}
+
+// march_substep in two stages for a partition of a decomposed mesh (always the mode-3 kernels; every mode is
+// bit-identical).  Stage 0: update(), calc_solt on every row, then soln+cfl+dsoln of the INTERFACE cells -- after
+// it their so0n/so1n are final and can be packed and sent.  Stage 1: the interior cells and the boundary kernels.
+// calc_dsoln of a cell reads so0n of that cell only (SURVEY.md 8a hazard 2), and the boundary kernels read
+// interior so0n / old so1c and write ghost rows that the NEXT substep reads, so the reordering changes nothing.
+int substep_split(scg_md * s, int stage)
+{
+    if (0 == stage)
+    {
+        s->cur ^= 1;
+        launch_solt(s);
+        launch_cell_phase(s, CP_SOLNCFL_STAGED, 1);
+        launch_cell_phase(s, CP_DSOLN_EQO, 1);
+        return 0;
+    }
+    launch_cell_phase(s, CP_SOLNCFL_STAGED, 2);
+    if (int rc = launch_bc_soln(s, true)) { return rc; }
+    launch_cell_phase(s, CP_DSOLN_EQO, 2);
+    return launch_bc_dsoln(s);
 }
 
 // march_substep, euler_march.cpp:339-348
@@ -1688,6 +1739,12 @@ int scg_md_phase(scg_md * s, int phase)
         break;
     case SCG_MD_SUBSTEP:
         if (int rc = substep(s)) { return rc; }
+        break;
+    case SCG_MD_SUBSTEP_IFACE:
+        if (int rc = substep_split(s, 0)) { return rc; }
+        break;
+    case SCG_MD_SUBSTEP_REST:
+        if (int rc = substep_split(s, 1)) { return rc; }
         break;
     default: return fail("scg_md_phase: unknown phase %d", phase);
     }

@@ -73,6 +73,7 @@ struct MeshGroup
     int32_t beg = 0; // first device cell
     int32_t n = 0;   // cells in the group
     int32_t nact = 0; // owned cells (stored first); the rest are halo copies owned by another partition
+    int32_t nif = 0;  // owned interface cells (stored first among the owned ones)
     int64_t off_nbr = 0;  // into scg_mesh::d_nbr   (ints)
     int64_t off_geo = 0;  // into scg_md::geo        (doubles): cevol, cecnd, sfcnd, sfnml in this order
     __host__ __device__ int64_t geo_cevol() const { return off_geo; }

@@ -51,6 +51,7 @@ struct MdGeo // one cell-type group
     int32_t beg;
     int32_t n;    // cells in the group (array stride)
     int32_t nact; // owned cells, stored first: the march kernels stop here
+    int32_t ibeg, iend; // cell range of this launch (mode-3 kernels): [0, nact) or the interface / interior part of it
 };
 
 // L1 / L2 prefetch of one address per lane (no register is tied up while the line is in flight)

@@ -179,8 +179,10 @@ int scg_mesh_create_part(scg_mesh ** out, int ndim, int64_t nnode, int64_t nface
     else if (SCG_ORDER_RCM == order) { rcm_rank(ncell, clfcs_b, fccls_b, key); }
     m->perm.resize(static_cast<size_t>(ncell));
     std::iota(m->perm.begin(), m->perm.end(), 0);
-    // primary key: cell type; then owned cells before halo copies; then the locality key
-    auto halo = [&](int32_t c) -> int { return (owned && !owned[c]) ? 1 : 0; };
+    // primary key: cell type; then owned interface cells (owned == 2: their state is sent to another partition, so
+    // they are marched first and their halo message travels while the interior cells are marched), owned
+    // interior cells, halo copies; then the locality key
+    auto halo = [&](int32_t c) -> int { return !owned ? 1 : (2 == owned[c] ? 0 : (owned[c] ? 1 : 2)); };
     if (key.empty())
     {
         std::stable_sort(m->perm.begin(), m->perm.end(), [&](int32_t a, int32_t b)
@@ -212,7 +214,12 @@ int scg_mesh_create_part(scg_mesh ** out, int ndim, int64_t nnode, int64_t nface
             g.beg = static_cast<int32_t>(k);
             g.n = static_cast<int32_t>(e - k);
             g.nact = 0;
-            for (int64_t q = k; q < e; ++q) { g.nact += halo(m->perm[q]) ? 0 : 1; }
+            g.nif = 0;
+            for (int64_t q = k; q < e; ++q)
+            {
+                g.nact += halo(m->perm[q]) < 2 ? 1 : 0;
+                g.nif += halo(m->perm[q]) == 0 ? 1 : 0;
+            }
             g.off_nbr = off_nbr;
             g.off_geo = off_geo;
             off_nbr += int64_t(ct_nfc(t)) * g.n;

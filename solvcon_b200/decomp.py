@@ -24,8 +24,13 @@ Results are bit-identical to the single-domain run for any number of parts
 
 Transport: :class:`LocalExchange` (all partitions in one process: tests, one GPU) or
 :class:`TorchExchange` (``torch.distributed``: NCCL send/recv of the packed device buffers between GPUs over
-NVLink, gloo for the CPU tests).  The halo of a 5e7-cell partition is ~2.5e5 cells x 160 B = 40 MB per
-neighbour per substep: ~50 us on NVLink against ~60 ms of compute, so the exchange is not overlapped.
+NVLink, gloo for the CPU tests).
+
+Overlap: the owned cells whose state a neighbour needs (*interface* cells, ``owned == 2``) are stored first in
+their type group and marched first (``EulerCore.substep_interface``); their message is packed on the compute
+stream, an event hands it to a communication stream where NCCL sends it while the compute stream marches the
+interior cells (``substep_rest``); a second event makes the unpack -- and with it the next substep -- wait for
+the receive.  No host synchronisation is left inside ``march``.
 """
 from __future__ import annotations
 
@@ -198,6 +203,32 @@ class LocalExchange:
             s.unpack_segments(segs, what)
 
 
+class LocalSplitExchange(LocalExchange):
+    """LocalExchange driving the two-stage substep (interface cells, pack, interior cells, unpack) of every
+    partition in turn -- the kernel ranges and the ordering of the overlapped march without the streams."""
+
+    def march(self, steps):
+        for _ in range(2 * int(steps)):
+            for s in self.solvers.values():
+                s.core.substep_interface()
+            packed = {}
+            for r, s in self.solvers.items():
+                ptr, n = s.core.halo_pack(0)
+                packed[r] = (ptr, s.send_offsets)
+            for s in self.solvers.values():
+                s.core.substep_rest()
+            from . import _lib
+            _lib.sync()
+            for r, s in self.solvers.items():
+                w = s.core.halo_width(0)
+                segs = []
+                for q in s.part.neighbours:
+                    ptr, offs = packed[q]
+                    o0, o1 = offs[r]
+                    segs.append((ptr + o0 * w * 8, (o1 - o0) * w))
+                s.unpack_segments(segs, 0)
+
+
 class TorchExchange:
     """``torch.distributed`` transport (NCCL between GPUs, gloo on the CPU): grouped isend/irecv of the
     packed buffers with every neighbour rank."""
@@ -205,7 +236,7 @@ class TorchExchange:
     def __init__(self, solver, device):
         import torch
         import torch.distributed as dist
-        self.torch, self.dist, self.s, self.device = torch, dist, solver, device
+        self.torch, self.dist, self.s, self.device = torch, dist, solver, torch.device(device)
         self.recvbuf = {}
 
     def _view(self, ptr, n):
@@ -243,6 +274,46 @@ class TorchExchange:
         if s.nrecv:
             s.core.halo_unpack(rb.data_ptr(), what)
 
+    def exchange_split(self, what, rest):
+        """Overlapped exchange (CUDA only): pack on the library stream -> event -> NCCL on a communication stream
+        while ``rest()`` (the interior march) is enqueued on the library stream -> event -> unpack."""
+        torch, dist, s = self.torch, self.dist, self.s
+        if self.device.type != "cuda":
+            rest()
+            return self.exchange(what)
+        if getattr(self, "_lib_stream", None) is None:
+            from . import _lib
+            self._lib_stream = torch.cuda.ExternalStream(int(_lib.load().scg_stream_handle()), device=self.device)
+            self._comm = torch.cuda.Stream(device=self.device)
+            self._ev_packed = torch.cuda.Event()
+            self._ev_done = torch.cuda.Event()
+        w = s.core.halo_width(what)
+        ptr, n = s.core.halo_pack(what)
+        self._ev_packed.record(self._lib_stream)
+        rest()  # interior cells + boundary kernels, enqueued behind the pack on the library stream
+        if what not in self.recvbuf:
+            self.recvbuf[what] = torch.empty(max(1, s.nrecv * w), dtype=torch.float64, device=self.device)
+        rb = self.recvbuf[what]
+        sendall = self._view(ptr, max(1, n)) if n else None
+        ops, ro = [], 0
+        for q in s.part.neighbours:
+            o0, o1 = s.send_offsets[q]
+            if o1 > o0:
+                ops.append(dist.P2POp(dist.isend, sendall[o0 * w:o1 * w], q))
+            nr = len(s.part.recv.get(q, ()))
+            if nr:
+                ops.append(dist.P2POp(dist.irecv, rb[ro * w:(ro + nr) * w], q))
+            ro += nr
+        with torch.cuda.stream(self._comm):
+            self._comm.wait_event(self._ev_packed)
+            if ops:
+                for req in dist.batch_isend_irecv(ops):
+                    req.wait()  # stream-ordered for NCCL: the communication stream waits, not the host
+            self._ev_done.record(self._comm)
+        self._lib_stream.wait_event(self._ev_done)
+        if s.nrecv:
+            s.core.halo_unpack(rb.data_ptr(), what)
+
 
 # ------------------------------------------------------------------------------------- solver ---
 
@@ -254,7 +325,11 @@ class DistEulerCore:
         from .multidim import EulerCore
         self.part = part
         mesh = part.build_mesh()
-        self.core = EulerCore(mesh, time_increment, order=order, owned=part.owned)
+        own = part.owned.astype(np.int8).copy()
+        snd0 = part.send_list()
+        if len(snd0):
+            own[snd0] = 2  # interface cells: marched first so that their message travels during the interior march
+        self.core = EulerCore(mesh, time_increment, order=order, owned=own)
         self.core.resident(True)
         snd, rcv = part.send_list(), part.recv_list()
         self.nsend, self.nrecv = len(snd), len(rcv)
@@ -295,6 +370,11 @@ class DistEulerCore:
         self.core.sync_to_host()
 
     def march(self, steps):
+        split = getattr(self.transport, "exchange_split", None)
         for _ in range(2 * int(steps)):
-            self.core.substep_local()
-            self.transport.exchange(0)
+            if split is not None:
+                self.core.substep_interface()
+                split(0, self.core.substep_rest)
+            else:
+                self.core.substep_local()
+                self.transport.exchange(0)

@@ -23,7 +23,8 @@ import numpy as np
 from . import _lib
 from .simplearray import SimpleArray
 
-(MD_UPDATE, MD_SOLT, MD_SOLN, MD_BC_SOLN, MD_CFL, MD_DSOLN, MD_BC_DSOLN, MD_PREPARE_CE, MD_SUBSTEP) = range(9)
+(MD_UPDATE, MD_SOLT, MD_SOLN, MD_BC_SOLN, MD_CFL, MD_DSOLN, MD_BC_DSOLN, MD_PREPARE_CE, MD_SUBSTEP,
+ MD_SUBSTEP_IFACE, MD_SUBSTEP_REST) = range(11)
 BC_NONREFL, BC_SLIPWALL, BC_INLET = 0, 1, 2
 ORDER_NONE, ORDER_MORTON, ORDER_RCM = 0, 1, 2
 _ORDERS = {"none": 0, "morton": 1, "rcm": 2, 0: 0, 1: 1, 2: 2}
@@ -350,6 +351,17 @@ class EulerCore:
     def substep_local(self):
         """One march_substep of this partition without any host transfer (resident mode only)."""
         if self._lib.scg_md_phase(self._h, MD_SUBSTEP):
+            _raise()
+
+    def substep_interface(self):
+        """First stage of a split substep: update(), calc_solt, then the owned INTERFACE cells (``owned == 2``);
+        their state may be packed and sent as soon as this returns (stream order)."""
+        if self._lib.scg_md_phase(self._h, MD_SUBSTEP_IFACE):
+            _raise()
+
+    def substep_rest(self):
+        """Second stage of a split substep: the interior cells and the boundary kernels."""
+        if self._lib.scg_md_phase(self._h, MD_SUBSTEP_REST):
             _raise()
 
     def algorithmic_bytes(self):

@@ -48,22 +48,26 @@ def _run_global(ndim, ndcrd, cltpn, clnds, dt, steps):
     return {n: getattr(core, n).body.copy() for n in STATE}, (lo, hi, ctr, span)
 
 
-def _run_parts(parts, dt, steps, geo):
-    from solvcon_b200.decomp import DistEulerCore, LocalExchange
+def _run_parts(parts, dt, steps, geo, split=False):
+    from solvcon_b200.decomp import DistEulerCore, LocalExchange, LocalSplitExchange
     lo, hi, ctr, span = geo
     solvers = {r: DistEulerCore(p, dt) for r, p in parts.items()}
     for r, s in solvers.items():
         _setup(s.core, s.part.mesh, s.part.physical_boundary_groups(lo, hi), s.part.ndim, ctr, span, s.upload_state)
-    ex = LocalExchange(solvers)
+    ex = LocalSplitExchange(solvers) if split else LocalExchange(solvers)
     for s in solvers.values():
         s.transport = ex
     ex.exchange(1)
     ex.exchange(0)
-    # lock-step march: every partition does its substep, then one exchange
-    for _ in range(2 * steps):
-        for s in solvers.values():
-            s.core.substep_local()
-        ex.exchange(0)
+    if split:
+        # the two-stage substep of the overlapped march: interface cells, pack, interior cells, unpack
+        ex.march(steps)
+    else:
+        # lock-step march: every partition does its substep, then one exchange
+        for _ in range(2 * steps):
+            for s in solvers.values():
+                s.core.substep_local()
+            ex.exchange(0)
     out = {}
     for r, s in solvers.items():
         s.download_state()
@@ -72,8 +76,9 @@ def _run_parts(parts, dt, steps, geo):
     return out
 
 
+@pytest.mark.parametrize("split", [False, True])
 @pytest.mark.parametrize("name,nparts", [("mixed3d", 2), ("mixed3d", 3), ("mixed2d", 4), ("hex3d", 2)])
-def test_rcb_partitions_bit_identical(gpu, name, nparts):
+def test_rcb_partitions_bit_identical(gpu, name, nparts, split):
     from cases import md_mesh_case
     from solvcon_b200.decomp import make_partitions, rcb_partition
     from solvcon_b200.mesh import make_mesh
@@ -85,7 +90,7 @@ def test_rcb_partitions_bit_identical(gpu, name, nparts):
     part = rcb_partition(gm.clcnd.body, nparts)
     assert len(np.unique(part)) == nparts
     parts = make_partitions(ndim, ndcrd, cltpn, clnds, part)
-    res = _run_parts(parts, dt, steps, geo)
+    res = _run_parts(parts, dt, steps, geo, split)
     seen = np.zeros(len(cltpn), dtype=int)
     for r, (gid, arrs) in res.items():
         seen[gid] += 1
