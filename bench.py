@@ -188,10 +188,123 @@ class E1DWorkload:
 def make_workload(args):
     if args.workload == "e1d":
         return E1DWorkload(args.size or 100_000_001, args.chunk)
+    if args.workload in ("st1d", "st1d_burgers"):
+        return ST1DWorkload(args.size or 1_000_000_001, args.chunk, eq=1 if args.workload.endswith("burgers") else 0)
     if args.workload in ("md3d", "md2d"):
         from solvcon_b200 import bench_md  # noqa
         return bench_md.make(args)
     raise SystemExit(f"unknown workload {args.workload}")
+
+
+class ST1DWorkload:
+    """1D scalar CESE (spacetime.LinearScalarSolver / InviscidBurgersSolver), BASELINE.json configs[1]: a periodic
+    grid of ``ncelm`` conservation elements PER GPU (2*ncelm+1 solution points), so0 = 1/2 sin x, dt = dx/2; with
+    more than one GPU the ranks are the slabs of one ring (solvcon_b200/decomp1d.py)."""
+
+    dtype = "f64"
+    balg = 56  # bytes per update, SURVEY.md 8(d)
+
+    def __init__(self, npoints, chunk, eq=0):
+        self.ncelm = max(4, int(npoints) // 2)
+        self.chunk = chunk
+        self.eq = int(eq)
+        self.name = "st1d_burgers" if self.eq else "st1d_linear"
+        self.dominant_kernel = "st_half_kernel<%s, alpha 2> (one launch per half step)" % ("burgers" if self.eq else "linear")
+
+    def describe(self, world):
+        return {"workload": f"1D scalar CESE (spacetime.{'InviscidBurgers' if self.eq else 'LinearScalar'}Solver), periodic, "
+                            f"{2 * self.ncelm + 1} solution points per GPU, so0 = sin(x)/2, dt = dx/2, "
+                            f"march_alpha2({self.chunk}) per step",
+                "points_per_gpu": 2 * self.ncelm + 1, "chunk_steps": self.chunk,
+                "l2_policy": "inputs larger than L2 (%.1f GB state per GPU)" % (self.ncelm * 2 * 32 / 1e9),
+                "decomposition": "none" if world == 1 else
+                "contiguous slabs on a ring, one per GPU; {so0, so1} of the two odd-plane end points exchanged with "
+                "both neighbours by NCCL send/recv once per step (32 B per rank per step)"}
+
+    def updates_per_step(self):
+        return (2 * self.ncelm + 1) * self.chunk
+
+    def launches_per_step(self):
+        return 2 * self.chunk
+
+    def alg_bytes_per_launch(self):
+        return self.balg * self.updates_per_step() / self.launches_per_step()
+
+    def _ic(self, x, so0, so1):
+        so0[2::2] = 0.5 * np.sin(x[2::2])
+        so1[2::2] = 0.5 * np.cos(x[2::2])
+
+    def build_device(self):
+        from solvcon_b200 import spacetime as st
+        world, rank = getattr(self, "world", 1), getattr(self, "rank", 0)
+        n = self.ncelm
+        # dx = 2^-14 exactly: the reference's Grid fills xloc by cumulative addition (core.cpp:36-43), which at 5e8
+        # elements drifts past xmax for a general dx (its own constructor then rejects the grid); with a power-of-two
+        # spacing every partial sum is exact.  ~1e5 points per wave length of the initial sine at every size.
+        span = n * 2.0 ** -14
+        self.dt = 0.5 * span / n
+        self.ring = None
+        if world > 1:
+            # weak scaling: the ring is `world` copies of the span; every rank generates its own slab's coordinates
+            # (bit-parity of the decomposition against one global grid is what tests/test_gpu_1d.py checks)
+            from solvcon_b200.decomp1d import TorchRing
+            xs = st.Grid(rank * span, (rank + 1) * span, n).xcoord.ndarray
+            self.ring = TorchRing(self.eq, xs, 0, n, self.dt, f"cuda:{self.local}")
+            self.dev = self.ring.slab.svr
+        else:
+            grid = st.Grid(0.0, span, n)
+            self.dev = (st.InviscidBurgersSolver if self.eq else st.LinearScalarSolver)(grid, self.dt)
+        self._ic(self.dev.grid.xcoord.ndarray, self.dev.so0.ndarray[:, 0], self.dev.so1.ndarray[:, 0])
+        return self.dev
+
+    def resident_begin(self):
+        self.dev.resident(True)
+
+    def resident_step(self):
+        if self.ring is not None:
+            self.ring.march(2, self.chunk)
+        else:
+            self.dev.march_alpha2(self.chunk)
+
+    def e2e_step(self):
+        if self.ring is not None:
+            self.dev._push(True)
+            self.ring.march(2, self.chunk)
+            self.dev.sync_to_host()
+        else:
+            self.dev.march_alpha2(self.chunk)
+
+    def e2e_bytes(self):
+        nx = 2 * self.ncelm + 5
+        return nx * 8 * 4, nx * 8 * 3
+
+    def result_check(self):
+        return float(self.dev.so0.ndarray[2::2, 0].sum())
+
+    def cpu_run(self, budget_s=15.0):
+        from oracle import bridge
+        n = min(self.ncelm, 2_000_000)
+        kind = "reference" if bridge.have_ref() else "port"
+        cls = bridge.RefScalar1D if bridge.have_ref() else bridge.PortScalar1D
+        span = n * 2.0 ** -14
+        chk = cls(self.eq, 0.0, span, n, 0.5 * span / n)
+        chk.so0[...] = 0.0
+        chk.so1[...] = 0.0
+        chk.cfl[...] = 0.0
+        self._ic(chk.x, chk.so0, chk.so1)
+        chk.march(2, 1)
+        t0 = time.perf_counter()
+        steps = 0
+        while True:
+            chk.march(2, 2)
+            steps += 2
+            el = time.perf_counter() - t0
+            if el > budget_s or steps >= 200:
+                break
+        upd = (2 * n + 1) * steps
+        return {"value": upd / el, "unit": UNIT, "cores": 1, "kind": kind,
+                "sample": f"1D {'Burgers' if self.eq else 'linear'} scalar, ncelm={n}, march_alpha2({steps}) in {el:.2f} s, "
+                          f"single thread (the reference is single-threaded)"}, upd, el
 
 
 # --------------------------------------------------------------------------------- main ---

@@ -96,6 +96,14 @@ SCG_API int scg_st_march(scg_st * s, int alpha, int64_t steps);
 SCG_API int scg_st_reduce(scg_st * s, double * cfl_min, double * cfl_max, double * so0_sum);
 /* slab decomposition: this object owns CEs [ce_begin, ce_end) of a global ncelm_global grid;
  * halo points are exchanged by the caller through scg_st_halo_pack/unpack */
+/* slab mode on/off: when on, march / march_half leave the odd-plane ghosts to scg_st_halo_unpack instead of the
+ * periodic copy of treat_boundary_so0/so1 (core.hpp:982-1004) */
+SCG_API int scg_st_set_halo_mode(scg_st * s, int on);
+/* one half step: 1 = march_half1_alpha (even -> odd plane, core.hpp:1006-1015), 2 = march_half2_alpha (:1017-1025).
+ * A slab marches half 1, exchanges {so0, so1} of its first / last odd-plane point with its ring neighbours
+ * (halo_pack -> send/recv -> halo_unpack), then marches half 2. */
+SCG_API int scg_st_march_half(scg_st * s, int half, int alpha);
+/* dev_send_left / right: 2 doubles each on the device ({so0, so1} of the first / last odd-plane point) */
 SCG_API int scg_st_halo_pack(scg_st * s, int odd_plane, double * dev_send_left, double * dev_send_right);
 SCG_API int scg_st_halo_unpack(scg_st * s, int odd_plane, const double * dev_recv_left, const double * dev_recv_right);
 

@@ -547,6 +547,25 @@ int scg_st_march(scg_st * s, int alpha, int64_t steps)
     return 0;
 }
 
+int scg_st_set_halo_mode(scg_st * s, int on)
+{
+    SCG_REQUIRE(s, "scg_st_set_halo_mode: null solver");
+    s->halo_mode = 0 != on;
+    return 0;
+}
+
+int scg_st_march_half(scg_st * s, int half, int alpha)
+{
+    SCG_REQUIRE(s, "scg_st_march_half: null solver");
+    SCG_REQUIRE(1 == half || 2 == half, "scg_st_march_half: half must be 1 or 2");
+    SCG_REQUIRE(alpha >= 0 && alpha <= 2, "scg_st_march_half: alpha must be 0, 1 or 2");
+    int const bc = s->halo_mode ? 0 : (F_BC0 | F_BC1);
+    if (1 == half) { launch_half(s, 1, F_SO0 | F_CFL | F_SO1 | bc, alpha); } // march_half1_alpha, core.hpp:1006-1015
+    else { launch_half(s, 0, F_SO0 | F_CFL | F_SO1, alpha); }                // march_half2_alpha, core.hpp:1017-1025
+    SCG_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int scg_st_reduce(scg_st * s, double * cfl_min, double * cfl_max, double * so0_sum)
 {
     int const nblk = 512;

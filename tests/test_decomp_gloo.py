@@ -54,3 +54,23 @@ def test_gloo_march_bit_identical(bridge, name, world):
            os.path.join(HERE, "decomp_worker.py"), name, "6"]
     res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+def test_slab_ranges_cover_the_grid():
+    from solvcon_b200.decomp1d import slab_ranges
+    for n, p in ((10, 1), (10, 3), (1_000_003, 8), (7, 7)):
+        r = slab_ranges(n, p)
+        assert r[0][0] == 0 and r[-1][1] == n and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+        sizes = [b - a for a, b in r]
+        assert min(sizes) >= 1 and max(sizes) - min(sizes) <= 1
+
+
+@pytest.mark.parametrize("eq,world", [(0, 2), (1, 3)])
+def test_gloo_1d_ring_bit_identical(bridge, eq, world):
+    """1D scalar slabs over a gloo ring: same message order as TorchRing, CPU checker as the engine."""
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(29440 + world + eq),
+           os.path.join(HERE, "decomp1d_worker.py"), str(eq), "2003", "30"]
+    res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]

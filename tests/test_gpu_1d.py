@@ -204,3 +204,34 @@ def test_scalar_reduce_and_resident(gpu):
     ref_pts = np.r_[cfl[2:2 * n + 3:2], cfl[3:2 * n + 2:2]]
     assert mn == ref_pts.min() and mx == ref_pts.max()
     assert abs(sm - svr.so0.ndarray[2:2 * n + 3:2, 0].sum()) < 1e-9
+
+
+@pytest.mark.parametrize("eq", [0, 1])
+@pytest.mark.parametrize("nparts", [1, 2, 3, 5])
+def test_scalar_slabs_bit_identical(gpu, bridge, eq, nparts):
+    """BASELINE config 2 at parity size: the slab-decomposed march (ring halo exchange of the odd-plane end points,
+    solvcon_b200/decomp1d.py) equals the reference's undecomposed periodic march in every slot of every slab."""
+    from solvcon_b200 import spacetime as st
+    from solvcon_b200.decomp1d import LocalRing, ScalarSlab, slab_ranges
+    n, steps, alpha = 20_003, 40, 2
+    xmax = 8 * np.pi
+    dt = 0.5 * xmax / n
+    chk = (bridge.RefScalar1D if bridge.have_ref() else bridge.PortScalar1D)(eq, 0.0, xmax, n, dt)
+    xg = st.Grid(0.0, xmax, n).xcoord.ndarray
+    assert np.array_equal(xg, chk.x)
+    scalar_ic(chk.x, chk.so0, chk.so1, chk.cfl)
+    so0, so1, cfl = chk.so0.copy(), chk.so1.copy(), chk.cfl.copy()
+    slabs = [ScalarSlab(eq, xg, c0, c1, dt) for c0, c1 in slab_ranges(n, nparts)]
+    assert slabs[0].c0 == 0 and slabs[-1].c1 == n and all(a.c1 == b.c0 for a, b in zip(slabs, slabs[1:]))
+    for s in slabs:
+        s.load_global(so0, so1, cfl)
+    chk.march(alpha, steps)
+    LocalRing(slabs).march(alpha, steps)
+    strict = bool(gpu.load().scg_build_is_strict())
+    for r, s in enumerate(slabs):
+        a0, a1, ac = s.fetch()
+        lo, hi = 2 * s.c0 + 1, 2 * s.c1 + 4       # every slot but the two outermost ghost coordinates
+        _assert_same(a0[1:-1], chk.so0[lo:hi], f"slab {r} so0", strict)
+        _assert_same(a1[1:-1], chk.so1[lo:hi], f"slab {r} so1", strict)
+        _assert_same(ac[1:-1], chk.cfl[lo:hi], f"slab {r} cfl", strict)
+    assert np.abs(chk.so1).max() > 0.1
