@@ -245,6 +245,19 @@ SCG_API int scg_md_march(scg_md * s, int64_t steps);
 /* caller-side reductions of solvcon/multidim/euler/_field.py:138-148 done on the device:
  * min/max of cflo over body cells and sum(density * clvol) */
 SCG_API int scg_md_reduce(scg_md * s, const double * clvol_host_or_null, double * cfl_min, double * cfl_max, double * mass);
+/* derived body-cell fields of EulerField (solvcon/multidim/euler/_field.py:56-126: density, velx, vely, speed,
+ * pressure, mach, total_energy, cfl; velz added) evaluated on the device from the newest solution (so0n) with
+ * numpy's operation order, written to out[ncell] in reference cell order */
+#define SCG_F_DENSITY 0
+#define SCG_F_VELX 1
+#define SCG_F_VELY 2
+#define SCG_F_VELZ 3
+#define SCG_F_SPEED 4
+#define SCG_F_PRESSURE 5
+#define SCG_F_MACH 6
+#define SCG_F_TOTAL_ENERGY 7
+#define SCG_F_CFL 8
+SCG_API int scg_md_derived(scg_md * s, int field, double * out);
 /* algorithmic bytes one substep moves for this mesh, for the roofline */
 SCG_API int scg_md_algorithmic_bytes(scg_md * s, int64_t * bytes_per_substep);
 /* get_normal_matrix(ifc), euler_bc.cpp:391-425 (host-side helper, row-major ndim x ndim) */

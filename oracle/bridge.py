@@ -330,6 +330,20 @@ class RefMesh:
             self.h = None
 
 
+def ref_gmsh_mesh(data: bytes):
+    """``Gmsh(data).to_block()`` of the reference (cpp/solvcon/inout/gmsh.cpp) as a RefMesh."""
+    lib = ref_lib()
+    lib.ref_gmsh_to_block.restype = C.c_void_p
+    lib.ref_gmsh_to_block.argtypes = [C.c_char_p, C.c_int64]
+    h = lib.ref_gmsh_to_block(data, len(data))
+    if not h:
+        raise ValueError(lib.ref_last_error().decode())
+    m = RefMesh.__new__(RefMesh)
+    m.lib, m.h = lib, h
+    m.ndim = int(lib.ref_mesh_count(h, C_NDIM))
+    return m
+
+
 def make_ref_mesh(ndim, ndcrd, cltpn, clnds, bcs=()):
     """Build a reference StaticMesh from nodes+cells the way the reference's tests do
     (tests/test_multidim.py:152-281): fill ndcrd/cltpn/clnds, build_interior,

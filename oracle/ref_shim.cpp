@@ -24,6 +24,7 @@
 #include <solvcon/spacetime/kernel/inviscid_burgers.hpp>
 #include <solvcon/mesh/mesh.hpp>
 #include <solvcon/multidim/euler.hpp>
+#include <solvcon/inout/gmsh.hpp>
 
 #include <cstring>
 #include <memory>
@@ -229,6 +230,23 @@ ref_mesh * ref_mesh_create(int ndim, int64_t nnode, int64_t nface, int64_t ncell
         return nullptr;
     }
 }
+// Gmsh(data).to_block(), cpp/solvcon/inout/gmsh.cpp:10-117 (the reference's reader, unmodified)
+ref_mesh * ref_gmsh_to_block(char const * data, int64_t nbytes)
+{
+    try
+    {
+        sc::inout::Gmsh gmsh(std::string(data, static_cast<size_t>(nbytes)));
+        auto * h = new ref_mesh;
+        h->p = gmsh.to_block();
+        return h;
+    }
+    catch (std::exception const & e)
+    {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+
 void ref_mesh_destroy(ref_mesh * h) { delete h; }
 
 int ref_mesh_build_interior(ref_mesh * h, int do_metric, int do_edge)

@@ -98,6 +98,7 @@ _SIGNATURES = {
     "scg_md_set_params": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double]),
     "scg_md_set_time_increment": (C.c_int, [C.c_void_p, C.c_double]),
     "scg_md_set_fused": (C.c_int, [C.c_void_p, C.c_int]),
+    "scg_md_derived": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "scg_md_init_solution": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_double]),
     "scg_md_add_bc": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]),
     "scg_md_clear_bc": (C.c_int, [C.c_void_p]),

@@ -994,6 +994,44 @@ __global__ void md_geo_rows_kernel(int which, double * stage, int64_t row0, int6
     else { stage[t] = slot ? *slot : 0.0; }
 }
 
+// Derived body-cell fields of solvcon/multidim/euler/_field.py:56-126 evaluated on the device, one value per
+// reference-order cell (the callers evaluate them with numpy after every chunk, which costs a full download of
+// the state; this moves 8 B per cell).  Same operations in numpy's order: vel = mom / rho; speed =
+// sqrt(sum vel^2); pressure = (gamma - 1) * (E - (0.5 * rho) * speed^2); mach = speed / sqrt(gamma * p / rho).
+template <int ND>
+__global__ void md_derived_kernel(int field, double const * so0, double const * gamma, double const * cflo, int64_t S,
+                                  int32_t const * rowmap_body, int64_t r0, int64_t nr, double * out)
+{
+    int64_t const q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (q >= nr) { return; }
+    int64_t const k = rowmap_body[r0 + q];
+    double const rho = so0[k];
+    double val;
+    if (SCG_F_DENSITY == field) { val = rho; }
+    else if (SCG_F_TOTAL_ENERGY == field) { val = so0[(ND + 1) * S + k]; }
+    else if (SCG_F_CFL == field) { val = cflo[k]; }
+    else if (field >= SCG_F_VELX && field <= SCG_F_VELZ) { val = so0[(1 + field - SCG_F_VELX) * S + k] / rho; }
+    else
+    {
+        double sq = 0.0;
+#pragma unroll
+        for (int d = 0; d < ND; ++d)
+        {
+            double const v = so0[(1 + d) * S + k] / rho;
+            sq = (0 == d) ? v * v : sq + v * v;
+        }
+        double const speed = sqrt(sq);
+        if (SCG_F_SPEED == field) { val = speed; }
+        else
+        {
+            double const ga = gamma[k];
+            double const pr = (ga - 1.0) * (so0[(ND + 1) * S + k] - 0.5 * rho * (speed * speed));
+            val = (SCG_F_PRESSURE == field) ? pr : speed / sqrt(ga * pr / rho);
+        }
+    }
+    out[q] = val;
+}
+
 __global__ void md_fill_kernel(double * p, int64_t n, double v)
 {
     int64_t const t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -1809,6 +1847,28 @@ int scg_md_reduce(scg_md * s, const double * clvol_host_or_null, double * cfl_mi
     if (cfl_min) { *cfl_min = mn; }
     if (cfl_max) { *cfl_max = mx; }
     if (mass) { *mass = sm; }
+    return 0;
+}
+
+int scg_md_derived(scg_md * s, int field, double * out)
+{
+    SCG_REQUIRE(s && out, "scg_md_derived: null argument");
+    SCG_REQUIRE(field >= SCG_F_DENSITY && field <= SCG_F_CFL, "scg_md_derived: unknown field %d", field);
+    SCG_REQUIRE(!(SCG_F_VELZ == field && 2 == s->ndim), "scg_md_derived: no z velocity in 2D");
+    scg_mesh * m = s->mesh;
+    double const * so0n = s->so0[1 - s->cur].p; // march() leaves the newest step in so0n (_field.py:47-54)
+    int32_t const * rowmap_body = m->d_rowmap.p + m->ngstcell;
+    int64_t const chunk = STAGE_DOUBLES;
+    for (int64_t r0 = 0; r0 < m->ncell; r0 += chunk)
+    {
+        int64_t const nr = (m->ncell - r0 < chunk) ? m->ncell - r0 : chunk;
+        unsigned const grid = static_cast<unsigned>(ceil_div(nr, 256));
+        if (2 == s->ndim) { md_derived_kernel<2><<<grid, 256, 0, stream()>>>(field, so0n, s->gamma.p, s->cflo.p, m->stride, rowmap_body, r0, nr, s->stage.p); }
+        else { md_derived_kernel<3><<<grid, 256, 0, stream()>>>(field, so0n, s->gamma.p, s->cflo.p, m->stride, rowmap_body, r0, nr, s->stage.p); }
+        count_launch();
+        SCG_CUDA(cudaMemcpyAsync(out + r0, s->stage.p, sizeof(double) * nr, cudaMemcpyDeviceToHost, stream()));
+        SCG_CUDA(cudaStreamSynchronize(stream()));
+    }
     return 0;
 }
 
