@@ -52,15 +52,18 @@ class StaticMeshBc:
     """Mirror of ``StaticMeshBc`` (``StaticMesh.hpp:146-246``): ``name``, ``nbound``, ``facn`` [n,3]."""
 
     def __init__(self, name, facn):
+        from .simplearray import SimpleArray
         self.name = name
-        self.facn = facn
+        # a SimpleArray like in the reference binding, so that ``bc.facn.ndarray[:, 0]`` (obsrefl _driver.py:489-491)
+        # and ``bc.facn[i, 0]`` both work
+        self.facn = facn if isinstance(facn, SimpleArray) else SimpleArray(array=np.ascontiguousarray(facn))
 
     def __len__(self):
         return self.nbound
 
     @property
     def nbound(self):
-        return self.facn.shape[0]
+        return self.facn.ndarray.shape[0]
 
 
 class StaticMesh:
