@@ -116,6 +116,23 @@ class MD3DWorkload:
     def build_device(self):
         world = getattr(self, "world", 1)
         if world > 1:
+            # every rank builds its own slab on the host (~0.85 KB of host memory per cell at the peak of the table
+            # construction): keep the ranks of one box inside its RAM
+            try:
+                import psutil
+                budget = 0.6 * psutil.virtual_memory().available / world
+                cap = int(budget / 850.0)
+                if getattr(self, "dist", None) is not None:   # the ranks must agree on the size: take the smallest view
+                    import torch
+                    t = torch.tensor([cap], dtype=torch.int64, device=f"cuda:{self.local}")
+                    self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+                    cap = int(t.item())
+                if cap < self.ncell_target:
+                    self.size_note = (f"cells per GPU reduced from {self.ncell_target} to {cap}: host RAM "
+                                      f"({psutil.virtual_memory().available / 2**30:.0f} GiB available for {world} ranks)")
+                    self.ncell_target = max(cap, 1_000_000)
+            except ImportError:
+                pass
             self.mesh, self.dist_svr, self.info = build_case_3d_dist(self.ncell_target, self.rank, world, self.local,
                                                                      self.order, self.kinds)
             self.dev = self.dist_svr.core
@@ -144,6 +161,8 @@ class MD3DWorkload:
              f"y-slabs, one per GPU, domain extended in y with the rank count; halo exchange of so0n+so1n after every "
              f"substep by NCCL isend/irecv ({self.info.get('halo_bytes_per_substep', 0)} B sent per rank per substep)",
              "mesh": self.info}
+        if getattr(self, "size_note", None):
+            d["size_note"] = self.size_note
         return d
 
     def updates_per_step(self):
