@@ -61,6 +61,7 @@ SCG_API int scg_host_free(void * ptr);
 /* raw device scratch and an async copy on the library stream (halo staging between partitions) */
 SCG_API int scg_dev_alloc(void ** ptr, int64_t bytes);
 SCG_API int scg_dev_free(void * ptr);
+
 SCG_API int scg_dev_copy(void * dst, const void * src, int64_t bytes);
 
 /* --------------------------------------------------------------- 1D scalar

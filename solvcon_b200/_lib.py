@@ -198,3 +198,24 @@ def pinned_empty(shape, dtype=np.float64):
     buf = (C.c_char * max(n, 1)).from_address(p.value)
     arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
     return arr, p
+
+
+def pinned_zeros(shape, dtype=np.float64):
+    """A zero-filled numpy array in page-locked host memory (``scg_host_alloc``), freed with the array; falls back
+    to ordinary memory where no CUDA device is available (CPU-only test runs).  Pinned memory makes the
+    upload/download of the API-visible arrays run at the PCIe rate."""
+    import weakref
+    shape = (int(shape),) if isinstance(shape, (int, np.integer)) else tuple(int(x) for x in shape)
+    dt = np.dtype(dtype)
+    nbytes = int(np.prod(shape, dtype=np.int64)) * dt.itemsize
+    if nbytes < (1 << 16) or os.environ.get("SCG_NO_PINNED"):
+        return np.zeros(shape, dtype=dt)
+    lib = load()
+    p = C.c_void_p()
+    if lib.scg_host_alloc(C.byref(p), nbytes) != 0 or not p.value:
+        return np.zeros(shape, dtype=dt)
+    buf = (C.c_char * nbytes).from_address(p.value)
+    a = np.frombuffer(buf, dtype=dt).reshape(shape)
+    a[...] = 0
+    weakref.finalize(buf, lib.scg_host_free, C.c_void_p(p.value))
+    return a

@@ -124,7 +124,7 @@ class EulerCore:
         a = self._a.get(name)
         if a is None:
             shape, ng = self._shapes[name]
-            a = SimpleArray(shape, 0.0, nghost=ng)
+            a = SimpleArray(shape, 0.0, nghost=ng, pinned=name in ARRAY_IDS)
             self._a[name] = a
             if name in ARRAY_IDS:
                 _lib.check(self._lib.scg_md_download(self._h, ARRAY_IDS[name], _lib.ptr(a.ndarray)))

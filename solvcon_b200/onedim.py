@@ -41,10 +41,11 @@ class Euler1DCore:
         self._ncoord = ncoord
         self._dt = float(time_increment)
         # host storage, reference layout (Euler1DCore.cpp:29-34)
-        self._coord = np.zeros(ncoord)
-        self._cfl = np.zeros(ncoord)
-        self._so0 = np.zeros((ncoord, 3))
-        self._so1 = np.zeros((ncoord, 3))
+        # page-locked host twins (plain memory without a device): transfers run at the PCIe rate
+        self._coord = _lib.pinned_zeros(ncoord)
+        self._cfl = _lib.pinned_zeros(ncoord)
+        self._so0 = _lib.pinned_zeros((ncoord, 3))
+        self._so1 = _lib.pinned_zeros((ncoord, 3))
         self._gamma = np.full(ncoord, 1.4)
         self._resident = False
 

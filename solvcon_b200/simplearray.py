@@ -23,13 +23,19 @@ import numpy as np
 class SimpleArray:
     __slots__ = ("_a", "_nghost", "_owner")
 
-    def __init__(self, shape=None, value=None, dtype=np.float64, array=None, nghost=0):
+    def __init__(self, shape=None, value=None, dtype=np.float64, array=None, nghost=0, pinned=False):
         if array is not None:
             self._a = array if isinstance(array, np.ndarray) else np.asarray(array)
         else:
             if isinstance(shape, (int, np.integer)):
                 shape = (int(shape),)
-            self._a = np.zeros(tuple(shape), dtype=dtype)
+            if pinned:
+                # page-locked memory for the host twins of device arrays (additive: ``pinned`` is not a reference
+                # argument); plain memory where no device is available
+                from . import _lib
+                self._a = _lib.pinned_zeros(tuple(shape), dtype)
+            else:
+                self._a = np.zeros(tuple(shape), dtype=dtype)
             if value is not None:
                 self._a.fill(value)
         self._nghost = 0

@@ -74,7 +74,7 @@ class Grid:
         self._xmin = float(xloc[0])
         self._xmax = float(xloc[n])
         nx = 2 * n + 5
-        x = np.zeros(nx)
+        x = _lib.pinned_zeros(nx)
         x[2:2 * n + 3:2] = xloc                                  # core.cpp:77-80
         x[3:2 * n + 2:2] = (x[2:2 * n + 1:2] + x[4:2 * n + 3:2]) / 2  # core.cpp:82-86
         for it in (1, 2):                                        # core.cpp:88-98
@@ -321,9 +321,9 @@ class _ScalarSolver:
         self._h = C.c_void_p()
         _lib.check(self._lib.scg_st_create(C.byref(self._h), self._eq, n, float(time_increment)))
         self._dt = float(time_increment)
-        self._so0 = SimpleArray((nx, 1))
-        self._so1 = SimpleArray((nx, 1))
-        self._cfl = SimpleArray((nx,))
+        self._so0 = SimpleArray((nx, 1), pinned=True)
+        self._so1 = SimpleArray((nx, 1), pinned=True)
+        self._cfl = SimpleArray((nx,), pinned=True)
         self._resident = False
         self._x_uploaded = False
 
