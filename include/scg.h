@@ -239,6 +239,10 @@ SCG_API int scg_md_add_bc(scg_md * s, int kind, const int32_t * faces, int64_t n
 SCG_API int scg_md_clear_bc(scg_md * s);
 /* host array (reference layout, ghost rows first) <-> device store */
 SCG_API int scg_md_upload(scg_md * s, int array_id, const double * host);
+/* as scg_md_upload for the stored rows [row_begin, row_end) only (host still points at row 0; ghost rows are stored
+ * first, so [0, ngstcell) are the ghost rows): march() needs the whole of so0n / so1n / gamma but only the ghost rows
+ * of the arrays it overwrites */
+SCG_API int scg_md_upload_rows(scg_md * s, int array_id, const double * host, int64_t row_begin, int64_t row_end);
 SCG_API int scg_md_download(scg_md * s, int array_id, double * host);
 SCG_API int scg_md_phase(scg_md * s, int phase);
 /* march(steps) = steps x 2 fused substeps, euler_march.cpp:350-359 */

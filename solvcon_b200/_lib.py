@@ -103,6 +103,7 @@ _SIGNATURES = {
     "scg_md_add_bc": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]),
     "scg_md_clear_bc": (C.c_int, [C.c_void_p]),
     "scg_md_upload": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "scg_md_upload_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int64]),
     "scg_md_download": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "scg_md_phase": (C.c_int, [C.c_void_p, C.c_int]),
     "scg_md_march": (C.c_int, [C.c_void_p, C.c_int64]),

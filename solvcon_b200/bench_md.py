@@ -193,11 +193,15 @@ class MD3DWorkload:
             self.dev.march(self.chunk)
 
     def e2e_bytes(self):
-        T = self.ncell + self.info["ngstcell"]
+        # EulerCore.march with host arrays: so0n, so1n, gamma go up in full and the ghost rows of so0c, so1c, cflo,
+        # cflc; every state array but gamma comes back (the distributed arm moves the whole state both ways)
+        T, ng = self.ncell + self.info["ngstcell"], self.info["ngstcell"]
         nd = 3
         neq = nd + 2
         per_row = 8 * (3 * neq + 2 * neq * nd + 3)
-        return T * per_row, T * per_row
+        if self.dist_svr is not None:
+            return T * per_row, T * per_row
+        return 8 * (T * (neq + neq * nd + 1) + ng * (neq + neq * nd + 2)), T * (per_row - 8)
 
     def result_check(self):
         return float(self.dev.so0n.body[:, 0].sum())
@@ -312,11 +316,11 @@ class MD2DWorkload(MD3DWorkload):
                 "decomposition": "none", "mesh": self.info}
 
     def e2e_bytes(self):
-        T = self.ncell + self.info["ngstcell"]
+        T, ng = self.ncell + self.info["ngstcell"], self.info["ngstcell"]
         nd = 2
         neq = nd + 2
         per_row = 8 * (3 * neq + 2 * neq * nd + 3)
-        return T * per_row, T * per_row
+        return 8 * (T * (neq + neq * nd + 1) + ng * (neq + neq * nd + 2)), T * (per_row - 8)
 
     def cpu_run(self, budget_s=15.0):
         return cpu_reference_2d(budget_s)

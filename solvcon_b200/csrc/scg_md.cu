@@ -1554,16 +1554,18 @@ int array_info(scg_md * s, int id, ArrayInfo & a)
     return 0;
 }
 
+// rows [row_begin, row_end) of the stored array (ghost rows first); row_end < 0 = all rows
 template <bool TO_DEVICE>
-int transfer(scg_md * s, int id, double * host)
+int transfer(scg_md * s, int id, double * host, int64_t row_begin = 0, int64_t row_end = -1)
 {
     ArrayInfo a;
     if (int rc = array_info(s, id, a)) { return rc; }
     scg_mesh * m = s->mesh;
-    int64_t const nrows = a.body_only ? m->ncell : m->T;
+    int64_t const all = a.body_only ? m->ncell : m->T;
+    int64_t const nrows = (row_end < 0 || row_end > all) ? all : row_end;
     int64_t const chunk = STAGE_DOUBLES / a.ncomp;
     GroupTable const GT = table_of(s);
-    for (int64_t r0 = 0; r0 < nrows; r0 += chunk)
+    for (int64_t r0 = row_begin < 0 ? 0 : row_begin; r0 < nrows; r0 += chunk)
     {
         int64_t const nr = (nrows - r0 < chunk) ? nrows - r0 : chunk;
         int64_t const cnt = nr * a.ncomp;
@@ -1748,6 +1750,12 @@ int scg_md_upload(scg_md * s, int array_id, const double * host)
 {
     SCG_REQUIRE(s && host, "scg_md_upload: null argument");
     return transfer<true>(s, array_id, const_cast<double *>(host));
+}
+
+int scg_md_upload_rows(scg_md * s, int array_id, const double * host, int64_t row_begin, int64_t row_end)
+{
+    SCG_REQUIRE(s && host, "scg_md_upload_rows: null argument");
+    return transfer<true>(s, array_id, const_cast<double *>(host), row_begin, row_end);
 }
 
 int scg_md_download(scg_md * s, int array_id, double * host)

@@ -243,10 +243,22 @@ class EulerCore:
 
     # -- march (wrap_multidim.cpp:309-327) -----------------------------------------------------------------
     def march(self, steps):
-        self._push()
+        if int(steps) < 1 or self._resident:
+            self._push()
+        else:
+            # march(steps >= 1) reads so0n / so1n (they become so0c / so1c at the first update()) and gamma; every
+            # body row of the other state arrays is overwritten before it is read, and so0t on all rows.  Their
+            # ghost rows are not all rewritten (unregistered ghosts, cflo / cflc), so those still travel.
+            for n in ("so0n", "so1n", "gamma"):
+                if n in self._a:
+                    _lib.check(self._lib.scg_md_upload(self._h, ARRAY_IDS[n], _lib.ptr(self._a[n].ndarray)))
+            for n in ("so0c", "so1c", "cflo", "cflc"):
+                if n in self._a and self._ngst:
+                    _lib.check(self._lib.scg_md_upload_rows(self._h, ARRAY_IDS[n], _lib.ptr(self._a[n].ndarray), 0, self._ngst))
+            self._push(names=())   # the CE geometry, when the caller wrote into it
         if self._lib.scg_md_march(self._h, int(steps)):
             _raise()
-        self._pull()
+        self._pull(tuple(n for n in _STATE if n != "gamma") if int(steps) >= 1 else _STATE)
 
     def march_substep(self):
         self.materialise(("so0c", "so0n", "so1c", "so1n"))

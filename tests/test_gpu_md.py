@@ -328,3 +328,27 @@ def test_gmsh_mesh_marches_like_the_checker(gpu, bridge, name):
         else:
             assert np.abs(a - c).max() / (np.abs(c).max() + 1e-300) < 1e-10, n
     assert np.isfinite(dev.so0n.ndarray).all()
+
+
+def test_march_sees_host_edits_between_calls(gpu, bridge):
+    """Host arrays stay the API-visible storage: edits of so0n / so1n / gamma and of GHOST rows of the
+    other arrays between two march() calls must reach the device -- march() uploads exactly that set."""
+    b = bridge
+    c = Case(b, "mixed3d", order="morton")
+    c.chk.phase(b.MD_BC_SOLN)
+    c.chk.phase(b.MD_BC_DSOLN)
+    c.dev.bc_soln()
+    c.dev.bc_dsoln()
+    c.chk.march(3)
+    c.dev.march(3)
+    for s, get in ((c.chk, c.chk.arr), (c.dev, lambda n: getattr(c.dev, n).ndarray)):
+        ng = c.dev.ngstcell
+        get("so0n")[ng + 5:ng + 9, 0] *= 1.01          # body rows of the newest solution
+        get("so1n")[ng + 2, 1, 0] += 1e-3
+        get("gamma")[ng + 7] = 1.39
+        get("so0c")[0] = 0.123                          # a ghost row of an array march() overwrites in the body
+        get("cflc")[1] = 0.5
+        get("so0t")[ng + 3] = 9.0                       # dead: recomputed by calc_solt
+    c.chk.march(3)
+    c.dev.march(3)
+    c.same("march after host edits", STATE, _strict(gpu))
