@@ -196,3 +196,43 @@ def boundary_groups(ndim, fccnd, fccls, nface, lo, hi, tol=1e-9):
     outlet = bnd[np.abs(xc - hi[0]) < tol]
     wall = bnd[(np.abs(xc - lo[0]) >= tol) & (np.abs(xc - hi[0]) >= tol)]
     return inlet, outlet, wall
+
+
+def pyramid_3d(nx, ny, nz, lx=None, ly=None, lz=None, jitter=0.0):
+    """``nx`` x ``ny`` x ``nz`` boxes, each cut into six pyramids whose apex is the box centre and whose bases are
+    the six box faces (the only conforming all-pyramid lattice; quadrilateral faces are shared between boxes,
+    triangular ones inside a box).  Node order of a pyramid: base 0-3 counter-clockwise seen from the apex, apex 4
+    (``StaticMesh_interior.cpp:261-305``).  With ``jitter`` the lattice nodes are displaced like in ``mixed_3d`` and the
+    centres are the mean of the eight displaced corners, so the quadrilateral faces are not planar.
+    Returns ``(ndcrd[nnode,3], cltpn, clnds)``."""
+    lx = float(nx) if lx is None else lx
+    ly = float(ny) if ly is None else ly
+    lz = float(nz) if lz is None else lz
+    ii, jj, kk = np.meshgrid(np.arange(nx + 1), np.arange(ny + 1), np.arange(nz + 1), indexing="ij")
+    x, y, z = ii * (lx / nx), jj * (ly / ny), kk * (lz / nz)
+    if jitter:
+        inner = (ii > 0) & (ii < nx) & (jj > 0) & (jj < ny) & (kk > 0) & (kk < nz)
+        x = x + np.where(inner, jitter * np.sin(12.9898 * ii + 78.233 * jj + 37.719 * kk), 0.0) * (lx / nx)
+        y = y + np.where(inner, jitter * np.cos(26.651 * ii + 41.347 * jj + 17.113 * kk), 0.0) * (ly / ny)
+        z = z + np.where(inner, jitter * np.sin(9.173 * ii + 53.519 * jj + 61.271 * kk), 0.0) * (lz / nz)
+    nid = (ii * (ny + 1) + jj) * (nz + 1) + kk
+    corners = np.stack([x.ravel(), y.ravel(), z.ravel()], axis=1)
+    bi, bj, bk = (a.ravel() for a in np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij"))
+    c = {(a, b, d): nid[bi + a, bj + b, bk + d] for a in (0, 1) for b in (0, 1) for d in (0, 1)}
+    nbox = len(bi)
+    centre = len(corners) + np.arange(nbox)
+    cxyz = sum(corners[c[k]] for k in c) / 8.0
+    ndcrd = np.concatenate([corners, cxyz], axis=0)
+    # box faces as node loops whose right-hand normal points OUT of the box
+    out = [((0, 0, 0), (0, 1, 0), (1, 1, 0), (1, 0, 0)), ((0, 0, 1), (1, 0, 1), (1, 1, 1), (0, 1, 1)),
+           ((0, 0, 0), (1, 0, 0), (1, 0, 1), (0, 0, 1)), ((0, 1, 0), (0, 1, 1), (1, 1, 1), (1, 1, 0)),
+           ((0, 0, 0), (0, 0, 1), (0, 1, 1), (0, 1, 0)), ((1, 0, 0), (1, 1, 0), (1, 1, 1), (1, 0, 1))]
+    clnds = np.full((6 * nbox, CLMND + 1), -1, dtype=np.int32)
+    for f, (a, b, cc, d) in enumerate(out):
+        rows = slice(f, None, 6)
+        clnds[rows, 0] = 5
+        # the pyramid's own base face is (1, 4, 3, 2) in 1-based local numbering and must point out of the box
+        clnds[rows, 1], clnds[rows, 2], clnds[rows, 3], clnds[rows, 4] = c[a], c[d], c[cc], c[b]
+        clnds[rows, 5] = centre
+    cltpn = np.full(6 * nbox, PYRAMID, dtype=np.int32)
+    return ndcrd, cltpn, clnds

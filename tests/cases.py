@@ -71,6 +71,8 @@ def md_mesh_case(name):
         return (3,) + meshgen.mixed_3d(4, 3, 3, kinds="p", jitter=0.15)
     if name == "mixed3d":
         return (3,) + meshgen.mixed_3d(6, 4, 4, kinds="hpt", jitter=0.15)
+    if name == "pyramid3d":
+        return (3,) + meshgen.pyramid_3d(4, 3, 3, jitter=0.12)
     raise KeyError(name)
 
 

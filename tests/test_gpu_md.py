@@ -7,7 +7,7 @@ from cases import md_bump_ic, md_mesh_case
 
 pytestmark = pytest.mark.gpu
 
-MESHES = ["quad2d", "tri2d", "mixed2d", "step2d", "hex3d", "tet3d", "prism3d", "mixed3d"]
+MESHES = ["quad2d", "tri2d", "mixed2d", "step2d", "hex3d", "tet3d", "prism3d", "mixed3d", "pyramid3d"]
 STATE = ("so0c", "so0n", "so0t", "so1c", "so1n", "cflo", "cflc", "gamma")
 GEOM = ("cevol", "cecnd", "sfcnd", "sfnml")
 
@@ -91,7 +91,7 @@ def test_md_geometry_and_phases(gpu, bridge, name):
     assert np.abs(c.dev.so1n.body).max() > 1e-3
 
 
-@pytest.mark.parametrize("name", ["mixed2d", "step2d", "mixed3d", "hex3d", "tet3d", "prism3d", "tri2d"])
+@pytest.mark.parametrize("name", ["mixed2d", "step2d", "mixed3d", "hex3d", "tet3d", "prism3d", "tri2d", "pyramid3d"])
 @pytest.mark.parametrize("order", ["none", "morton", "rcm"])
 @pytest.mark.parametrize("fused", [3, 2, 1, 0])
 def test_md_march_matches(gpu, bridge, name, order, fused):

@@ -6,7 +6,7 @@ import pytest
 
 from cases import md_mesh_case
 
-MESHES = ["quad2d", "tri2d", "mixed2d", "step2d", "hex3d", "tet3d", "prism3d", "mixed3d"]
+MESHES = ["quad2d", "tri2d", "mixed2d", "step2d", "hex3d", "tet3d", "prism3d", "mixed3d", "pyramid3d"]
 
 
 def _build(ndim, ndcrd, cltpn, clnds, bcs=()):
