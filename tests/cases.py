@@ -71,6 +71,19 @@ def md_mesh_case(name):
         return (3,) + meshgen.mixed_3d(4, 3, 3, kinds="p", jitter=0.15)
     if name == "mixed3d":
         return (3,) + meshgen.mixed_3d(6, 4, 4, kinds="hpt", jitter=0.15)
+    # smallest meshes: every neighbour of every cell is a ghost, groups far smaller than a thread block
+    if name == "one_quad":
+        return (2,) + meshgen.mixed_2d(1, 1, lx=1.0, ly=1.0, tri_every=0)
+    if name == "two_tri":
+        return (2,) + meshgen.mixed_2d(1, 1, lx=1.0, ly=1.0, tri_every=1)
+    if name == "one_hex":
+        return (3,) + meshgen.mixed_3d(1, 1, 1, kinds="h")
+    if name == "six_tet":
+        return (3,) + meshgen.mixed_3d(1, 1, 1, kinds="t")
+    if name == "two_prism":
+        return (3,) + meshgen.mixed_3d(1, 1, 1, kinds="p")
+    if name == "six_pyramid":
+        return (3,) + meshgen.pyramid_3d(1, 1, 1)
     if name == "pyramid3d":
         return (3,) + meshgen.pyramid_3d(4, 3, 3, jitter=0.12)
     raise KeyError(name)
@@ -82,6 +95,7 @@ def md_bump_ic(core_body, clcnd_body, ndim, gamma=1.4, mach=2.0, amp=0.3):
     c = clcnd_body
     ctr = c.mean(axis=0)
     span = c.max(axis=0) - c.min(axis=0)
+    span = np.where(span > 0, span, 1.0)   # one-cell meshes
     r2 = (((c - ctr) / (0.25 * span)) ** 2).sum(axis=1)
     rho = 1.4 * (1.0 + amp * np.exp(-r2))
     p = 1.0 * (1.0 + amp * np.exp(-r2))

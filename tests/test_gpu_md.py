@@ -352,3 +352,21 @@ def test_march_sees_host_edits_between_calls(gpu, bridge):
     c.chk.march(3)
     c.dev.march(3)
     c.same("march after host edits", STATE, _strict(gpu))
+
+
+@pytest.mark.parametrize("name", ["one_quad", "two_tri", "one_hex", "six_tet", "two_prism", "six_pyramid"])
+@pytest.mark.parametrize("fused", [3, 0])
+def test_md_smallest_meshes(gpu, bridge, name, fused):
+    """Edge sizes: one box of every cell type -- all neighbours ghosts, a handful of cells per type group."""
+    b = bridge
+    c = Case(b, name, order="morton")
+    c.dev.set_fused(fused)
+    strict = _strict(gpu)
+    c.same("prepare_ce", GEOM, strict)
+    c.chk.phase(b.MD_BC_SOLN)
+    c.chk.phase(b.MD_BC_DSOLN)
+    c.dev.bc_soln()
+    c.dev.bc_dsoln()
+    c.chk.march(6)
+    c.dev.march(6)
+    c.same(f"march(6) fused={fused}", STATE, strict)
