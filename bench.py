@@ -382,7 +382,7 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("SCG_BENCH_WORKLOAD", "md3d"))
     ap.add_argument("--size", type=int, default=0, help="points / cells per GPU (0 = workload default)")
     ap.add_argument("--chunk", type=int, default=5, help="time steps per march() call (one bench step)")
-    ap.add_argument("--order", default="morton", help="multidim cell ordering: none | morton | rcm")
+    ap.add_argument("--order", default="rcm", help="multidim cell ordering: none | morton | rcm (BASELINE configs[4] compares morton and rcm: on the lattice-generated bench meshes rcm is 4-5 % faster, profiles/README.md)")
     ap.add_argument("--ref-budget", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true")
