@@ -197,6 +197,30 @@ __global__ void __launch_bounds__(256) md_solt_kernel(MdField const F, int32_t r
     for (int e = 0; e < ND + 2; ++e) { F.so0t[e * S + k] = t[e]; }
 }
 
+// calc_solt for a list of rows (device indices): the rows the fused path does not cover -- ghost rows without a
+// boundary condition, halo copies of a partition
+template <int ND>
+__global__ void __launch_bounds__(256) md_solt_rows_kernel(MdField const F, int32_t const * rows, int32_t nrow)
+{
+    int32_t const r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrow) { return; }
+    int64_t const k = rows[r];
+    int64_t const S = F.S;
+    double u[ND + 2], g[ND + 2][ND], t[ND + 2];
+#pragma unroll
+    for (int e = 0; e < ND + 2; ++e)
+    {
+        u[e] = F.so0c[e * S + k];
+#pragma unroll
+        for (int d = 0; d < ND; ++d) { g[e][d] = F.so1c[(e * ND + d) * S + k]; }
+    }
+    Jaco<ND> J;
+    jaco_update<ND>(J, F.gamma[k], u);
+    solt_row<ND>(J, g, t);
+#pragma unroll
+    for (int e = 0; e < ND + 2; ++e) { F.so0t[e * S + k] = t[e]; }
+}
+
 template <int TYPE>
 __global__ void __launch_bounds__(128) md_soln_kernel(MdField const F, MdGeo const G)
 {
@@ -392,7 +416,7 @@ __global__ void __launch_bounds__(SCG_STAGED_TB, StagedCfg<TYPE>::MB) md_solncfl
 #define SCG_EQO_MB_HEX 4
 #endif
 #ifndef SCG_EQO_MB_PRISM
-#define SCG_EQO_MB_PRISM 6
+#define SCG_EQO_MB_PRISM 5
 #endif
 #ifndef SCG_EQO_MB_TET
 #define SCG_EQO_MB_TET 8
@@ -922,6 +946,18 @@ __global__ void __launch_bounds__(128) md_bc_dsoln_kernel(MdField const F, BcDev
 #pragma unroll
         for (int d = 0; d < ND; ++d) { F.so1n[(e * ND + d) * S + jcl] = gj[e][d]; }
     }
+    if (F.fuse_solt)
+    {
+        // fused calc_solt of the next substep for this ghost row: its so0n was set by bc_soln, its so1n just now
+        double u[NEQ], t[NEQ];
+#pragma unroll
+        for (int e = 0; e < NEQ; ++e) { u[e] = F.so0n[e * S + jcl]; }
+        Jaco<ND> J;
+        jaco_update<ND>(J, F.gamma[jcl], u);
+        solt_row<ND>(J, gj, t);
+#pragma unroll
+        for (int e = 0; e < NEQ; ++e) { F.so0t_next[e * S + jcl] = t[e]; }
+    }
 }
 
 // ================================================================================================
@@ -1170,7 +1206,15 @@ struct scg_md
     int ndim = 0, neq = 0;
     double dt = 0, sigma0 = 3.0, taumin = 0.0, tauscale = 1.0; // euler.hpp:184-188
     int cur = 0;                                               // so0[cur] is so0c, so0[1-cur] is so0n
-    DevBuf<double> so0[2], so1[2], so0t, gamma, cflo, cflc, solpt, geo, eraw, stage, red, clvol;
+    DevBuf<double> so0[2], so1[2], so0t[2], gamma, cflo, cflc, solpt, geo, eraw, stage, red, clvol;
+    // fused calc_solt (march mode 3): so0t[tcur] belongs to the current so0c/so1c; while a substep runs, its gradient
+    // kernels fill so0t[1 - tcur] for the next one.  so0t_valid: so0t[1 - tcur] is complete for every covered row
+    // (owned body cells and ghost rows with a boundary condition); solt_rows lists the others.
+    int tcur = 0;
+    bool so0t_valid = false;
+    bool fuse_now = false;
+    DevBuf<int32_t> solt_rows;
+    int32_t nsolt_rows = 0;
     bool have_clvol = false;
     int fused = 3; // 0: one kernel per reference phase, 1: one fused thread-per-cell kernel, 2: soln+cfl kernel + cooperative dsoln kernel,
                    // 3: cp.async-staged soln+cfl kernel + equation-outer dsoln kernel
@@ -1195,7 +1239,9 @@ MdField field_of(scg_md * s)
     F.so0n = s->so0[1 - s->cur].p;
     F.so1c = s->so1[s->cur].p;
     F.so1n = s->so1[1 - s->cur].p;
-    F.so0t = s->so0t.p;
+    F.so0t = s->so0t[s->tcur].p;
+    F.so0t_next = s->so0t[1 - s->tcur].p;
+    F.fuse_solt = s->fuse_now ? 1 : 0;
     F.gamma = s->gamma.p;
     F.cflo = s->cflo.p;
     F.cflc = s->cflc.p;
@@ -1346,6 +1392,17 @@ void launch_solt(scg_md * s)
     count_launch();
 }
 
+void launch_solt_rows(scg_md * s)
+{
+    if (0 == s->nsolt_rows) { return; }
+    MdField const F = field_of(s);
+    unsigned const grid = static_cast<unsigned>(ceil_div(s->nsolt_rows, 256));
+    TimeScope const ts("solt_rows");
+    if (2 == s->ndim) { md_solt_rows_kernel<2><<<grid, 256, 0, stream()>>>(F, s->solt_rows.p, s->nsolt_rows); }
+    else { md_solt_rows_kernel<3><<<grid, 256, 0, stream()>>>(F, s->solt_rows.p, s->nsolt_rows); }
+    count_launch();
+}
+
 int prepare_ce(scg_md * s)
 {
     scg_mesh * m = s->mesh;
@@ -1425,6 +1482,28 @@ int rebuild_bc(scg_md * s)
         SCG_CUDA(cudaMemcpyAsync(s->bc_val.p, val.data(), sizeof(double) * val.size(), cudaMemcpyHostToDevice, stream()));
         SCG_CUDA(cudaStreamSynchronize(stream()));
     }
+    // rows the fused calc_solt does not cover: everything but the owned body cells and the ghost rows written above
+    {
+        std::vector<char> covered(static_cast<size_t>(m->T), 0);
+        for (auto const & g : m->groups)
+        {
+            for (int32_t i = 0; i < g.nact; ++i) { covered[static_cast<size_t>(g.beg) + i] = 1; }
+        }
+        for (int32_t const j : jcl) { covered[static_cast<size_t>(j)] = 1; }
+        std::vector<int32_t> rows;
+        for (int64_t k = 0; k < m->T; ++k)
+        {
+            if (!covered[static_cast<size_t>(k)]) { rows.push_back(static_cast<int32_t>(k)); }
+        }
+        s->nsolt_rows = static_cast<int32_t>(rows.size());
+        if (!rows.empty())
+        {
+            SCG_CUDA(s->solt_rows.alloc(static_cast<int64_t>(rows.size())));
+            SCG_CUDA(cudaMemcpyAsync(s->solt_rows.p, rows.data(), sizeof(int32_t) * rows.size(), cudaMemcpyHostToDevice, stream()));
+            SCG_CUDA(cudaStreamSynchronize(stream()));
+        }
+    }
+    s->so0t_valid = false;
     s->bc_dirty = false;
     return 0;
 }
@@ -1475,6 +1554,24 @@ int launch_bc_dsoln(scg_md * s)
     return 0;
 }
 
+// update() and calc_solt of a mode-3 substep.  When the previous substep was a fused one, so0t of every covered row
+// was already evaluated by its gradient kernels (into the other so0t buffer): flip to it and evaluate only the rows
+// nobody covered.  Otherwise calc_solt runs over all rows.
+int begin_fused_substep(scg_md * s)
+{
+    if (int rc = rebuild_bc(s)) { return rc; } // may invalidate so0t_next (the set of covered rows depends on the BCs)
+    s->cur ^= 1; // update(): swap so0c<->so0n, so1c<->so1n (euler.hpp:123-127)
+    if (s->so0t_valid)
+    {
+        s->tcur ^= 1;
+        launch_solt_rows(s);
+    }
+    else { launch_solt(s); }
+    s->so0t_valid = false;
+    s->fuse_now = true;
+    return 0;
+}
+
 // march_substep in two stages for a partition of a decomposed mesh (always the mode-3 kernels; every mode is
 // bit-identical).  Stage 0: update(), calc_solt on every row, then soln+cfl+dsoln of the INTERFACE cells -- after
 // it their so0n/so1n are final and can be packed and sent.  Stage 1: the interior cells and the boundary kernels.
@@ -1484,8 +1581,7 @@ int substep_split(scg_md * s, int stage)
 {
     if (0 == stage)
     {
-        s->cur ^= 1;
-        launch_solt(s);
+        if (int rc = begin_fused_substep(s)) { return rc; }
         launch_cell_phase(s, CP_SOLNCFL_STAGED, 1);
         launch_cell_phase(s, CP_DSOLN_EQO, 1);
         return 0;
@@ -1493,19 +1589,34 @@ int substep_split(scg_md * s, int stage)
     launch_cell_phase(s, CP_SOLNCFL_STAGED, 2);
     if (int rc = launch_bc_soln(s, true)) { return rc; }
     launch_cell_phase(s, CP_DSOLN_EQO, 2);
-    return launch_bc_dsoln(s);
+    int const rc = launch_bc_dsoln(s);
+    s->fuse_now = false;
+    s->so0t_valid = (0 == rc);
+    return rc;
 }
 
 // march_substep, euler_march.cpp:339-348
 int substep(scg_md * s)
 {
+    if (3 == s->fused)
+    {
+        if (int rc = begin_fused_substep(s)) { return rc; }
+        launch_cell_phase(s, CP_SOLNCFL_STAGED);
+        if (int rc = launch_bc_soln(s, true)) { return rc; }
+        launch_cell_phase(s, CP_DSOLN_EQO);
+        int const rc = launch_bc_dsoln(s);
+        s->fuse_now = false;
+        s->so0t_valid = (0 == rc);
+        return rc;
+    }
+    s->so0t_valid = false;
     s->cur ^= 1; // update(): swap so0c<->so0n, so1c<->so1n (euler.hpp:123-127)
     launch_solt(s);
-    if (2 == s->fused || 3 == s->fused)
+    if (2 == s->fused)
     {
-        launch_cell_phase(s, 3 == s->fused ? CP_SOLNCFL_STAGED : CP_SOLNCFL);
+        launch_cell_phase(s, CP_SOLNCFL);
         if (int rc = launch_bc_soln(s, true)) { return rc; }
-        launch_cell_phase(s, 3 == s->fused ? CP_DSOLN_EQO : CP_DSOLN_COOP);
+        launch_cell_phase(s, CP_DSOLN_COOP);
     }
     else if (1 == s->fused)
     {
@@ -1543,7 +1654,7 @@ int array_info(scg_md * s, int id, ArrayInfo & a)
     case SCG_A_SFNML: a = {CLMFC * FCMND * nd, true, true, nullptr}; break;
     case SCG_A_SO0C: a = {neq, false, false, s->so0[s->cur].p}; break;
     case SCG_A_SO0N: a = {neq, false, false, s->so0[1 - s->cur].p}; break;
-    case SCG_A_SO0T: a = {neq, false, false, s->so0t.p}; break;
+    case SCG_A_SO0T: a = {neq, false, false, s->so0t[s->tcur].p}; break;
     case SCG_A_SO1C: a = {neq * nd, false, false, s->so1[s->cur].p}; break;
     case SCG_A_SO1N: a = {neq * nd, false, false, s->so1[1 - s->cur].p}; break;
     case SCG_A_CFLO: a = {1, false, false, s->cflo.p}; break;
@@ -1617,7 +1728,8 @@ int scg_md_create(scg_md ** out, scg_mesh * mesh, double time_increment)
         z(s->so0[q], S * neq);
         z(s->so1[q], S * neq * nd);
     }
-    z(s->so0t, S * neq);
+    z(s->so0t[0], S * neq);
+    z(s->so0t[1], S * neq);
     z(s->gamma, S);
     z(s->cflo, S);
     z(s->cflc, S);
@@ -1680,6 +1792,7 @@ int scg_md_set_fused(scg_md * s, int fused)
     SCG_REQUIRE(s, "scg_md_set_fused: null solver");
     SCG_REQUIRE(fused >= 0 && fused <= 3, "scg_md_set_fused: mode must be 0, 1, 2 or 3");
     s->fused = fused;
+    s->so0t_valid = false;
     return 0;
 }
 
@@ -1693,6 +1806,7 @@ int scg_md_init_solution(scg_md * s, double gamma, double rho, const double * v,
     double vsq = 0.0;
     for (int d = 0; d < s->ndim; ++d) { vsq += v[d] * v[d]; }
     double const energy = p / (gamma - 1.0) + 0.5 * rho * vsq;
+    s->so0t_valid = false;
     double u[5] = {0, 0, 0, 0, 0};
     u[0] = rho;
     for (int d = 0; d < s->ndim; ++d) { u[1 + d] = rho * v[d]; }
@@ -1749,12 +1863,14 @@ int scg_md_clear_bc(scg_md * s)
 int scg_md_upload(scg_md * s, int array_id, const double * host)
 {
     SCG_REQUIRE(s && host, "scg_md_upload: null argument");
+    s->so0t_valid = false;
     return transfer<true>(s, array_id, const_cast<double *>(host));
 }
 
 int scg_md_upload_rows(scg_md * s, int array_id, const double * host, int64_t row_begin, int64_t row_end)
 {
     SCG_REQUIRE(s && host, "scg_md_upload_rows: null argument");
+    s->so0t_valid = false;
     return transfer<true>(s, array_id, const_cast<double *>(host), row_begin, row_end);
 }
 
@@ -1767,6 +1883,11 @@ int scg_md_download(scg_md * s, int array_id, double * host)
 int scg_md_phase(scg_md * s, int phase)
 {
     SCG_REQUIRE(s, "scg_md_phase: null solver");
+    if (phase != SCG_MD_SUBSTEP && phase != SCG_MD_SUBSTEP_IFACE && phase != SCG_MD_SUBSTEP_REST)
+    {
+        s->so0t_valid = false; // a fine-grained phase changes the state behind the fused calc_solt's back
+        s->fuse_now = false;
+    }
     switch (phase)
     {
     case SCG_MD_UPDATE: s->cur ^= 1; break;

@@ -29,6 +29,7 @@ struct MdField // by value to every kernel
     double * so0c;
     double * so0n;
     double * so0t;
+    double * so0t_next; // fused calc_solt: so0t of the NEXT substep, written by the dsoln / bc_dsoln kernels
     double * so1c;
     double * so1n;
     double * gamma;
@@ -39,6 +40,7 @@ struct MdField // by value to every kernel
     int32_t ncell;
     int32_t T;
     double dt, sigma0, taumin, tauscale;
+    int fuse_solt; // 1: the gradient kernels also evaluate calc_solt for the rows they finish
 };
 
 struct MdGeo // one cell-type group
@@ -1212,7 +1214,12 @@ struct DsolnEqo
     static constexpr int ND = ct_ndim(TYPE);
     static constexpr int NFGE = ct_nfge(TYPE);
     static constexpr int RPF = ND * ND + 1; // rows per gradient element: adj, det
-    static constexpr int ROWS = NFGE * RPF;
+    // the cell's new gradient so1n[NEQ][ND] for the fused calc_solt: parked in shared memory in 2D (8 rows, 5 % faster
+    // than reading it back); in 3D 15 more rows per thread would shrink L1 by as much and the gathers of the
+    // equation loop live on L1 (tetrahedra: 318 -> 452 us), so there it is read back from L2
+    static constexpr bool G_IN_SMEM = (2 == ND);
+    static constexpr int R_G = NFGE * RPF;
+    static constexpr int ROWS = R_G + (G_IN_SMEM ? (ND + 2) * ND : 0);
     static constexpr int BYTES = ROWS * TB * int(sizeof(double));
 };
 
@@ -1533,7 +1540,34 @@ __device__ __forceinline__ void cell_dsoln_eqo(MdField const & F, MdGeo const & 
             for (int d = 0; d < ND; ++d) { o[d] += wgt * grad[isub][d]; }
         }
 #pragma unroll
-        for (int d = 0; d < ND; ++d) { F.so1n[(e * ND + d) * S + k] = o[d]; }
+        for (int d = 0; d < ND; ++d)
+        {
+            F.so1n[(e * ND + d) * S + k] = o[d];
+            if (DsolnEqo<TYPE, TB>::G_IN_SMEM) { sadj[(DsolnEqo<TYPE, TB>::R_G + e * ND + d) * TB] = o[d]; }
+        }
+    }
+    // ---- fused calc_solt of the NEXT substep (euler_march.cpp:161-191): this cell's so0n and so1n are final, and
+    //      after update() they are its so0c and so1c (see DsolnEqo::G_IN_SMEM for where the gradient comes from)
+    if (F.fuse_solt)
+    {
+        if (DsolnEqo<TYPE, TB>::G_IN_SMEM) { asm volatile("" ::: "memory"); }
+        double u[NEQ], g[NEQ][ND], t[NEQ];
+#pragma unroll
+        for (int e = 0; e < NEQ; ++e)
+        {
+            u[e] = F.so0n[e * S + k];
+#pragma unroll
+            for (int d = 0; d < ND; ++d)
+            {
+                g[e][d] = DsolnEqo<TYPE, TB>::G_IN_SMEM ? sadj[(DsolnEqo<TYPE, TB>::R_G + e * ND + d) * TB]
+                                                        : __ldcg(&F.so1n[(e * ND + d) * S + k]);
+            }
+        }
+        Jaco<ND> J;
+        jaco_update<ND>(J, F.gamma[k], u);
+        solt_row<ND>(J, g, t);
+#pragma unroll
+        for (int e = 0; e < NEQ; ++e) { F.so0t_next[e * S + k] = t[e]; }
     }
 }
 
