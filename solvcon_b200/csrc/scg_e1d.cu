@@ -15,6 +15,7 @@
 // 31 targets, adjacent warps overlap by one source.  so0, cfl and so1 of a half step are produced
 // by one launch, the NRBC copies (treat_boundary_*) ride on the first half step of march_alpha.
 #include "scg_common.cuh"
+#include "scg_fastmath.cuh"
 
 #include <cfloat>
 #include <vector>
@@ -55,6 +56,97 @@ __device__ __forceinline__ double pow_alpha(double v)
     return v * v;
 }
 
+// Everything a source solution element contributes (Euler1DKernel::derive, Euler1DCore.hpp:210-244, and
+// update_cfl at the source point, Euler1DCore.cpp:70-94).  FAST: the ten Jacobian / flux quotients share three
+// refined reciprocals (u0 + tiny, u0^2 + tiny, u0^3 + tiny), the CFL part three more, the two square roots run the
+// inlined IEEE sequence, and every range test lands in one flag -- one basic block instead of 16 slow-path branches;
+// the caller redoes the element with the plain operators when the flag is false (scg_fastmath.cuh).
+struct E1dElem
+{
+    double f1, f2, ut0, ut1, ut2, ft0, ft1, ft2, cfl;
+};
+
+template <bool FAST, bool WITH_CFL>
+__device__ __forceinline__ bool e1d_derive(double ga, double u0, double u1, double u2, double ux0, double ux1, double ux2,
+                                           double hdt, double dmin, E1dElem & o)
+{
+    double const tiny = E1D_TINY;
+    DivBy<FAST> by_a(u0 + tiny);
+    DivBy<FAST> by_b(u0 * u0 + tiny);
+    DivBy<FAST> by_c(u0 * u0 * u0 + tiny);
+    double const j00 = 0.0, j01 = 1.0, j02 = 0.0;
+    double const j10 = by_b((ga - 3.0) / 2.0 * u1 * u1);
+    double const j11 = by_a(-(ga - 3.0) * u1);
+    double const j12 = ga - 1.0;
+    double const j20 = by_c((ga - 1.0) * u1 * u1 * u1) - by_b(ga * u1 * u2);
+    double const j21 = by_a(ga * u2) - by_b(3.0 / 2.0 * (ga - 1.0) * u1 * u1);
+    double const j22 = by_a(ga * u1);
+
+    o.f1 = (ga - 1.0) * u2 + by_a((3.0 - ga) / 2.0 * u1 * u1);
+    o.f2 = by_a(ga * u1 * u2) - by_b((ga - 1.0) / 2.0 * u1 * u1 * u1);
+
+    o.ut0 = -j00 * ux0 - j01 * ux1 - j02 * ux2;
+    o.ut1 = -j10 * ux0 - j11 * ux1 - j12 * ux2;
+    o.ut2 = -j20 * ux0 - j21 * ux1 - j22 * ux2;
+
+    o.ft0 = j00 * o.ut0 + j01 * o.ut1 + j02 * o.ut2;
+    o.ft1 = j10 * o.ut0 + j11 * o.ut1 + j12 * o.ut2;
+    o.ft2 = j20 * o.ut0 + j21 * o.ut1 + j22 * o.ut2;
+    bool ok = by_a.ok && by_b.ok && by_c.ok;
+    if (WITH_CFL)
+    {
+        DivBy<FAST> by_2u0(2.0 * u0);
+        DivBy<FAST> by_u0(u0);
+        DivBy<FAST> by_dmin(dmin);
+        double wspd = u1;
+        wspd *= wspd;
+        double const ke = by_2u0(wspd);
+        double pr = (ga - 1.0) * (u2 - ke);
+        pr = (pr + fabs(pr)) / 2.0;
+        double const c2 = by_u0(ga * pr);
+        double const s1 = FAST ? sqrt_fast_z(c2, ok) : sqrt(c2);
+        double const s2 = FAST ? sqrt_fast_z(wspd, ok) : sqrt(wspd);
+        wspd = s1 + by_u0(s2);
+        o.cfl = by_dmin(hdt * wspd);
+        ok = ok && by_2u0.ok && by_u0.ok && by_dmin.ok;
+    }
+    return ok;
+}
+
+// march_half_so0's flux balance (Euler1DCore.cpp:117-128) and march_half_so1_alpha (Euler1DCore.hpp:306-318) of one
+// target; n[] holds so0 of the target on exit (and on entry when DO_SO0 is false)
+template <int ALPHA, bool FAST, bool DO_SO0, bool DO_SO1>
+__device__ __forceinline__ bool e1d_target(double const (&bal)[3], double dx, double dn, double dp, double const (&upn)[3],
+                                           double const (&upp)[3], double (&n)[3], double (&g)[3])
+{
+    bool ok = true;
+    if (DO_SO0)
+    {
+        DivBy<FAST> by_dx(dx);
+#pragma unroll
+        for (int iv = 0; iv < 3; ++iv) { n[iv] = by_dx(bal[iv]); }
+        ok = ok && by_dx.ok;
+    }
+    if (DO_SO1)
+    {
+        DivBy<FAST> by_dn(dn);
+        DivBy<FAST> by_dp(dp);
+#pragma unroll
+        for (int iv = 0; iv < 3; ++iv)
+        {
+            double const duxn = by_dn(n[iv] - upn[iv]);
+            double const duxp = by_dp(upp[iv] - n[iv]);
+            double const fan = pow_alpha<ALPHA>(fabs(duxn));
+            double const fap = pow_alpha<ALPHA>(fabs(duxp));
+            DivBy<FAST> by_w(fap + fan + E1D_TINY);
+            g[iv] = by_w(fap * duxn + fan * duxp);
+            ok = ok && by_w.ok;
+        }
+        ok = ok && by_dn.ok && by_dp.ok;
+    }
+    return ok;
+}
+
 // S: source plane, T = 1-S.  Source s of plane S has xneg = xT[s+b], xpos = xT[s+b+1] and the target
 // between sources s and s+1 is t = s+b+1, with b = -1 for S = even and b = 0 for S = odd.
 // Sources run over [sbeg, slast]; targets over t(sbeg) .. t(slast-1); cfl over sources [sbeg, slast-1]
@@ -82,45 +174,25 @@ __global__ void __launch_bounds__(256) e1d_half_kernel(EPlane const ps, EPlane c
     double const u0 = ps.u[0][s], u1 = ps.u[1][s], u2 = ps.u[2][s];
     double const ux0 = ps.g[0][s], ux1 = ps.g[1][s], ux2 = ps.g[2][s];
 
-    // ---- Euler1DKernel::derive, Euler1DCore.hpp:210-244 (expression order kept)
-    double const tiny = E1D_TINY;
-    double const j00 = 0.0, j01 = 1.0, j02 = 0.0;
-    double const j10 = (ga - 3.0) / 2.0 * u1 * u1 / (u0 * u0 + tiny);
-    double const j11 = -(ga - 3.0) * u1 / (u0 + tiny);
-    double const j12 = ga - 1.0;
-    double const j20 = (ga - 1.0) * u1 * u1 * u1 / (u0 * u0 * u0 + tiny) - ga * u1 * u2 / (u0 * u0 + tiny);
-    double const j21 = ga * u2 / (u0 + tiny) - 3.0 / 2.0 * (ga - 1.0) * u1 * u1 / (u0 * u0 + tiny);
-    double const j22 = ga * u1 / (u0 + tiny);
-
-    double const f0 = u1;
-    double const f1 = (ga - 1.0) * u2 + (3.0 - ga) / 2.0 * u1 * u1 / (u0 + tiny);
-    double const f2 = ga * u1 * u2 / (u0 + tiny) - (ga - 1.0) / 2.0 * u1 * u1 * u1 / (u0 * u0 + tiny);
-
-    double const ut0 = -j00 * ux0 - j01 * ux1 - j02 * ux2;
-    double const ut1 = -j10 * ux0 - j11 * ux1 - j12 * ux2;
-    double const ut2 = -j20 * ux0 - j21 * ux1 - j22 * ux2;
-
-    double const ft0 = j00 * ut0 + j01 * ut1 + j02 * ut2;
-    double const ft1 = j10 * ut0 + j11 * ut1 + j12 * ut2;
-    double const ft2 = j20 * ut0 + j21 * ut1 + j22 * ut2;
+    // ---- derive + update_cfl of the source (expression order kept)
+    constexpr bool WITH_CFL = 0 != (FLAGS & F_CFL);
+    double const dxpos = xpos - x;
+    double const dxneg = x - xneg;
+    double const dmin = dxpos < dxneg ? dxpos : dxneg;
+    E1dElem el;
+    if (!e1d_derive<true, WITH_CFL>(ga, u0, u1, u2, ux0, ux1, ux2, hdt, dmin, el))
+    {
+        e1d_derive<false, WITH_CFL>(ga, u0, u1, u2, ux0, ux1, ux2, hdt, dmin, el);
+    }
+    double const f0 = u1, f1 = el.f1, f2 = el.f2;
+    double const ut0 = el.ut0, ut1 = el.ut1, ut2 = el.ut2;
+    double const ft0 = el.ft0, ft1 = el.ft1, ft2 = el.ft2;
 
     double const up0 = u0 + (x - xctr) * ux0 + hdt * ut0;
     double const up1 = u1 + (x - xctr) * ux1 + hdt * ut1;
     double const up2 = u2 + (x - xctr) * ux2 + hdt * ut2;
 
-    // ---- update_cfl at the source point, Euler1DCore.cpp:70-94
-    if ((FLAGS & F_CFL) && live && lane < 31 && s < slast)
-    {
-        double wspd = u1;
-        wspd *= wspd;
-        double const ke = wspd / (2.0 * u0);
-        double pr = (ga - 1.0) * (u2 - ke);
-        pr = (pr + fabs(pr)) / 2.0;
-        wspd = sqrt(ga * pr / u0) + sqrt(wspd) / u0;
-        double const dxpos = xpos - x;
-        double const dxneg = x - xneg;
-        ps.cfl[s] = hdt * wspd / (dxpos < dxneg ? dxpos : dxneg);
-    }
+    if (WITH_CFL && live && lane < 31 && s < slast) { ps.cfl[s] = el.cfl; }
 
     // ---- NRBC copies riding on the even->odd half step (treat_boundary_so0/so1, Euler1DCore.cpp:132-172):
     // so[1] <- so[2] is odd slot 0 <- even slot 1, so[N-2] <- so[N-3] is odd slot slast <- even slot slast.
@@ -165,48 +237,54 @@ __global__ void __launch_bounds__(256) e1d_half_kernel(EPlane const ps, EPlane c
     if (lane == 31 || s_raw >= slast) { return; } // no target to the right of this source here
     int64_t const t = s + b + 1;
 
-    double n0, n1, n2;
-    if (FLAGS & F_SO0)
+    constexpr bool DO_SO0 = 0 != (FLAGS & F_SO0);
+    constexpr bool DO_SO1 = 0 != (FLAGS & F_SO1);
+    double bal[3] = {0.0, 0.0, 0.0}, n[3], g[3];
+    if (DO_SO0)
     {
-        // calc_flux_ll of this source (LEFT element), Euler1DCore.hpp:246-255, and
-        // march_half_so0's flux balance, Euler1DCore.cpp:117-128
+        // calc_flux_ll of this source (LEFT element), Euler1DCore.hpp:246-255, and the flux balance
         double const deltax = xpos - x;
         double const dxmid = 0.5 * (x + xpos) - xctr;
         double const ll0 = deltax * (u0 + dxmid * ux0) + hdt * (f0 - (dxctr * ut0) + (qdt * ft0));
         double const ll1 = deltax * (u1 + dxmid * ux1) + hdt * (f1 - (dxctr * ut1) + (qdt * ft1));
         double const ll2 = deltax * (u2 + dxmid * ux2) + hdt * (f2 - (dxctr * ut2) + (qdt * ft2));
-        double const dx = r_x - x;
-        n0 = (ll0 + r_lr0) / dx;
-        n1 = (ll1 + r_lr1) / dx;
-        n2 = (ll2 + r_lr2) / dx;
-        pt.u[0][t] = n0;
-        pt.u[1][t] = n1;
-        pt.u[2][t] = n2;
+        bal[0] = ll0 + r_lr0;
+        bal[1] = ll1 + r_lr1;
+        bal[2] = ll2 + r_lr2;
     }
     else
     {
-        n0 = pt.u[0][t];
-        n1 = pt.u[1][t];
-        n2 = pt.u[2][t];
+        n[0] = pt.u[0][t];
+        n[1] = pt.u[1][t];
+        n[2] = pt.u[2][t];
     }
-    if (FLAGS & F_SO1)
+    // kernxn = this source, kernxp = lane+1; kernxp.xneg is this source's xpos (the target point itself)
+    double const upn[3] = {up0, up1, up2};
+    double const upp[3] = {r_up0, r_up1, r_up2};
+    double const dx = r_x - x;
+    double const dn = xpos - x;
+    double const dp = r_x - xpos;
+    if (!e1d_target<ALPHA, true, DO_SO0, DO_SO1>(bal, dx, dn, dp, upn, upp, n, g))
     {
-        // march_half_so1_alpha, Euler1DCore.hpp:306-318: kernxn = this source, kernxp = lane+1;
-        // kernxp.xneg is this source's xpos (the target point itself).
-        double const dn = xpos - x;
-        double const dp = r_x - xpos;
-#define SCG_E1D_SO1(IV, UTP, UPN, UPP)                                            \
-        {                                                                          \
-            double const duxn = ((UTP) - (UPN)) / dn;                              \
-            double const duxp = ((UPP) - (UTP)) / dp;                              \
-            double const fan = pow_alpha<ALPHA>(fabs(duxn));                       \
-            double const fap = pow_alpha<ALPHA>(fabs(duxp));                       \
-            pt.g[IV][t] = (fap * duxn + fan * duxp) / (fap + fan + E1D_TINY);      \
+        if (!DO_SO0)
+        {
+            n[0] = pt.u[0][t];
+            n[1] = pt.u[1][t];
+            n[2] = pt.u[2][t];
         }
-        SCG_E1D_SO1(0, n0, up0, r_up0)
-        SCG_E1D_SO1(1, n1, up1, r_up1)
-        SCG_E1D_SO1(2, n2, up2, r_up2)
-#undef SCG_E1D_SO1
+        e1d_target<ALPHA, false, DO_SO0, DO_SO1>(bal, dx, dn, dp, upn, upp, n, g);
+    }
+    if (DO_SO0)
+    {
+        pt.u[0][t] = n[0];
+        pt.u[1][t] = n[1];
+        pt.u[2][t] = n[2];
+    }
+    if (DO_SO1)
+    {
+        pt.g[0][t] = g[0];
+        pt.g[1][t] = g[1];
+        pt.g[2][t] = g[2];
     }
 }
 

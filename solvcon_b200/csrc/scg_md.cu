@@ -354,16 +354,17 @@ __global__ void __launch_bounds__(128, SCG_SOLN_MINBLOCKS) md_solncfl_kernel(MdF
 #ifndef SCG_STAGED_TB
 #define SCG_STAGED_TB 128
 #endif
-// resident CTAs per SM the register budget is sized for: the 3D flux evaluation wants ~250 registers (two
-// CTAs); tetrahedra and the 2D types get by with 168 (three CTAs)
+// threads per CTA and resident CTAs per SM the register budget is sized for: the 3D flux evaluation wants ~250
+// registers (8 warps per SM; 64-thread CTAs are 3 % faster than 128-thread ones at the same 8 warps), tetrahedra
+// run at 204 (10 warps), the 2D types at 128 (16 warps of 128-thread CTAs)
 #ifndef SCG_STAGED_MB_HEX
-#define SCG_STAGED_MB_HEX 2
+#define SCG_STAGED_MB_HEX 4
 #endif
 #ifndef SCG_STAGED_MB_PRISM
-#define SCG_STAGED_MB_PRISM 2
+#define SCG_STAGED_MB_PRISM 4
 #endif
 #ifndef SCG_STAGED_MB_TET
-#define SCG_STAGED_MB_TET 3
+#define SCG_STAGED_MB_TET 5
 #endif
 #ifndef SCG_STAGED_MB_QUAD
 #define SCG_STAGED_MB_QUAD 4
@@ -371,28 +372,40 @@ __global__ void __launch_bounds__(128, SCG_SOLN_MINBLOCKS) md_solncfl_kernel(MdF
 #ifndef SCG_STAGED_MB_TRI
 #define SCG_STAGED_MB_TRI 4
 #endif
+#ifndef SCG_STAGED_TB_HEX
+#define SCG_STAGED_TB_HEX 64
+#endif
+#ifndef SCG_STAGED_TB_PRISM
+#define SCG_STAGED_TB_PRISM 64
+#endif
+#ifndef SCG_STAGED_TB_TET
+#define SCG_STAGED_TB_TET 64
+#endif
 template <int TYPE>
 struct StagedCfg
 {
+    static constexpr int TB = (TYPE == CT_HEX) ? SCG_STAGED_TB_HEX
+                            : (TYPE == CT_PRISM || TYPE == CT_PYRAMID) ? SCG_STAGED_TB_PRISM
+                            : (TYPE == CT_TET) ? SCG_STAGED_TB_TET : SCG_STAGED_TB;
     static constexpr int MB = (TYPE == CT_HEX) ? SCG_STAGED_MB_HEX
                             : (TYPE == CT_PRISM || TYPE == CT_PYRAMID) ? SCG_STAGED_MB_PRISM
                             : (TYPE == CT_TET) ? SCG_STAGED_MB_TET
                             : (TYPE == CT_QUAD) ? SCG_STAGED_MB_QUAD : SCG_STAGED_MB_TRI;
 };
 template <int TYPE>
-__global__ void __launch_bounds__(SCG_STAGED_TB, StagedCfg<TYPE>::MB) md_solncfl_staged_kernel(MdField const F, MdGeo const G, double * eraw)
+__global__ void __launch_bounds__(StagedCfg<TYPE>::TB, StagedCfg<TYPE>::MB) md_solncfl_staged_kernel(MdField const F, MdGeo const G, double * eraw)
 {
     constexpr int ND = ct_ndim(TYPE);
     constexpr int NEQ = ND + 2;
     constexpr int NFC = ct_nfc(TYPE);
     extern __shared__ double stage_smem[];
-    int32_t const i = G.ibeg + blockIdx.x * SCG_STAGED_TB + threadIdx.x;
+    int32_t const i = G.ibeg + blockIdx.x * StagedCfg<TYPE>::TB + threadIdx.x;
     if (i >= G.iend) { return; }
     int64_t const k = G.beg + i;
     double un[NEQ];
     double dist;
     int32_t jmax;
-    cell_soln_staged<TYPE, SCG_STAGED_TB>(F, G, i, stage_smem + threadIdx.x, un, dist, jmax);
+    cell_soln_staged<TYPE, StagedCfg<TYPE>::TB>(F, G, i, stage_smem + threadIdx.x, un, dist, jmax);
     if (jmax >= F.ncell)
     {
 #pragma unroll
@@ -1332,14 +1345,15 @@ void launch_cell_phase_t(scg_md * s, MeshGroup const & g, CellPhase ph, int part
     case CP_SOLNCFL: md_solncfl_kernel<TYPE><<<grid, 128, 0, stream()>>>(F, G, s->eraw.p); break;
     case CP_SOLNCFL_STAGED:
     {
-        constexpr int BYTES = SolnStage<TYPE, SCG_STAGED_TB>::BYTES;
+        constexpr int TBS = StagedCfg<TYPE>::TB;
+        constexpr int BYTES = SolnStage<TYPE, TBS>::BYTES;
         static bool attr_set = false;
         if (!attr_set)
         {
             cudaFuncSetAttribute(md_solncfl_staged_kernel<TYPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, BYTES);
             attr_set = true;
         }
-        md_solncfl_staged_kernel<TYPE><<<static_cast<unsigned>(ceil_div(ncl, SCG_STAGED_TB)), SCG_STAGED_TB, BYTES, stream()>>>(F, G, s->eraw.p);
+        md_solncfl_staged_kernel<TYPE><<<static_cast<unsigned>(ceil_div(ncl, TBS)), TBS, BYTES, stream()>>>(F, G, s->eraw.p);
         break;
     }
     case CP_DSOLN_EQO:

@@ -14,6 +14,7 @@
 //     not once per gradient element that uses the face.
 #pragma once
 
+#include "scg_fastmath.cuh"
 #include "scg_md.cuh"
 
 #include <cfloat>
@@ -59,76 +60,6 @@ struct MdGeo // one cell-type group
 // L1 / L2 prefetch of one address per lane (no register is tied up while the line is in flight)
 __device__ __forceinline__ void prefetch_l1(void const * p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l2(void const * p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
-// ------------------------------------------------------------------------------------------------
-// IEEE division with a shared reciprocal.
-//
-// The march divides many numerators by the same denominator (9 per Jacobian, 15 per gradient element).
-// ptxas expands every `a / b` into: seed = MUFU.RCP64H(hi(b)) with low word 1, two Newton steps (5 DFMA),
-// then q0 = a*y, r = fma(-b, q0, a), q = fma(y, r, q0), a range test on hi(a) and hi(q), and a call to a
-// slow path when the test fails.  DivBy<true> runs EXACTLY that sequence (checked against the SASS of
-// `div.rn.f64` for sm_100a and, bit for bit, by scg_selftest_div) but refines the reciprocal once per
-// denominator, so each further quotient costs 3 fp64 instructions instead of 9.  `ok` records the range
-// test; when it fails the caller recomputes with DivBy<false>, i.e. the plain operator.
-// ------------------------------------------------------------------------------------------------
-template <bool FAST>
-struct DivBy
-{
-    double b;
-    double y;
-    int bhi;
-    bool ok;
-    bool bsane; // b is normal and 2^-900 < |b| < 2^900: the refined reciprocal is finite and normal
-    __device__ __forceinline__ explicit DivBy(double denom)
-        : b(denom)
-        , y(0.0)
-        , bhi(0)
-        , ok(true)
-        , bsane(false)
-    {
-        if (FAST)
-        {
-            bhi = __double2hiint(denom);
-            bsane = (((static_cast<unsigned>(bhi) >> 20) & 0x7ffu) - 124u) < 1800u;
-            double y0;
-            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(denom));
-            y0 = __hiloint2double(__double2hiint(y0), 1);
-            double e = __fma_rn(-denom, y0, 1.0);
-            e = __fma_rn(e, e, e);
-            double const y1 = __fma_rn(y0, e, y0);
-            double const e2 = __fma_rn(-denom, y1, 1.0);
-            y = __fma_rn(y1, e2, y1);
-        }
-    }
-    // ZMODE 0: a zero numerator fails the range test like in ptxas's own expansion.
-    // ZMODE 1: +-0 over a sane denominator passes and returns the IEEE result (a zero with the sign of a*b).
-    //          Uniform regions of a flow are full of exact zeros (transverse momentum, gradients); without this
-    //          every one of them would drop to the plain operator AND its slow path.
-    // ZMODE 2: as 1 but the sign of the returned zero is unspecified -- for callers that provably do not depend
-    //          on it (saves the select).
-    template <int ZMODE>
-    __device__ __forceinline__ double quot(double a)
-    {
-        if (!FAST) { return a / b; }
-        double const q0 = __dmul_rn(a, y);
-        double const r = __fma_rn(-b, q0, a);
-        double const q = __fma_rn(y, r, q0);
-        int const ahi = __double2hiint(a);
-        float const ah = __int_as_float(ahi);
-        float const t = __fmaf_rn(0.0f, __int_as_float(bhi), __int_as_float(__double2hiint(q)));
-        bool const in_range = !(fabsf(ah) < 6.5827683646048100446e-37f) && (fabsf(t) > 1.469367938527859385e-39f);
-        if (0 == ZMODE)
-        {
-            ok = ok && in_range;
-            return q;
-        }
-        bool const a_zero = 0 == ((ahi & 0x7fffffff) | __double2loint(a));
-        ok = ok && (a_zero ? bsane : in_range);
-        if (2 == ZMODE) { return q; } // q is +-0 here when a is: y is finite
-        return a_zero ? __hiloint2double((ahi ^ bhi) & static_cast<int>(0x80000000u), 0) : q;
-    }
-    __device__ __forceinline__ double operator()(double a) { return quot<1>(a); }
-};
 
 // zero-numerator mode of the gradient quotients in eqo_solve: the sign of a zero gradient cannot reach so1n
 // (grad*grad is +0 either way; o[d] starts at +0 and +0 + (+-0) is +0, x + (+-0) is x)
@@ -1222,50 +1153,6 @@ struct DsolnEqo
     static constexpr int ROWS = R_G + (G_IN_SMEM ? (ND + 2) * ND : 0);
     static constexpr int BYTES = ROWS * TB * int(sizeof(double));
 };
-
-// ------------------------------------------------------------------------------------------------
-// IEEE square root and reciprocal with a deferred range test.
-//
-// ptxas expands sqrt.rn.f64 / rcp.rn.f64 into a MUFU seed, a fixed Newton sequence, a range test on the
-// high word of the argument and a call to a slow path when the test fails -- one basic block boundary per
-// operation, which keeps the scheduler from overlapping independent operations.  sqrt_fast / rcp_fast run
-// EXACTLY the fast sequences (read off the sm_100a SASS, including the odd low words of the seeds; checked
-// bit for bit by scg_selftest_rsq) and only record the test in `ok`; the caller redoes the work with the
-// plain operators when it is false.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double rcp_fast(double x, bool & ok)
-{
-    int const xh = __double2hiint(x);
-    int const lo = xh + 0x300402;
-    double s;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(s) : "d"(x));
-    double const y0 = __hiloint2double(__double2hiint(s), lo);
-    double e = __fma_rn(-x, y0, 1.0);
-    e = __fma_rn(e, e, e);
-    double const y1 = __fma_rn(y0, e, y0);
-    double const e2 = __fma_rn(-x, y1, 1.0);
-    ok = ok && !(fabsf(__int_as_float(lo)) < 5.8789094863358348022e-39f);
-    return __fma_rn(y1, e2, y1);
-}
-
-__device__ __forceinline__ double sqrt_fast(double x, bool & ok)
-{
-    int const xh = __double2hiint(x);
-    unsigned const lo = static_cast<unsigned>(xh) + 0xfcb00000u;
-    double s;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(s) : "d"(x));
-    double const y0 = __hiloint2double(__double2hiint(s), static_cast<int>(lo));
-    double const t = __dmul_rn(y0, y0);
-    double const e = __fma_rn(x, -t, 1.0);
-    double const c = __fma_rn(e, 0.375, 0.5);
-    double const ye = __dmul_rn(y0, e);
-    double const y1 = __fma_rn(c, ye, y0);
-    double const g = __dmul_rn(x, y1);
-    double const h = __hiloint2double(__double2hiint(y1) - 0x100000, __double2loint(y1));
-    double const r = __fma_rn(g, -g, x);
-    ok = ok && (lo < 0x7ca00000u);
-    return __fma_rn(r, h, g);
-}
 
 // The arithmetic of one equation of calc_dsoln after the Taylor differences (euler_gradient.cpp:74-110):
 // the NFGE gradients, their W-1/2 weights normalised and shifted, and sigma_max.  FAST: see above;
