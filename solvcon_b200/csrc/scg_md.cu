@@ -404,8 +404,25 @@ __global__ void __launch_bounds__(StagedCfg<TYPE>::TB, StagedCfg<TYPE>::MB) md_s
     int64_t const k = G.beg + i;
     double un[NEQ];
     double dist;
+    bool dist_ok;
     int32_t jmax;
-    cell_soln_staged<TYPE, StagedCfg<TYPE>::TB>(F, G, i, stage_smem + threadIdx.x, un, dist, jmax);
+    cell_soln_staged<TYPE, StagedCfg<TYPE>::TB>(F, G, i, stage_smem + threadIdx.x, un, dist, dist_ok, jmax);
+    if (!dist_ok)
+    {
+        // a square root of calc_cfl's distance left the fast range: redo the distance with the plain operator
+        dist = DBL_MAX;
+        for (int f = 0; f < NFC; ++f)
+        {
+            double d2 = 0.0;
+            for (int d = 0; d < ND; ++d)
+            {
+                double const diff = G.cecnd[(f * ND + d) * int64_t(G.n) + i] - F.solpt[d * F.S + k];
+                d2 += diff * diff;
+            }
+            double const r = sqrt(d2);
+            dist = (r < dist) ? r : dist;
+        }
+    }
     if (jmax >= F.ncell)
     {
 #pragma unroll

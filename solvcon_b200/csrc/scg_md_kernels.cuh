@@ -585,24 +585,46 @@ __device__ __forceinline__ void cell_cfl(MdField const & F, MdGeo const & G, int
     u[NEQ - 1] = pr_adj / ga1 + ke + MD_TINY;
 }
 
-// The thermodynamic half of calc_cfl (euler_solution.cpp:133-158) once `dist` is known.
-template <int ND>
-__device__ __forceinline__ void cfl_from_dist(double hdt, double ga, double dist, double (&u)[ND + 2], double & cflo, double & cflc)
+// The thermodynamic half of calc_cfl (euler_solution.cpp:133-158) once `dist` is known.  FAST: the six quotients and
+// two square roots run their inlined IEEE sequences with one deferred range flag (scg_fastmath.cuh); returns it.
+template <int ND, bool FAST>
+__device__ __forceinline__ bool cfl_from_dist_impl(double hdt, double ga, double dist, double (&u)[ND + 2], double & cflo, double & cflc)
 {
     constexpr int NEQ = ND + 2;
+    bool ok = true;
     double const ga1 = ga - 1.0;
     double const density = u[0];
     double momsq = 0.0;
 #pragma unroll
     for (int d = 0; d < ND; ++d) { momsq += u[1 + d] * u[1 + d]; }
-    double const ke = momsq / (2.0 * density);
+    DivBy<FAST> by_2rho(2.0 * density);
+    DivBy<FAST> by_rho(density);
+    DivBy<FAST> by_dist(dist);
+    DivBy<FAST> by_ga1(ga1);
+    double const ke = by_2rho(momsq);
     double const energy = u[NEQ - 1];
     double const pr = ga1 * (energy - ke);
     double const pr_adj = (pr + fabs(pr)) / 2.0;
-    double const wspd = sqrt(ga * pr_adj / density) + sqrt(momsq) / density;
-    cflo = hdt * wspd / dist;
-    cflc = (cflo - 1.0) * pr_adj / (pr_adj + MD_TINY) + 1.0;
-    u[NEQ - 1] = pr_adj / ga1 + ke + MD_TINY;
+    DivBy<FAST> by_pr(pr_adj + MD_TINY);
+    double const c2 = by_rho(ga * pr_adj);
+    double const s1 = FAST ? sqrt_fast_z(c2, ok) : sqrt(c2);
+    double const s2 = FAST ? sqrt_fast_z(momsq, ok) : sqrt(momsq);
+    double const wspd = s1 + by_rho(s2);
+    cflo = by_dist(hdt * wspd);
+    cflc = by_pr((cflo - 1.0) * pr_adj) + 1.0;
+    double const e_new = by_ga1(pr_adj) + ke + MD_TINY;
+    ok = ok && by_2rho.ok && by_rho.ok && by_dist.ok && by_ga1.ok && by_pr.ok;
+    if (ok || !FAST) { u[NEQ - 1] = e_new; }
+    return ok;
+}
+
+template <int ND>
+__device__ __forceinline__ void cfl_from_dist(double hdt, double ga, double dist, double (&u)[ND + 2], double & cflo, double & cflc)
+{
+#if SCG_SHARED_RCP
+    if (cfl_from_dist_impl<ND, true>(hdt, ga, dist, u, cflo, cflc)) { return; }
+#endif
+    cfl_from_dist_impl<ND, false>(hdt, ga, dist, u, cflo, cflc);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -832,7 +854,7 @@ __device__ __forceinline__ void soln_stage_issue_b(MdGeo const & G, int64_t i, i
 
 template <int TYPE, int TB>
 __device__ __forceinline__ void cell_soln_staged(MdField const & F, MdGeo const & G, int32_t i, double * st,
-                                                 double (&out)[ct_ndim(TYPE) + 2], double & dist, int32_t & jmax)
+                                                 double (&out)[ct_ndim(TYPE) + 2], double & dist, bool & dist_ok, int32_t & jmax)
 {
     using L = SolnStage<TYPE, TB>;
     constexpr int ND = ct_ndim(TYPE);
@@ -855,6 +877,7 @@ __device__ __forceinline__ void cell_soln_staged(MdField const & F, MdGeo const 
 #pragma unroll
     for (int d = 0; d < ND; ++d) { cc[d] = F.solpt[d * F.S + G.beg + i]; }
     dist = DBL_MAX;
+    dist_ok = true;
 
 #pragma unroll 1
     for (int f = 0; f < NFC; ++f)
@@ -897,7 +920,7 @@ __device__ __forceinline__ void cell_soln_staged(MdField const & F, MdGeo const 
                     double const diff = bc[d] - cc[d];
                     d2 += diff * diff;
                 }
-                double const r = sqrt(d2);
+                double const r = sqrt_fast(d2, dist_ok); // range test deferred: no branch inside the face loop
                 dist = (r < dist) ? r : dist; // std::min(dist, r), euler_solution.cpp:129
             }
             // ---- Taylor state on every sub-face (euler_march.cpp:268-280)
