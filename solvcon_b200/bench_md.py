@@ -150,17 +150,30 @@ class MD3DWorkload:
                 self.ncu_traffic = float(json.load(f)["bytes_per_cell_substep"]) * self.ncell
         return self.dev
 
+    def _planned(self):
+        """Mesh numbers of the target size without building anything (the reference arm never builds the device case)."""
+        nx, ny, nz, x1, z1 = dims_3d(self.ncell_target)
+        nhex, npri, ntet = x1 * ny * z1, 2 * (nx - x1) * ny * z1, 6 * (nx - x1) * ny * (nz - z1)
+        ncell = nhex + npri + ntet
+        info = {"boxes": [nx, ny, nz], "x1": x1, "z1": z1, "h": 1.0 / ny, "dt": 0.05 / ny, "ncell": ncell,
+                "cells_by_type": {"hex": nhex, "tet": ntet, "prism": npri}, "planned_only": True}
+        return ncell, info, float(1752 * nhex + 1428 * npri + 1104 * ntet)
+
     def describe(self, world):
+        if hasattr(self, "info"):
+            ncell, info, balg = self.ncell, self.info, float(self.balg_substep)
+        else:
+            ncell, info, balg = self._planned()
         d = {"workload": f"3D Euler CESE (multidim EulerCore.march), synthetic mixed tet/hex/prism stepped channel, "
-                         f"{self.ncell} cells per GPU ({self.info['cells_by_type']}), Mach-3 inlet / nonrefl outlet / "
+                         f"{ncell} cells per GPU ({info['cells_by_type']}), Mach-3 inlet / nonrefl outlet / "
                          f"slip walls, march({self.chunk}) per step, {self.order} cell ordering",
-             "cells_per_gpu": self.ncell, "chunk_steps": self.chunk, "ordering": self.order,
-             "alg_bytes_per_cell_substep": self.balg_substep / self.ncell,
-             "l2_policy": "inputs larger than L2 (%.1f GB streamed per substep)" % (self.balg_substep / 1e9),
+             "cells_per_gpu": ncell, "chunk_steps": self.chunk, "ordering": self.order,
+             "alg_bytes_per_cell_substep": balg / ncell,
+             "l2_policy": "inputs larger than L2 (%.1f GB streamed per substep)" % (balg / 1e9),
              "decomposition": "none" if world == 1 else
              f"y-slabs, one per GPU, domain extended in y with the rank count; halo exchange of so0n+so1n after every "
-             f"substep by NCCL isend/irecv ({self.info.get('halo_bytes_per_substep', 0)} B sent per rank per substep)",
-             "mesh": self.info}
+             f"substep by NCCL isend/irecv ({info.get('halo_bytes_per_substep', 0)} B sent per rank per substep)",
+             "mesh": info}
         if getattr(self, "size_note", None):
             d["size_note"] = self.size_note
         return d
@@ -307,13 +320,22 @@ class MD2DWorkload(MD3DWorkload):
         return self.dev
 
     def describe(self, world):
+        if hasattr(self, "info"):
+            ncell, info, balg = self.ncell, self.info, float(self.balg_substep)
+        else:
+            nx, ny = dims_2d(self.ncell_target)
+            kept = nx * ny - (nx - int(round(0.6 / 3.0 * nx))) * int(round(0.2 * ny))
+            ncell = kept + kept // 4
+            info = {"boxes": [nx, ny], "h": 1.0 / ny, "dt": 0.05 / ny, "ncell": ncell, "planned_only": True,
+                    "cells_by_type": {"quad": kept - kept // 4, "tri": 2 * (kept // 4)}}
+            balg = float(616 * info["cells_by_type"]["quad"] + 524 * info["cells_by_type"]["tri"])
         return {"workload": f"2D Euler CESE (multidim EulerCore.march), synthetic mixed tri/quad forward-facing step, "
-                            f"{self.ncell} cells ({self.info['cells_by_type']}), Mach-3 inlet / nonrefl outlet / slip walls, "
+                            f"{ncell} cells ({info['cells_by_type']}), Mach-3 inlet / nonrefl outlet / slip walls, "
                             f"march({self.chunk}) per step, {self.order} cell ordering",
-                "cells_per_gpu": self.ncell, "chunk_steps": self.chunk, "ordering": self.order,
-                "alg_bytes_per_cell_substep": self.balg_substep / self.ncell,
-                "l2_policy": "inputs larger than L2 (%.1f GB streamed per substep)" % (self.balg_substep / 1e9),
-                "decomposition": "none", "mesh": self.info}
+                "cells_per_gpu": ncell, "chunk_steps": self.chunk, "ordering": self.order,
+                "alg_bytes_per_cell_substep": balg / ncell,
+                "l2_policy": "inputs larger than L2 (%.1f GB streamed per substep)" % (balg / 1e9),
+                "decomposition": "none", "mesh": info}
 
     def e2e_bytes(self):
         T, ng = self.ncell + self.info["ngstcell"], self.info["ngstcell"]

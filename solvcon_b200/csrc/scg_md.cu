@@ -352,11 +352,11 @@ __global__ void __launch_bounds__(128, SCG_SOLN_MINBLOCKS) md_solncfl_kernel(MdF
 // face issued one face ahead (cell_soln_staged); calc_cfl's distance is taken from the staged cecnd rows
 // instead of a second pass over them.
 #ifndef SCG_STAGED_TB
-#define SCG_STAGED_TB 128
+#define SCG_STAGED_TB 64
 #endif
 // threads per CTA and resident CTAs per SM the register budget is sized for: the 3D flux evaluation wants ~250
 // registers (8 warps per SM; 64-thread CTAs are 3 % faster than 128-thread ones at the same 8 warps), tetrahedra
-// run at 204 (10 warps), the 2D types at 128 (16 warps of 128-thread CTAs)
+// run at 204 (10 warps), the 2D types at 128 (16 warps)
 #ifndef SCG_STAGED_MB_HEX
 #define SCG_STAGED_MB_HEX 4
 #endif
@@ -367,10 +367,10 @@ __global__ void __launch_bounds__(128, SCG_SOLN_MINBLOCKS) md_solncfl_kernel(MdF
 #define SCG_STAGED_MB_TET 5
 #endif
 #ifndef SCG_STAGED_MB_QUAD
-#define SCG_STAGED_MB_QUAD 4
+#define SCG_STAGED_MB_QUAD 8
 #endif
 #ifndef SCG_STAGED_MB_TRI
-#define SCG_STAGED_MB_TRI 4
+#define SCG_STAGED_MB_TRI 8
 #endif
 #ifndef SCG_STAGED_TB_HEX
 #define SCG_STAGED_TB_HEX 64
@@ -442,6 +442,9 @@ __global__ void __launch_bounds__(StagedCfg<TYPE>::TB, StagedCfg<TYPE>::MB) md_s
 
 // Split substep, kernel 2, equation-outer variant (march mode 3): one thread per cell, adj(D)/det(D) of the
 // gradient elements parked in shared memory, then one equation at a time (cell_dsoln_eqo).
+#ifndef SCG_EQO_TB
+#define SCG_EQO_TB 64
+#endif
 #ifndef SCG_EQO_MB_HEX
 #define SCG_EQO_MB_HEX 4
 #endif
@@ -475,7 +478,7 @@ struct EqoCfg
     // prefetch the next equation's neighbour gather into registers
     static constexpr bool PF = (TYPE == CT_HEX) ? SCG_EQO_PF_HEX : (TYPE == CT_PRISM || TYPE == CT_PYRAMID) ? SCG_EQO_PF_PRISM
                              : (TYPE == CT_TET) ? SCG_EQO_PF_TET : SCG_EQO_PF_2D;
-    static constexpr int TB = 64;
+    static constexpr int TB = SCG_EQO_TB;
     // resident CTAs per SM the register budget is sized for (shared memory allows at least as many)
     static constexpr int MB = (TYPE == CT_HEX) ? SCG_EQO_MB_HEX
                             : (TYPE == CT_PRISM || TYPE == CT_PYRAMID) ? SCG_EQO_MB_PRISM
