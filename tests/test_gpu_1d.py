@@ -18,8 +18,9 @@ def _assert_same(a, b, name, strict):
     if strict:
         assert np.array_equal(a, b), f"{name}: max abs diff {np.abs(a - b).max()}"
     else:
+        # FMA speed variant (not the product default): documented distance from the reference, DESIGN.md section 2
         scale = np.abs(b).max() + 1e-300
-        assert np.abs(a - b).max() / scale < 1e-11, name
+        assert np.abs(a - b).max() / scale < 1e-9, name
 
 
 @pytest.mark.parametrize("alpha", [1, 2])
@@ -168,8 +169,9 @@ def test_scalar_fine_interface_bit_equal(gpu, eq):
         b.march_half_so0(odd_plane=True)
         b.update_cfl(odd_plane=False)
         b.march_half_so1_alpha2(odd_plane=True)
+        strict = bool(gpu.load().scg_build_is_strict())   # the FMA speed variant contracts the fused kernel differently
         for name in ("so0", "so1", "cfl"):
-            assert np.array_equal(getattr(a, name).ndarray, getattr(b, name).ndarray), name
+            _assert_same(getattr(a, name).ndarray, getattr(b, name).ndarray, name, strict)
 
 
 @pytest.mark.parametrize("ncelm", [1, 2, 3, 255, 256, 257])
