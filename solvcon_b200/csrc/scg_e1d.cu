@@ -56,6 +56,10 @@ __device__ __forceinline__ double pow_alpha(double v)
     return v * v;
 }
 
+#ifndef SCG_E1D_MINBLOCKS
+#define SCG_E1D_MINBLOCKS 3
+#endif
+
 // Everything a source solution element contributes (Euler1DKernel::derive, Euler1DCore.hpp:210-244, and
 // update_cfl at the source point, Euler1DCore.cpp:70-94).  FAST: the ten Jacobian / flux quotients share three
 // refined reciprocals (u0 + tiny, u0^2 + tiny, u0^3 + tiny), the CFL part three more, the two square roots run the
@@ -152,7 +156,7 @@ __device__ __forceinline__ bool e1d_target(double const (&bal)[3], double dx, do
 // Sources run over [sbeg, slast]; targets over t(sbeg) .. t(slast-1); cfl over sources [sbeg, slast-1]
 // (update_cfl's loop stops one source short, Euler1DCore.cpp:73-76).
 template <int ALPHA, int FLAGS>
-__global__ void __launch_bounds__(256) e1d_half_kernel(EPlane const ps, EPlane const pt, int S, int64_t sbeg, int64_t slast, double dt)
+__global__ void __launch_bounds__(256, SCG_E1D_MINBLOCKS) e1d_half_kernel(EPlane const ps, EPlane const pt, int S, int64_t sbeg, int64_t slast, double dt)
 {
     int const lane = threadIdx.x & 31;
     int64_t const warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
