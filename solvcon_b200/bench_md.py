@@ -1,8 +1,9 @@
 """Multidim benchmark workloads for bench.py: 3D Euler CESE on the synthetic mixed tet/hex/prism stepped
 channel (BASELINE.json configs[3]/[4]) and 2D Euler on the mixed tri/quad forward-facing step (configs[2]).
 
-Everything here is product code (mesh generator -> native StaticMesh builder -> device EulerCore); the CPU
-reference arm (``cpu_run``) is the only place that touches ``oracle/`` and only bench.py calls it.
+Everything here is product code (mesh generator -> native StaticMesh builder -> device EulerCore) and nothing here
+imports ``oracle/``: the CPU reference arm (``cpu_run``) forwards to ``bench_cpu.py`` at the repo root, which belongs
+to bench.py's ``cpu_baseline`` / ``--impl reference`` leg.
 """
 from __future__ import annotations
 
@@ -220,50 +221,9 @@ class MD3DWorkload:
         return float(self.dev.so0n.body[:, 0].sum())
 
     def cpu_run(self, budget_s=15.0):
-        return cpu_reference_3d(budget_s, self.kinds)
+        import bench_cpu   # repo root, next to bench.py: the only code on the bench path that touches oracle/
+        return bench_cpu.cpu_reference_3d(budget_s, self.kinds)
 
-
-def cpu_reference_3d(budget_s=15.0, kinds="hpt", ncell_target=60000):
-    """The reference's own EulerCore.march (oracle/_ref, else the pinned C port) on the same generator at a
-    size that finishes in seconds, single thread (the reference is single-threaded)."""
-    from oracle import bridge as b
-    nx, ny, nz, x1, z1 = dims_3d(ncell_target)
-    h = 1.0 / ny
-    ndcrd, cltpn, clnds = meshgen.mixed_3d(nx, ny, nz, lx=nx * h, ly=1.0, lz=nz * h, x1=x1, z1=z1, kinds=kinds, jitter=0.1)
-    dt = 0.05 * h
-    if b.have_ref():
-        mesh = b.make_ref_mesh(3, ndcrd, cltpn, clnds)
-        svr = b.RefEuler(mesh, dt)
-        fccnd, fccls, nface = mesh.body("fccnd"), mesh.body("fccls"), mesh.nface
-        kind = "reference"
-    else:
-        pm = make_mesh(3, ndcrd, cltpn, clnds)
-        svr = b.PortEuler(pm.tables(), 3, dt)
-        svr.phase(b.MD_PREPARE_CE)
-        fccnd, fccls, nface = pm.fccnd.body, pm.fccls.body, pm.nface
-        kind = "port"
-    lo, hi = ndcrd.min(axis=0), ndcrd.max(axis=0)
-    inlet, outlet, wall = meshgen.boundary_groups(3, fccnd, fccls, nface, lo, hi)
-    svr.init_solution(1.4, 1.4, [3.0, 0.0, 0.0], 1.0)
-    svr.add_bc(b.BC_INLET, inlet, [1.4, 3.0, 0.0, 0.0, 1.0, 1.4])
-    svr.add_bc(b.BC_NONREFL, outlet)
-    svr.add_bc(b.BC_SLIPWALL, wall)
-    svr.phase(b.MD_BC_SOLN)
-    svr.phase(b.MD_BC_DSOLN)
-    svr.march(1)
-    ncell = len(cltpn)
-    t0 = time.perf_counter()
-    steps = 0
-    while True:
-        svr.march(1)
-        steps += 1
-        el = time.perf_counter() - t0
-        if el > budget_s or steps >= 200:
-            break
-    upd = 2 * steps * ncell
-    return ({"value": upd / el, "unit": UNIT, "cores": 1, "kind": kind,
-             "sample": f"3D Euler mixed tet/hex/prism channel, {ncell} cells, march({steps}) in {el:.2f} s, single "
-                       f"thread (the reference is single-threaded)"}, upd, el)
 
 
 # ------------------------------------------------------------------------------------------ 2D ---
@@ -345,49 +305,8 @@ class MD2DWorkload(MD3DWorkload):
         return 8 * (T * (neq + neq * nd + 1) + ng * (neq + neq * nd + 2)), T * (per_row - 8)
 
     def cpu_run(self, budget_s=15.0):
-        return cpu_reference_2d(budget_s)
-
-
-def cpu_reference_2d(budget_s=15.0, ncell_target=120000):
-    """The reference's EulerCore.march on the same 2D generator at a size that finishes in seconds, single thread."""
-    from oracle import bridge as b
-    nx, ny = dims_2d(ncell_target)
-    h = 1.0 / ny
-    ndcrd, cltpn, clnds = meshgen.mixed_2d(nx, ny, lx=3.0, ly=1.0, tri_every=4, jitter=0.3, step=(0.6, 0.2))
-    dt = 0.05 * h
-    if b.have_ref():
-        mesh = b.make_ref_mesh(2, ndcrd, cltpn, clnds)
-        svr = b.RefEuler(mesh, dt)
-        fccnd, fccls, nface = mesh.body("fccnd"), mesh.body("fccls"), mesh.nface
-        kind = "reference"
-    else:
-        pm = make_mesh(2, ndcrd, cltpn, clnds)
-        svr = b.PortEuler(pm.tables(), 2, dt)
-        svr.phase(b.MD_PREPARE_CE)
-        fccnd, fccls, nface = pm.fccnd.body, pm.fccls.body, pm.nface
-        kind = "port"
-    lo, hi = ndcrd.min(axis=0), ndcrd.max(axis=0)
-    inlet, outlet, wall = meshgen.boundary_groups(2, fccnd, fccls, nface, lo, hi)
-    svr.init_solution(1.4, 1.4, [3.0, 0.0], 1.0)
-    svr.add_bc(b.BC_INLET, inlet, [1.4, 3.0, 0.0, 1.0, 1.4])
-    svr.add_bc(b.BC_NONREFL, outlet)
-    svr.add_bc(b.BC_SLIPWALL, wall)
-    svr.phase(b.MD_BC_SOLN)
-    svr.phase(b.MD_BC_DSOLN)
-    svr.march(1)
-    ncell = len(cltpn)
-    t0 = time.perf_counter()
-    steps = 0
-    while True:
-        svr.march(1)
-        steps += 1
-        el = time.perf_counter() - t0
-        if el > budget_s or steps >= 400:
-            break
-    upd = 2 * steps * ncell
-    return ({"value": upd / el, "unit": UNIT, "cores": 1, "kind": kind,
-             "sample": f"2D Euler mixed tri/quad forward step, {ncell} cells, march({steps}) in {el:.2f} s, single "
-                       f"thread (the reference is single-threaded)"}, upd, el)
+        import bench_cpu
+        return bench_cpu.cpu_reference_2d(budget_s)
 
 
 def make(args):
