@@ -440,6 +440,23 @@ class RefEuler:
         _check(self.lib.ref_md_normal_matrix(self.h, ifc, _p(out)), self.lib)
         return out
 
+    def gradient_element(self, icl, tau, udf):
+        """The reference's GradientElement(mesh, cecnd, icl, tau) flattened: dict of meta / rcl / idis / jdis / faces
+        (1-based) / dmat / grads (= solve_gradient(ifge, udf)) / nfge_inverse."""
+        lib = self.lib
+        lib.ref_md_gradient_element.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p,
+                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        meta, rcl = np.zeros(4, np.int32), np.zeros(6, np.int32)
+        idis, jdis = np.zeros(19), np.zeros(18)
+        faces, dmat, grads = np.zeros(24, np.int32), np.zeros(72), np.zeros(24)
+        u = np.zeros(3)
+        u[:len(udf)] = udf
+        _check(lib.ref_md_gradient_element(self.h, self.mesh.h, icl, tau, _p(u), _p(meta), _p(rcl), _p(idis), _p(jdis),
+                                           _p(faces), _p(dmat), _p(grads)), lib)
+        return {"meta": meta, "rcl": rcl, "idis": idis[:18].reshape(6, 3), "jdis": jdis.reshape(6, 3),
+                "faces": faces.reshape(8, 3), "dmat": dmat.reshape(8, 3, 3), "grads": grads.reshape(8, 3),
+                "nfge_inverse": float(idis[18])}
+
     def snapshot(self):
         return {n: self.arr(n).copy() for n in MD_ARRAYS}
 

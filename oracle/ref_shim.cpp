@@ -24,6 +24,7 @@
 #include <solvcon/spacetime/kernel/inviscid_burgers.hpp>
 #include <solvcon/mesh/mesh.hpp>
 #include <solvcon/multidim/euler.hpp>
+#include <solvcon/multidim/GradientElement.hpp>
 #include <solvcon/inout/gmsh.hpp>
 
 #include <cstring>
@@ -416,6 +417,52 @@ int ref_md_march(ref_md * h, int64_t steps)
 }
 
 /* Array access by name; pointer to the first stored element (ghost rows first). */
+// GradientElement(mesh, cecnd, icl, tau) of the reference (GradientElement.cpp:137-213) flattened for ctypes:
+// rcl[6], idis[6][3], jdis[6][3], faces[8][3] (1-based), dmat[8][3][3], and grads[8][3] = solve_gradient(ifge, udf)
+int ref_md_gradient_element(ref_md * h, ref_mesh * mesh, int32_t icl, double tau, double const * udf, int32_t * meta,
+                            int32_t * rcl, double * idis, double * jdis, int32_t * faces, double * dmat, double * grads)
+{
+    try
+    {
+        sc::GradientElement ge(*mesh->p, h->p->cecnd(), icl, tau);
+        int const nd = ge.ndim();
+        meta[0] = ge.icl();
+        meta[1] = nd;
+        meta[2] = ge.clnfc();
+        meta[3] = ge.nfge();
+        idis[18] = ge.nfge_inverse(); // one spare slot behind idis[6][3]
+        for (int f = 0; f < ge.clnfc(); ++f)
+        {
+            rcl[f] = ge.rcl(f);
+            for (int d = 0; d < nd; ++d)
+            {
+                idis[f * 3 + d] = ge.idis(f, d);
+                jdis[f * 3 + d] = ge.jdis(f, d);
+            }
+        }
+        for (int g = 0; g < ge.nfge(); ++g)
+        {
+            auto const & tf = ge.faces(g);
+            auto const dm = ge.displacement_matrix(g);
+            sc::GradientElement::ge_vector_type u = {0, 0, 0};
+            for (int d = 0; d < nd; ++d) { u[d] = udf[d]; }
+            auto const gr = ge.solve_gradient(g, u);
+            for (int v = 0; v < nd; ++v)
+            {
+                faces[g * 3 + v] = tf[v];
+                grads[g * 3 + v] = gr[v];
+                for (int d = 0; d < nd; ++d) { dmat[(g * 3 + v) * 3 + d] = dm[v][d]; }
+            }
+        }
+        return 0;
+    }
+    catch (std::exception const & e)
+    {
+        g_err = e.what();
+        return 1;
+    }
+}
+
 double * ref_md_array(ref_md * h, char const * name, int64_t * size, int64_t * nghost)
 {
     auto & s = *h->p;

@@ -7,8 +7,15 @@ The package holds only what the hot path needs:
 * ``spacetime``    mirror of ``_solvcon.spacetime.{Grid,LinearScalarSolver,InviscidBurgersSolver}``
 * ``mesh``         mirror of ``_solvcon.StaticMesh`` (host table builder)
 * ``multidim``     mirror of ``_solvcon.EulerCore``
+* ``gradient_element``  mirror of ``_solvcon.GradientElement`` (host-side probe of one cell)
+* ``euler_field``  ``EulerField`` with device-side derived fields and reductions
+* ``gmsh``         Gmsh MSH 2.2 reader (``solvcon.Gmsh``)
+* ``apps.obsrefl`` the oblique-shock-reflection application over the device core
 * ``meshgen``      deterministic synthetic meshes for the named benchmark configurations
-* ``decomp``       slab / RCB domain decomposition and halo exchange (one process per GPU)
+* ``decomp`` / ``decomp1d``  domain decomposition and halo exchange (one process per GPU)
+
+The names of the reference's extension module are available at the package level too (``EulerCore``, ``StaticMesh``,
+``GradientElement``, ``Gmsh``, ...), resolved lazily so that importing the package stays cheap.
 
 There is no CPU fallback: every solver call goes through the CUDA library and raises when it
 is missing or no device is present.
@@ -16,4 +23,15 @@ is missing or no device is present.
 from . import _lib  # noqa: F401
 from .simplearray import SimpleArray, SimpleArrayFloat64, SimpleArrayInt32  # noqa: F401
 
-__all__ = ["_lib", "SimpleArray", "SimpleArrayFloat64", "SimpleArrayInt32"]
+__all__ = ["_lib", "SimpleArray", "SimpleArrayFloat64", "SimpleArrayInt32", "EulerCore", "StaticMesh", "StaticMeshBc",
+           "GradientElement", "EulerField", "Gmsh", "Euler1DCore"]
+
+_LAZY = {"EulerCore": "multidim", "StaticMesh": "mesh", "StaticMeshBc": "mesh", "GradientElement": "gradient_element",
+         "EulerField": "euler_field", "Gmsh": "gmsh", "Euler1DCore": "onedim"}
+
+
+def __getattr__(name):
+    if name in _LAZY:
+        import importlib
+        return getattr(importlib.import_module("." + _LAZY[name], __name__), name)
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")
