@@ -62,6 +62,8 @@ _SIGNATURES = {
     "scg_st_phase": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "scg_st_march": (C.c_int, [C.c_void_p, C.c_int, C.c_int64]),
     "scg_st_reduce": (C.c_int, [C.c_void_p, DP, DP, DP]),
+    "scg_st_set_halo_mode": (C.c_int, [C.c_void_p, C.c_int]),
+    "scg_st_march_half": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "scg_st_halo_pack": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "scg_st_halo_unpack": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     # 1D Euler
