@@ -84,6 +84,11 @@ def md_mesh_case(name):
         return (3,) + meshgen.mixed_3d(1, 1, 1, kinds="p")
     if name == "six_pyramid":
         return (3,) + meshgen.pyramid_3d(1, 1, 1)
+    # several waves of CTAs per cell-type group (148 SMs x 4 CTAs x 64 cells = 38k cells per wave)
+    if name == "mixed3d_150k":
+        return (3,) + meshgen.mixed_3d(48, 44, 48, kinds="hpt", jitter=0.15)
+    if name == "mixed2d_200k":
+        return (2,) + meshgen.mixed_2d(600, 280, lx=3.0, ly=1.0, tri_every=4, jitter=0.25, step=(0.6, 0.2))
     if name == "pyramid3d":
         return (3,) + meshgen.pyramid_3d(4, 3, 3, jitter=0.12)
     raise KeyError(name)

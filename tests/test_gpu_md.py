@@ -370,3 +370,22 @@ def test_md_smallest_meshes(gpu, bridge, name, fused):
     c.chk.march(6)
     c.dev.march(6)
     c.same(f"march(6) fused={fused}", STATE, strict)
+
+
+@pytest.mark.parametrize("name,order", [("mixed3d_150k", "rcm"), ("mixed3d_150k", "morton"), ("mixed2d_200k", "rcm")])
+def test_md_many_waves_matches(gpu, bridge, name, order):
+    """Meshes of 1.5e5 - 2e5 cells: several waves of CTAs per kernel, ragged last CTAs in every type group, both
+    production orderings -- still bit-equal to the checker after 3 steps."""
+    b = bridge
+    c = Case(b, name, order=order)
+    assert c.dev.ncell > 140_000
+    c.chk.phase(b.MD_BC_SOLN)
+    c.chk.phase(b.MD_BC_DSOLN)
+    c.dev.bc_soln()
+    c.dev.bc_dsoln()
+    c.chk.march(3)
+    c.dev.march(3)
+    c.same(f"march(3) {name} {order}", STATE, _strict(gpu))
+    vol = c.mesh.clvol.body
+    assert np.isfinite(c.dev.so0n.ndarray).all() and (c.dev.so0n.body[:, 0] > 0).all()
+    assert abs((c.dev.so0n.body[:, 0] * vol).sum() - (c.chk.body("so0n")[:, 0] * vol).sum()) <= 1e-13 * vol.sum()
