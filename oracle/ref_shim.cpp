@@ -13,6 +13,8 @@
  *                                             cpp/solvcon/spacetime/core.hpp:98-1053
  *   solvcon::StaticMesh                       cpp/solvcon/mesh/StaticMesh.hpp:253-455
  *   solvcon::EulerCore                        cpp/solvcon/multidim/euler.hpp:56-211
+ *   solvcon::GradientElement                  cpp/solvcon/multidim/GradientElement.hpp
+ *   solvcon::inout::Gmsh                      cpp/solvcon/inout/gmsh.hpp:80-262
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference legs may load the resulting library.
