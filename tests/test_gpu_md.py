@@ -389,3 +389,50 @@ def test_md_many_waves_matches(gpu, bridge, name, order):
     vol = c.mesh.clvol.body
     assert np.isfinite(c.dev.so0n.ndarray).all() and (c.dev.so0n.body[:, 0] > 0).all()
     assert abs((c.dev.so0n.body[:, 0] * vol).sum() - (c.chk.body("so0n")[:, 0] * vol).sum()) <= 1e-13 * vol.sum()
+
+
+def test_ce_geometry_hand_values(gpu):
+    """The reference's own CE-geometry known answers (tests/test_euler_multidim.py:11-144), written against the
+    mirrored classes exactly as the reference writes them: a fan of 3 triangles and a unit-square quadrilateral."""
+    import solvcon_b200 as solvcon
+    mh = solvcon.StaticMesh(ndim=2, nnode=4, nface=0, ncell=3)
+    mh.ndcrd[:, :] = [(0, 0), (-1, -1), (1, -1), (0, 1)]
+    mh.cltpn.fill(solvcon.StaticMesh.TRIANGLE)
+    mh.clnds[:, :4] = (3, 0, 1, 2), (3, 0, 2, 3), (3, 0, 3, 1)
+    mh.build_interior(do_metric=True)
+    mh.build_boundary()
+    mh.build_ghost()
+    ec = solvcon.EulerCore(mesh=mh, time_increment=0.01)
+    assert (ec.ndim, ec.ncell, ec.ngstcell) == (2, 3, 3)
+    total = ec.ngstcell + ec.ncell
+    CLMFC, FCMND = solvcon.StaticMesh.CLMFC, solvcon.StaticMesh.FCMND
+    assert ec.cevol.shape == (total, CLMFC + 1) and ec.cecnd.shape == (total, (CLMFC + 1) * 2)
+    assert ec.sfcnd.shape == (3, CLMFC * FCMND, 2) and ec.sfnml.shape == (3, CLMFC * FCMND, 2)
+    for icl in range(3):
+        assert ec.cevol[icl, 0] > 0.0
+        nfc = mh.clfcs[icl, 0]
+        assert abs(sum(ec.cevol[icl, ifl] for ifl in range(1, nfc + 1)) - ec.cevol[icl, 0]) < 1e-12
+    assert abs(ec.cevol[0, 1] - 0.5) < 1e-10 and abs(ec.cevol[0, 2] - 2.0 / 3.0) < 1e-10 and abs(ec.cevol[0, 3] - 0.5) < 1e-10
+    assert abs(ec.cevol[0, 0] - (0.5 + 2.0 / 3.0 + 0.5)) < 1e-10
+    before = ec.cevol[0, 0]
+    ec.prepare_ce()
+    assert ec.cevol[0, 0] == before
+
+    mq = solvcon.StaticMesh(ndim=2, nnode=4, nface=0, ncell=1)
+    mq.ndcrd[:, :] = [(0, 0), (1, 0), (1, 1), (0, 1)]
+    mq.cltpn.fill(solvcon.StaticMesh.QUADRILATERAL)
+    mq.clnds[:, :5] = [(4, 0, 1, 2, 3)]
+    mq.build_interior(do_metric=True)
+    mq.build_boundary()
+    mq.build_ghost()
+    eq = solvcon.EulerCore(mesh=mq, time_increment=0.01)
+    assert (eq.ndim, eq.ncell, eq.ngstcell) == (2, 1, 4)
+    for ifl in range(1, 5):
+        assert abs(eq.cevol[0, ifl] - 0.5) < 1e-10
+    assert abs(eq.cevol[0, 0] - 2.0) < 1e-10
+    mags = [np.linalg.norm(eq.sfnml.ndarray[0, ifc * FCMND + ind]) for ifc in range(4) for ind in range(FCMND)]
+    assert any(m > 1e-14 for m in mags)
+    for m in mags:
+        if m > 1e-14:
+            assert abs(m - 0.5 * np.sqrt(2.0)) < 1e-10
+    assert np.any(eq.sfcnd.ndarray[0] != 0)
