@@ -436,3 +436,59 @@ def test_ce_geometry_hand_values(gpu):
         if m > 1e-14:
             assert abs(m - 0.5 * np.sqrt(2.0)) < 1e-10
     assert np.any(eq.sfcnd.ndarray[0] != 0)
+
+
+@pytest.mark.parametrize("name", ["mixed2d", "mixed3d", "pyramid3d"])
+def test_reference_invariants(gpu, name):
+    """Invariants the reference's tests/test_multidim.py pins without any second implementation: init_solution
+    validation (:505-515), calc_cfl on a uniform field (:517-541), the negative-pressure clamp (:543-558), update()
+    swapping the buffers (:560-577), free-stream preservation of calc_soln (:657-675)."""
+    from cases import md_mesh_case
+    from solvcon_b200.mesh import make_mesh
+    from solvcon_b200.multidim import EulerCore
+    nd, ndcrd, cltpn, clnds = md_mesh_case(name)
+    mesh = make_mesh(nd, ndcrd, cltpn, clnds)
+    GAMMA, RHO, PRES = 1.4, 1.2, 0.9
+    v = [0.3, -0.2, 0.1][:nd]
+    ec = EulerCore(mesh, 1.e-3)
+    good = dict(gamma=GAMMA, rho=RHO, v=v, p=PRES)
+    for bad in (dict(v=[0.1] * (nd - 1)), dict(gamma=1.0), dict(rho=0.0), dict(p=-1.0)):
+        with pytest.raises(ValueError):
+            ec.init_solution(**dict(good, **bad))
+    # ---- calc_cfl, uniform field
+    ec.init_solution(**good)
+    ec.calc_cfl()
+    hdt = ec.time_increment / 2.0
+    vsq = sum(c * c for c in v)
+    wspd = np.sqrt(GAMMA * PRES / RHO) + np.sqrt(vsq)
+    energy0 = PRES / (GAMMA - 1.0) + 0.5 * RHO * vsq
+    ce = ec.cecnd.body
+    nfc = mesh.clfcs.body[:, 0]
+    for icl in range(0, ec.ncell, max(1, ec.ncell // 50)):
+        dist = min(np.sqrt(((ce[icl, f * nd:(f + 1) * nd] - ce[icl, :nd]) ** 2).sum()) for f in range(1, nfc[icl] + 1))
+        assert abs(ec.cflo[icl] - hdt * wspd / dist) < 1e-7 * ec.cflo[icl] + 1e-12
+        assert abs(ec.cflc[icl] - ec.cflo[icl]) < 1e-7
+        assert abs(ec.so0n[icl, nd + 1] - energy0) < 1e-7
+    # ---- negative pressure: clamped CFL forced to 1, energy rebuilt from the kinetic part
+    ec.init_solution(**good)
+    ec.so0n.body[:, nd + 1] = 0.0
+    ec.calc_cfl()
+    ke = sum((RHO * c) ** 2 for c in v) / (2.0 * RHO)
+    assert np.allclose(ec.cflc.body, 1.0, rtol=0, atol=1e-7) and np.allclose(ec.so0n.body[:, nd + 1], ke, rtol=0, atol=1e-7)
+    # ---- update() swaps
+    ec.init_solution(**good)
+    ec.so1n.ndarray[...] = np.arange(ec.so1n.ndarray.size, dtype="float64").reshape(ec.so1n.ndarray.shape)
+    before = {n: getattr(ec, n).ndarray.copy() for n in ("so0n", "so0c", "so1n", "so1c")}
+    ec.update()
+    assert np.array_equal(ec.so0c.ndarray, before["so0n"]) and np.array_equal(ec.so0n.ndarray, before["so0c"])
+    assert np.array_equal(ec.so1c.ndarray, before["so1n"]) and np.array_equal(ec.so1n.ndarray, before["so1c"])
+    # ---- free stream: a uniform state with zero gradient is preserved by the flux integral
+    ec2 = EulerCore(mesh, 1.e-3)
+    row = [RHO] + [RHO * c for c in v] + [energy0]
+    ec2.gamma.ndarray[...] = GAMMA
+    ec2.so0c.ndarray[...] = row
+    ec2.so0t.ndarray[...] = 0.0
+    ec2.so1c.ndarray[...] = 0.0
+    ec2.calc_solt()
+    ec2.calc_soln()
+    assert np.allclose(ec2.so0n.body, row, rtol=0, atol=1e-10)
