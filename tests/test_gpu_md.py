@@ -492,3 +492,41 @@ def test_reference_invariants(gpu, name):
     ec2.calc_solt()
     ec2.calc_soln()
     assert np.allclose(ec2.so0n.body, row, rtol=0, atol=1e-10)
+
+
+@pytest.mark.parametrize("dims", [2, 3])
+def test_channel_march_stays_uniform(gpu, dims):
+    """tests/test_multidim.py:1028-1083 of the reference: a walled channel with a supersonic inlet, slip walls and a
+    non-reflective outflow keeps the aligned uniform stream (density within 1e-6 of the inflow after 5 steps), and the
+    inlet ghosts hold the prescribed state -- written like the reference writes it (bndfcs, fccnd, fccls, so0n[ghost])."""
+    from solvcon_b200 import meshgen
+    from solvcon_b200.mesh import make_mesh
+    from solvcon_b200.multidim import EulerCore
+    GAMMA, RHO, PRES, VX = 1.4, 1.0, 1.0, 2.0
+    if dims == 2:
+        lx = 4.0
+        mh = make_mesh(2, *meshgen.mixed_2d(4, 2, lx=lx, ly=2.0, tri_every=0))
+        vel, dt = [VX, 0.0], 0.04
+    else:
+        lx = 4.0
+        mh = make_mesh(3, *meshgen.mixed_3d(4, 2, 2, lx=lx, ly=2.0, lz=2.0, kinds="h"))
+        vel, dt = [VX, 0.0, 0.0], 0.04
+    left, right, walls = [], [], []
+    for ifc in mh.bndfcs.ndarray[:, 0]:
+        cx = mh.fccnd[int(ifc), 0]
+        (left if abs(cx) < 1e-9 else right if abs(cx - lx) < 1e-9 else walls).append(int(ifc))
+    assert left and right and walls
+    ec = EulerCore(mh, dt)
+    ec.init_solution(gamma=GAMMA, rho=RHO, v=vel, p=PRES)
+    ec.add_inlet(left, value=[RHO] + vel + [PRES, GAMMA])
+    ec.add_nonrefl(right)
+    ec.add_slipwall(walls)
+    ec.bc_soln()
+    ec.bc_dsoln()
+    ec.march(steps=5)
+    so0n = ec.so0n.ndarray
+    assert np.all(np.isfinite(so0n)) and np.abs(so0n).max() < 1e6
+    for icl in range(ec.ncell):
+        assert ec.so0n[icl, 0] > 0.0 and abs(ec.so0n[icl, 0] - RHO) < 1e-6
+    for ifc in left:
+        assert abs(ec.so0n[int(mh.fccls[ifc, 1]), 0] - RHO) < 1e-7
