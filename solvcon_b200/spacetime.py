@@ -180,15 +180,24 @@ class Selm:
 
     # per-element flux accessors (kernel/linear_scalar.hpp:45-87, inviscid_burgers.hpp:51-109);
     # inspection only -- the march computes these on the device.
+    def _kernel(self):
+        return getattr(self._svr, "kernel", None)   # only the generic Solver carries a Kernel of Python callables
+
     def xn(self, iv):
+        if self._kernel() is not None:
+            return self._kernel().xn_calc(self, iv)
         disp = 0.5 * (self.x + self.xneg) - self.xctr
         return self.dxneg * (self.get_so0(iv) + disp * self.get_so1(iv))
 
     def xp(self, iv):
+        if self._kernel() is not None:
+            return self._kernel().xp_calc(self, iv)
         disp = 0.5 * (self.x + self.xpos) - self.xctr
         return self.dxpos * (self.get_so0(iv) + disp * self.get_so1(iv))
 
     def _t(self, iv, sign):
+        if self._kernel() is not None:
+            return (self._kernel().tn_calc if sign > 0 else self._kernel().tp_calc)(self, iv)
         disp = self.x - self.xctr
         u, ux = self.get_so0(iv), self.get_so1(iv)
         if self._svr._eq == 0:
@@ -206,12 +215,17 @@ class Selm:
     def tp(self, iv): return self._t(iv, -1.0)
 
     def so0p(self, iv):
+        if self._kernel() is not None:
+            return self._kernel().so0p_calc(self, iv)
         ret = self.get_so0(iv)
         ret += (self.x - self.xctr) * self.get_so1(iv)
         ret -= self.hdt * self.get_so1(iv)
         return ret
 
     def update_cfl(self):
+        if self._kernel() is not None:
+            self._kernel().cfl_updater(self)
+            return
         hdx = min(self.dxneg, self.dxpos)
         if self._svr._eq == 0:
             self.set_cfl(self.hdt / hdx)
@@ -543,6 +557,139 @@ class InviscidBurgersSolver(_ScalarSolver):
 
     def __init__(self, grid, time_increment):
         super().__init__(grid, time_increment)
+
+
+class Kernel:
+    """``spacetime::Kernel`` (core.hpp:223-273, 505-519): six callables ``xn_calc, xp_calc, tn_calc, tp_calc,
+    so0p_calc(se, iv) -> float`` and ``cfl_updater(se)``; ``reset()`` restores the defaults (zeros, identity, cfl = 0)."""
+
+    def __init__(self):
+        self.reset()
+
+    def reset(self):
+        self.xn_calc = lambda se, iv: 0.0
+        self.xp_calc = lambda se, iv: 0.0
+        self.tn_calc = lambda se, iv: 0.0
+        self.tp_calc = lambda se, iv: 0.0
+        self.so0p_calc = lambda se, iv: se.get_so0(iv)
+        self.cfl_updater = lambda se: se.set_cfl(0.0)
+
+
+class Solver(_ScalarSolver):
+    """The generic ``spacetime::Solver`` (core.hpp:1038-1053; binding wrap_spacetime.cpp:130-164) whose physics is a
+    :class:`Kernel` of PYTHON CALLABLES.  It is host-only BY CONSTRUCTION, here as in the reference: the march calls back
+    into Python once per solution element, which a device cannot do.  It is part of the drop-in surface (the reference's
+    tests drive it, tests/test_spacetime_solution.py) and is NOT a fallback of the device solvers --
+    ``LinearScalarSolver`` / ``InviscidBurgersSolver`` never come here.  The loops are those of ``SolverBase``
+    (core.hpp:946-1036) over the cursor classes above."""
+
+    _eq = -1
+
+    def __init__(self, grid, time_increment, nvar=1):
+        self._grid = grid
+        self._nvar = int(nvar)
+        nx = 2 * grid.ncelm + 5
+        self._dt = float(time_increment)
+        self._so0 = SimpleArray((nx, self._nvar))
+        self._so1 = SimpleArray((nx, self._nvar))
+        self._cfl = SimpleArray((nx,))
+        self.kernel = Kernel()
+        self._h = None
+        self._resident = False
+
+    def __del__(self):
+        pass
+
+    nvar = property(lambda s: s._nvar)
+
+    @property
+    def time_increment(self):
+        return self._dt
+
+    @time_increment.setter
+    def time_increment(self, v):
+        self._dt = float(v)
+
+    def clone(self, grid=False):
+        other = Solver(self._grid.clone() if grid else self._grid, self._dt, self._nvar)
+        for n in ("_so0", "_so1", "_cfl"):
+            getattr(other, n).ndarray[...] = getattr(self, n).ndarray
+        k, o = self.kernel, other.kernel
+        o.xn_calc, o.xp_calc, o.tn_calc, o.tp_calc, o.so0p_calc, o.cfl_updater = (
+            k.xn_calc, k.xp_calc, k.tn_calc, k.tp_calc, k.so0p_calc, k.cfl_updater)
+        return other
+
+    def _check_iv(self, iv, what):
+        if iv >= self._nvar:
+            raise IndexError(f"{what}(): out of nvar range")
+
+    def set_so0(self, iv, arr, odd_plane=False):
+        if iv >= self._nvar:
+            raise IndexError(f"set_so0(): iv {iv} >= nvar {self._nvar}")
+        self._set(self._so0.ndarray[:, iv], "set_so0", arr, odd_plane)
+
+    # -- coherence: nothing to do, the arrays ARE the state ----------------------------------------------
+    def resident(self, flag=True): return self
+    def sync_to_host(self): pass
+    def _push(self, force=False): pass
+    def _pull(self): pass
+
+    def reduce(self):
+        cfl = self.get_cfl().ndarray
+        return float(cfl.min()), float(cfl.max()), float(self.get_so0(0).ndarray.sum())
+
+    # -- SolverBase loops, core.hpp:946-1004 ---------------------------------------------------------------
+    def march_half_so0(self, odd_plane):
+        start = -1 if odd_plane else 0
+        for ic in range(start, self._grid.ncelm):
+            ce = Celm(self, ic, odd_plane)
+            for iv in range(self._nvar):
+                ce.selm_tp.set_so0(iv, ce.calc_so0(iv))
+
+    def update_cfl(self, odd_plane):
+        start = -1 if odd_plane else 0
+        for ic in range(start, self._grid.nselm):
+            Selm(self, ic, odd_plane).update_cfl()
+
+    def _march_so1(self, odd_plane, alpha):
+        start = -1 if odd_plane else 0
+        for ic in range(start, self._grid.ncelm):
+            ce = Celm(self, ic, odd_plane)
+            for iv in range(self._nvar):
+                ce.selm_tp.set_so1(iv, ce._calc_so1(iv, alpha))
+
+    def _treat(self, arr):
+        n = self._grid.ncelm
+        left, right = Selm(self, -1, True), Selm(self, n, True)          # the two odd-plane ghosts
+        for iv in range(self._nvar):
+            arr[left._k, iv] = arr[Selm(self, n - 1, True)._k, iv]
+            arr[right._k, iv] = arr[Selm(self, 0, True)._k, iv]
+
+    def treat_boundary_so0(self): self._treat(self._so0.ndarray)
+    def treat_boundary_so1(self): self._treat(self._so1.ndarray)
+
+    def _half1(self, alpha):
+        self.march_half_so0(False)
+        self.treat_boundary_so0()
+        self.update_cfl(True)
+        self._march_so1(False, alpha)
+        self.treat_boundary_so1()
+
+    def _half2(self, alpha):
+        self.march_half_so0(True)
+        self.update_cfl(False)
+        self._march_so1(True, alpha)
+
+    def _march(self, alpha, steps):
+        for _ in range(int(steps)):
+            self._half1(alpha)
+            self._half2(alpha)
+
+    def _phase(self, phase, odd_plane=False, alpha=2):
+        if phase == PH_SO1:
+            self._march_so1(odd_plane, alpha)
+        else:
+            raise NotImplementedError
 
 
 LinearScalarSelm = InviscidBurgersSelm = Selm
