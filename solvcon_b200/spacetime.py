@@ -692,5 +692,28 @@ class Solver(_ScalarSolver):
             raise NotImplementedError
 
 
+class SolverProxy:
+    """``solvcon.spacetime.SolverProxy`` (solvcon/spacetime.py:42-72): owns a generic :class:`Solver` whose kernel hooks are
+    this object's ``_xn_calc / _xp_calc / _tn_calc / _tp_calc / _so0p_calc / _cfl_updater`` methods -- subclass and
+    override them; everything else is forwarded to the solver."""
+
+    _HOOKS = ("xn_calc", "xp_calc", "tn_calc", "tp_calc", "so0p_calc", "cfl_updater")
+
+    def __init__(self, *args, **kw):
+        self.svr = Solver(*args, **kw)
+        for name in self._HOOKS:
+            setattr(self.svr.kernel, name, getattr(self, "_" + name))
+
+    def _xn_calc(self, se, iv): return 1.0
+    def _xp_calc(self, se, iv): return 1.0
+    def _tn_calc(self, se, iv): return 1.0
+    def _tp_calc(self, se, iv): return 1.0
+    def _so0p_calc(self, se, iv): return se.get_so0(iv)
+    def _cfl_updater(self, se): se.set_cfl(1.0)
+
+    def __getattr__(self, name):
+        return getattr(self.svr, name)
+
+
 LinearScalarSelm = InviscidBurgersSelm = Selm
 LinearScalarCelm = InviscidBurgersCelm = Celm

@@ -119,3 +119,32 @@ def test_callback_path_equals_the_c_port(bridge):
     assert np.array_equal(svr.so0.ndarray[:, 0], chk.so0)
     assert np.array_equal(svr.so1.ndarray[:, 0], chk.so1)
     assert np.array_equal(svr.cfl.ndarray, chk.cfl)
+
+
+def test_solver_proxy_subclass_marches_like_the_plain_solver():
+    """tests/test_spacetime_solution.py:361-460: a SolverProxy subclass supplying the linear-wave hooks."""
+    from solvcon_b200 import spacetime as libst
+    nstep, xcrd, plain = _build()
+
+    class LinearProxy(libst.SolverProxy):
+        def _xn_calc(self, se, iv): return plain.kernel.xn_calc(se, iv)
+        def _xp_calc(self, se, iv): return plain.kernel.xp_calc(se, iv)
+        def _tn_calc(self, se, iv): return plain.kernel.tn_calc(se, iv)
+        def _tp_calc(self, se, iv): return plain.kernel.tp_calc(se, iv)
+        def _so0p_calc(self, se, iv): return plain.kernel.so0p_calc(se, iv)
+        def _cfl_updater(self, se): return plain.kernel.cfl_updater(se)
+
+    svr = LinearProxy(grid=libst.Grid(xcrd), time_increment=plain.time_increment, nvar=1)
+    svr.set_so0(0, np.sin(xcrd))
+    svr.set_so1(0, np.cos(xcrd))
+    svr.setup_march()
+    svr.march_alpha2(nstep * 10)
+    np.testing.assert_allclose(svr.get_so0(0), np.sin(xcrd), rtol=0, atol=1.e-14)
+    np.testing.assert_allclose(svr.get_cfl(), np.ones(svr.grid.nselm), rtol=0, atol=1.e-14)
+    plain.march_alpha2(nstep * 10)
+    assert svr.get_so0(0).ndarray.tolist() == plain.get_so0(0).ndarray.tolist()
+    svr.kernel.reset()
+    svr.march_alpha2(nstep)
+    np.testing.assert_array_equal(svr.get_so0(0), np.zeros_like(xcrd))
+    base = libst.SolverProxy(grid=libst.Grid(xcrd), time_increment=0.1, nvar=1)
+    assert base.selm(0).xn(0) == 1.0
