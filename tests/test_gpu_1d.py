@@ -265,3 +265,36 @@ def test_celm_selm_cursors_known_answers(gpu):
     assert sol.so0.shape == (nx, 1) and sol.so1.shape == (nx, 1) and sol.so0.ndarray.dtype == np.float64
     assert len(list(sol.celms())) == sol.grid.ncelm and len(list(sol.selms())) == sol.grid.nselm
     assert len(list(sol.celms(odd_plane=True))) == sol.grid.ncelm - 1
+
+
+def test_shocktube_front_end(gpu, bridge):
+    """``apps.shocktube.ShockTube``: numerical Sod tube on the device against the analytic solution (acceptance,
+    like the reference's sodtube1d application) and, same initial condition, bit-exact against the CPU checker."""
+    from solvcon_b200.apps.shocktube import ShockTube
+    n, dt, steps = 1001, 1.6e-3, 100
+    st = ShockTube()
+    st.build_constant(gamma=1.4, pressure1=1.0, density1=1.0, pressure5=0.1, density5=0.125)
+    st.build_numerical(xmin=-1, xmax=1, ncoord=n, time_increment=dt)
+    svr = st.svr
+    assert svr.ncoord == n and svr.xindices[0] == 2 and svr.xindices[-1] == n - 3 and len(svr.xindices) == (n - 5) // 2 + 1
+    chk = bridge.RefEuler1D(n, dt) if bridge.have_ref() else bridge.PortEuler1D(n, dt)
+    for name in ("coord", "so0", "so1"):
+        getattr(chk, name)[...] = getattr(svr, name)
+    chk.gamma.fill(1.4)
+    svr.march_alpha2(steps)
+    chk.march(2, steps)
+    strict = bool(gpu.load().scg_build_is_strict())
+    for name in ("so0", "so1", "cfl"):
+        _assert_same(getattr(svr, name), getattr(chk, name), name, strict)
+    st.build_field(t=dt * steps)
+    xi = svr.xindices
+    # first-order-accurate capture of the three waves: mean error of a few 1e-3 at 500 cells, measured 1.3e-3 / 2.2e-3 / 1.0e-3
+    assert np.abs(svr.density[xi] - st.density_field).mean() < 4e-3
+    assert np.abs(svr.velocity[xi] - st.velocity_field).mean() < 6e-3
+    assert np.abs(svr.pressure[xi] - st.pressure_field).mean() < 4e-3
+    # plateau between the fan and the contact surface
+    l12, l23, l34, l45 = st.calc_locations(dt * steps)
+    x = svr.coord[xi]
+    mid = (x > l23 + 0.05) & (x < l34 - 0.05)
+    assert np.abs(svr.pressure[xi][mid] - st.pressure3).max() < 1e-3
+    assert np.abs(svr.density[xi][mid] - st.density3).max() < 1e-3
