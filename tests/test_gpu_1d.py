@@ -278,7 +278,7 @@ def test_shocktube_front_end(gpu, bridge):
     svr = st.svr
     assert svr.ncoord == n and svr.xindices[0] == 2 and svr.xindices[-1] == n - 3 and len(svr.xindices) == (n - 5) // 2 + 1
     chk = bridge.RefEuler1D(n, dt) if bridge.have_ref() else bridge.PortEuler1D(n, dt)
-    for name in ("coord", "so0", "so1"):
+    for name in ("coord", "so0", "so1", "cfl"):      # cfl: build_numerical already ran setup_march on the device
         getattr(chk, name)[...] = getattr(svr, name)
     chk.gamma.fill(1.4)
     svr.march_alpha2(steps)
