@@ -58,6 +58,7 @@ def ref_lib():
         lib.ref_e1d_destroy.argtypes = [C.c_void_p]
         lib.ref_e1d_phase.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         lib.ref_e1d_march.argtypes = [C.c_void_p, C.c_int, C.c_int64]
+        lib.ref_e1d_derived.argtypes = [C.c_void_p, C.c_int, DP]
         lib.ref_st_create.restype = C.c_void_p
         lib.ref_st_create.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int64, C.c_double]
         lib.ref_st_create_xloc.restype = C.c_void_p
@@ -160,6 +161,14 @@ class RefEuler1D:
 
     def march(self, alpha, steps):
         _check(self.lib.ref_e1d_march(self.h, alpha, steps), self.lib)
+
+    E1D_FIELDS = ("density", "velocity", "pressure", "temperature", "internal_energy", "entropy")
+
+    def derived(self, name):
+        """The reference's own derived-field array (Euler1DCore.cpp:37-205)."""
+        out = np.empty(self.ncoord)
+        _check(self.lib.ref_e1d_derived(self.h, self.E1D_FIELDS.index(name), _p(out)), self.lib)
+        return out
 
     def __del__(self):
         if getattr(self, "h", None):

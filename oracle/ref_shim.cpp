@@ -138,6 +138,27 @@ int ref_e1d_march(ref_e1d * h, int alpha, int64_t steps)
     REF_CATCH
 }
 
+/* derived fields of Euler1DCore.hpp:106-117; which: 0 density, 1 velocity, 2 pressure, 3 temperature,
+ * 4 internal_energy, 5 entropy */
+int ref_e1d_derived(ref_e1d * h, int which, double * out)
+{
+    REF_TRY
+    auto const & s = *h->p;
+    sc::SimpleArray<double> r;
+    switch (which)
+    {
+    case 0: r = s.density(); break;
+    case 1: r = s.velocity(); break;
+    case 2: r = s.pressure(); break;
+    case 3: r = s.temperature(); break;
+    case 4: r = s.internal_energy(); break;
+    case 5: r = s.entropy(); break;
+    default: throw std::invalid_argument("ref_e1d_derived: bad field");
+    }
+    for (size_t it = 0; it < r.size(); ++it) { out[it] = r.data()[it]; }
+    REF_CATCH
+}
+
 /* --------------------------------------------------------------- 1D scalar */
 
 struct ref_st
