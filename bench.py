@@ -15,7 +15,8 @@ solution point (1D) / one body cell (multidim) advanced by one half-step / subst
 * ``cpu_baseline`` the reference's own CPU march (oracle/_ref, else the pinned C port) timed on
                   this box's host cores on a bounded sample of the same workload
 
-``--impl reference`` runs only the CPU reference arm and prints its line.
+``--impl reference`` runs only the CPU reference arm and prints its line.  The reference march is single-threaded, so
+``value`` is one thread; ``cpu_baseline.all_cores`` adds the summed rate of one independent replica per host thread.
 """
 from __future__ import annotations
 
@@ -348,6 +349,45 @@ def sum_over_ranks(dist, v, local):
     return float(t.item())
 
 
+def run_replica(args):
+    """``--impl reference-replica``: one bounded sample of the reference march, printed as a bare JSON object (child of
+    :func:`all_core_replicas`)."""
+    wl = make_workload(args)
+    _, upd, el = wl.cpu_run(budget_s=args.ref_budget)
+    print(json.dumps({"upd": upd, "el": el}))
+
+
+def all_core_replicas(args):
+    """The reference's march is single-threaded, so one solver cannot use more than one core; what a host CAN do with all
+    its cores is run independent solvers side by side.  Start one replica of the same bounded sample per host thread
+    (separate processes), and report the sum of their rates: an upper bound for a perfectly threaded reference, memory
+    contention included.  Extra information in ``cpu_baseline.all_cores``; the line's ``value`` stays the real thing."""
+    n = args.ref_replicas
+    if n < 0:
+        n = min(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1), 128)
+    if n <= 1:
+        return None
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference-replica", "--workload", args.workload,
+           "--size", str(args.size), "--ref-budget", str(args.ref_budget)]
+    env = dict(os.environ, OMP_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1", MKL_NUM_THREADS="1", RANK="0")
+    procs = [subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, env=env) for _ in range(n)]
+    rate, done = 0.0, 0
+    deadline = time.monotonic() + 4 * args.ref_budget + 180     # one deadline for the whole batch
+    for p in procs:
+        try:
+            out, _ = p.communicate(timeout=max(1.0, deadline - time.monotonic()))
+            d = json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
+            rate += d["upd"] / d["el"]
+            done += 1
+        except Exception:   # a replica that failed or overran is left out of the sum (and of ``cores``)
+            p.kill()
+    if not done:
+        return None
+    return {"value": rate, "unit": UNIT, "cores": done,
+            "sample": f"{done} concurrent independent replicas of the same bounded sample, one single-threaded reference "
+                      f"march per host thread; sum of the replicas' rates"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -364,6 +404,9 @@ def run_reference(args):
     el = sum(v[1] for v in vals)
     value = upd / el
     samples["value"] = value
+    allc = all_core_replicas(args)
+    if allc:
+        samples["all_cores"] = allc
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": el / max(len(vals), 1) * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": wl.dtype,
@@ -384,6 +427,8 @@ def main():
     ap.add_argument("--chunk", type=int, default=5, help="time steps per march() call (one bench step)")
     ap.add_argument("--order", default="rcm", help="multidim cell ordering: none | morton | rcm (BASELINE configs[4] compares morton and rcm: on the lattice-generated bench meshes rcm is 4-5 % faster, profiles/README.md)")
     ap.add_argument("--ref-budget", type=float, default=12.0)
+    ap.add_argument("--ref-replicas", type=int, default=-1,
+                    help="--impl reference: also time this many concurrent replicas (-1 = one per host thread, 0 = off)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -391,6 +436,9 @@ def main():
 
     if args.impl == "reference":
         run_reference(args)
+        return
+    if args.impl == "reference-replica":
+        run_replica(args)
         return
 
     rank, world, local, dist = dist_setup(args.gpus)

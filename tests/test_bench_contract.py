@@ -15,7 +15,8 @@ KEYS = {"impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_
 @pytest.mark.parametrize("workload,size", [("md3d", 0), ("md2d", 0), ("st1d", 200001), ("st1d_burgers", 200001), ("e1d", 200001)])
 def test_reference_arm_json_line(workload, size):
     cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", workload, "--steps", "1",
-           "--warmup", "0", "--ref-budget", "0.5"] + (["--size", str(size)] if size else [])
+           "--warmup", "0", "--ref-budget", "0.5", "--ref-replicas", "2" if workload in ("md3d", "st1d") else "0"] \
+        + (["--size", str(size)] if size else [])
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert res.returncode == 0, res.stderr[-2000:]
     lines = [l for l in res.stdout.splitlines() if l.startswith("{")]
@@ -25,6 +26,11 @@ def test_reference_arm_json_line(workload, size):
     assert d["impl"] == "reference" and d["unit"] == "updates/s" and d["value"] > 0 and d["higher_is_better"] is True
     assert d["vs_baseline"] is None and d["dtype"] == "f64" and d["data"] == "synthetic"
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] == 1
+    if workload in ("md3d", "st1d"):      # the all-host-threads figure: independent replicas of the single-threaded march
+        allc = d["cpu_baseline"]["all_cores"]
+        assert allc["cores"] == 2 and allc["value"] > 0 and allc["unit"] == d["unit"]
+    else:
+        assert "all_cores" not in d["cpu_baseline"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and "workload" in d["config"]
 
 
