@@ -395,6 +395,8 @@ def run_reference(args):
     wl = make_workload(args)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     vals, samples = [], None
+    # each step is a bounded sample; the whole run stays within a few minutes whatever K and W the caller picks
+    args.ref_budget = min(args.ref_budget, max(1.0, 150.0 / max(args.warmup + args.steps, 1)))
     for i in range(args.warmup + args.steps):
         base, upd, el = wl.cpu_run(budget_s=args.ref_budget)
         if i >= args.warmup:
