@@ -11,6 +11,7 @@ The package holds only what the hot path needs:
 * ``euler_field``  ``EulerField`` with device-side derived fields and reductions
 * ``gmsh``         Gmsh MSH 2.2 reader (``solvcon.Gmsh``)
 * ``apps.shocktube`` the Sod shock tube front end (``Euler1DSolver``, ``ShockTube``) over the 1D device core
+* ``apps.linear_scalar`` the linear-scalar demonstration solver (``onedim/linear_scalar.py``)
 * ``apps.obsrefl`` the oblique-shock-reflection application over the device core
 * ``meshgen``      deterministic synthetic meshes for the named benchmark configurations
 * ``decomp`` / ``decomp1d``  domain decomposition and halo exchange (one process per GPU)

@@ -12,6 +12,8 @@ Only the subset the CESE front ends and tests use is mirrored
 * ``a[...] = value`` for scalars, tuples, slices / tuples of slices / ellipsis with
   broadcasting (these address the buffer like numpy does, ghost rows included)
 * the buffer protocol via ``__array__`` so ``np.testing.assert_*`` accept it directly
+* ``add/sub/mul/div`` (+ in-place forms and the Python operators), ``min/max/sum/abs`` -- what front ends apply to
+  solver output (``svr.xctr() / np.pi``)
 
 Everything else of the reference class (sort, matmul, SIMD, plex, ...) is off the march path.
 """
@@ -118,6 +120,51 @@ class SimpleArray:
 
     def tolist(self):
         return self._a.tolist()
+
+    # -- elementwise arithmetic and reductions the front ends use on solver output ---------------------------------
+    # (wrap_SimpleArray.hpp:287-345,470-500: add/sub/mul/div with an array or a scalar, their in-place forms,
+    #  min/max/sum/abs; the Python operators map onto the same calls)
+    @staticmethod
+    def _operand(other):
+        return other._a if isinstance(other, SimpleArray) else other
+
+    def _wrap(self, a):
+        out = SimpleArray(array=a)
+        out._nghost = self._nghost if a.shape[:1] == self._a.shape[:1] else 0
+        return out
+
+    def add(self, other): return self._wrap(self._a + self._operand(other))
+    def sub(self, other): return self._wrap(self._a - self._operand(other))
+    def mul(self, other): return self._wrap(self._a * self._operand(other))
+    def div(self, other): return self._wrap(self._a / self._operand(other))
+
+    def iadd(self, other): self._a += self._operand(other)
+    def isub(self, other): self._a -= self._operand(other)
+    def imul(self, other): self._a *= self._operand(other)
+    def idiv(self, other): self._a /= self._operand(other)
+
+    __add__, __sub__, __mul__, __truediv__ = add, sub, mul, div
+
+    def __iadd__(self, other):
+        self.iadd(other)
+        return self
+
+    def __isub__(self, other):
+        self.isub(other)
+        return self
+
+    def __imul__(self, other):
+        self.imul(other)
+        return self
+
+    def __itruediv__(self, other):
+        self.idiv(other)
+        return self
+
+    def min(self): return self._a.min().item()
+    def max(self): return self._a.max().item()
+    def sum(self): return self._a.sum().item()
+    def abs(self): return self._wrap(np.abs(self._a))
 
     # -- element access ------------------------------------------------------------
     def _shift(self, i):

@@ -71,3 +71,27 @@ def test_slice_assignment_like_the_reference_tests():
     assert tp.tolist() == [7, 7, 7]
     cl[0] = 5            # integer key on a multi-dimensional array: flat offset, SimpleArray::operator[](size_t)
     assert cl.ndarray[0, 0] == 5 and cl[0] == 5
+
+
+def test_arithmetic_and_reductions():
+    """add/sub/mul/div with arrays and scalars, in-place forms, operators, min/max/sum/abs (wrap_SimpleArray.hpp:287-345)."""
+    a = SimpleArray(array=np.array([1.0, -2.0, 4.0]))
+    b = SimpleArray(array=np.array([2.0, 2.0, 0.5]))
+    assert a.add(b).tolist() == [3.0, 0.0, 4.5] and a.add(1.0).tolist() == [2.0, -1.0, 5.0]
+    assert a.sub(b).tolist() == [-1.0, -4.0, 3.5] and a.mul(b).tolist() == [2.0, -4.0, 2.0]
+    assert a.div(b).tolist() == [0.5, -1.0, 8.0] and a.div(2.0).tolist() == [0.5, -1.0, 2.0]
+    assert isinstance(a / np.pi, SimpleArray) and (a / 2.0).tolist() == a.div(2.0).tolist()
+    assert (a + b).tolist() == a.add(b).tolist() and (a - 1.0).tolist() == [0.0, -3.0, 3.0] and (a * b).tolist() == [2.0, -4.0, 2.0]
+    assert a.tolist() == [1.0, -2.0, 4.0]                      # the out-of-place forms leave the operand alone
+    assert (a.min(), a.max(), a.sum()) == (-2.0, 4.0, 3.0) and a.abs().tolist() == [1.0, 2.0, 4.0]
+    buf = a.ndarray
+    a.iadd(b)
+    a.imul(2.0)
+    assert a.tolist() == [6.0, 0.0, 9.0] and a.ndarray is buf   # in place: same buffer
+    a -= b
+    a /= 2.0
+    assert a.tolist() == [2.0, -1.0, 4.25] and a.ndarray is buf
+    g = SimpleArray(array=np.arange(6.0).reshape(3, 2), nghost=1)
+    assert (g * 2.0).nghost == 1 and (g * 2.0)[-1, 1] == 2.0   # ghost bookkeeping follows an elementwise result
+    # numpy on the left keeps working through the buffer protocol
+    assert (np.ones(3) * b).tolist() == [2.0, 2.0, 0.5]
