@@ -433,6 +433,7 @@ def main():
                     help="--impl reference: also time this many concurrent replicas (-1 = one per host thread, 0 = off)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the in-run parity leg (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
@@ -449,8 +450,17 @@ def main():
     lib = _lib.load()
     wl = make_workload(args)
     wl.rank, wl.world, wl.dist, wl.local = rank, world, dist, local
+    # ---- in-run parity leg (before anything is timed): the workload's own generator, IC and BCs at a size the CPU
+    # checker finishes in seconds, device march against oracle/_ref (else the pinned C port), every element compared
+    parity = None
+    if rank == 0 and not args.no_parity and hasattr(wl, "parity"):
+        parity = wl.parity()
+        if not parity["bit_equal"] and parity.get("build", "").startswith("strict"):
+            print(json.dumps({"error": "parity leg failed", "parity": parity}), file=sys.stderr)
+            sys.exit(4)
     wl.build_device()
     barrier(dist, local)
+    steps_marched = 0
 
     # ---- device-resident arm
     wl.resident_begin()
@@ -466,6 +476,7 @@ def main():
         _lib.sync()
     barrier(dist, local)
     launches = _lib.launch_count()
+    steps_marched += (args.warmup + args.steps) * args.chunk
     ms = max_over_ranks(dist, t.ms, local)
     upd_total = sum_over_ranks(dist, float(wl.updates_per_step()), local) * args.steps
     value = upd_total / (ms * 1e-3)
@@ -497,9 +508,22 @@ def main():
         barrier(dist, local)
         el = max_over_ranks(dist, time.perf_counter() - t0, local)
         hi, lo = wl.e2e_bytes()
+        steps_marched += (1 + n_e2e) * args.chunk
         e2e = {"value": sum_over_ranks(dist, float(wl.updates_per_step()), local) * n_e2e / el, "unit": UNIT,
                "h2d_bytes_per_step": hi, "d2h_bytes_per_step": lo, "steps": n_e2e,
                "check": wl.result_check()}
+
+    # ---- the field every timed step ran on must still be a flow field: finite everywhere, density positive
+    check = sum_over_ranks(dist, wl.result_check(), local)
+    health = None
+    if hasattr(wl, "health"):
+        health = wl.health()
+        health["cflo_max"] = max_over_ranks(dist, health["cflo_max"], local)
+        health["rho_min"] = -max_over_ranks(dist, -health["rho_min"], local)
+        health["p_min"] = -max_over_ranks(dist, -health["p_min"], local)
+        health["finite"] = bool(max_over_ranks(dist, 0.0 if health["finite"] else 1.0, local) == 0.0)
+        health["steps_marched"] = steps_marched
+    bad = (not np.isfinite(check)) or (health is not None and (not health["finite"] or not health["rho_min"] > 0.0))
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -511,12 +535,21 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic",
                 "config": wl.describe(world), "clocks": clk.summary(), "e2e": e2e,
                 "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
-                "strict_fp": bool(lib.scg_build_is_strict())}
-        print(json.dumps(line))
+                "strict_fp": bool(lib.scg_build_is_strict()), "parity": parity, "check": check}
+        if health is not None:
+            line["config"]["mesh"].update(health)
+        if bad:
+            # a march that left the physical regime (NaN / non-positive density) is not a measurement
+            print(json.dumps({"error": "the marched field is not finite and positive", "check": repr(check),
+                              "health": {k: repr(v) for k, v in (health or {}).items()}}), file=sys.stderr)
+        else:
+            print(json.dumps(line, allow_nan=False))
         if os.environ.get("SCG_TIMING") == "1":   # diagnostics: per-kernel device times to stderr
             lib.scg_timing_dump()
     if dist is not None:
         dist.destroy_process_group()
+    if bad:
+        sys.exit(3)
 
 
 if __name__ == "__main__":

@@ -147,6 +147,11 @@ SCG_API int scg_hmesh_build_interior(scg_hmesh * m, int do_metric, int do_edge);
 SCG_API int scg_hmesh_build_edge(scg_hmesh * m);                                  /* StaticMesh_interior.cpp:566-609 */
 SCG_API int scg_hmesh_add_bc(scg_hmesh * m, const char * name, const int32_t * faces, int64_t n); /* StaticMesh_boundary.cpp:14-78 */
 SCG_API int scg_hmesh_bc(scg_hmesh * m, int64_t ibc, const char ** name, int32_t ** facn, int64_t * nbound);
+SCG_API int scg_hmesh_bc_rename(scg_hmesh * m, int64_t ibc, const char * name); /* StaticMeshBc::set_name, StaticMesh.hpp:243 */
+/* Tables handed out by scg_hmesh_table stay valid across build_* calls: a re-made table retires its old buffer
+ * instead of freeing it (the reference's views keep the old SimpleArray buffer alive, python/common.hpp:209-215).
+ * scg_hmesh_drop_retired frees those old generations; only for callers that hold no earlier view. */
+SCG_API int scg_hmesh_drop_retired(scg_hmesh * m);
 SCG_API int scg_hmesh_build_boundary(scg_hmesh * m); /* StaticMesh_boundary.cpp:103-182 */
 SCG_API int scg_hmesh_build_ghost(scg_hmesh * m);    /* StaticMesh_boundary.cpp:185-627 */
 

@@ -8,13 +8,13 @@ The package holds only what the hot path needs:
 * ``mesh``         mirror of ``_solvcon.StaticMesh`` (host table builder)
 * ``multidim``     mirror of ``_solvcon.EulerCore``
 * ``gradient_element``  mirror of ``_solvcon.GradientElement`` (host-side probe of one cell)
-* ``euler_field``  ``EulerField`` with device-side derived fields and reductions
 * ``gmsh``         Gmsh MSH 2.2 reader (``solvcon.Gmsh``)
-* ``apps.shocktube`` the Sod shock tube front end (``Euler1DSolver``, ``ShockTube``) over the 1D device core
-* ``apps.linear_scalar`` the linear-scalar demonstration solver (``onedim/linear_scalar.py``)
-* ``apps.obsrefl`` the oblique-shock-reflection application over the device core
 * ``meshgen``      deterministic synthetic meshes for the named benchmark configurations
 * ``decomp`` / ``decomp1d``  domain decomposition and halo exchange (one process per GPU)
+
+The reference's front ends (``solvcon/onedim/euler1d.py``, ``solvcon/onedim/linear_scalar.py``,
+``solvcon/multidim/euler/_field.py``, ``solvcon/pilot/apps/obsrefl``) are NOT re-implemented here: they run unmodified
+over these classes through ``dropin/_solvcon`` (see ``dropin/stage.py``, ``INTEGRATION.md``).
 
 The names of the reference's extension module are available at the package level too (``EulerCore``, ``StaticMesh``,
 ``GradientElement``, ``Gmsh``, ...), resolved lazily so that importing the package stays cheap.
@@ -26,10 +26,10 @@ from . import _lib  # noqa: F401
 from .simplearray import SimpleArray, SimpleArrayFloat64, SimpleArrayInt32  # noqa: F401
 
 __all__ = ["_lib", "SimpleArray", "SimpleArrayFloat64", "SimpleArrayInt32", "EulerCore", "StaticMesh", "StaticMeshBc",
-           "GradientElement", "EulerField", "Gmsh", "Euler1DCore"]
+           "GradientElement", "Gmsh", "Euler1DCore"]
 
 _LAZY = {"EulerCore": "multidim", "StaticMesh": "mesh", "StaticMeshBc": "mesh", "GradientElement": "gradient_element",
-         "EulerField": "euler_field", "Gmsh": "gmsh", "Euler1DCore": "onedim"}
+         "Gmsh": "gmsh", "Euler1DCore": "onedim"}
 
 
 def __getattr__(name):

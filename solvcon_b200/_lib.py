@@ -84,6 +84,8 @@ _SIGNATURES = {
     "scg_hmesh_build_edge": (C.c_int, [C.c_void_p]),
     "scg_hmesh_add_bc": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]),
     "scg_hmesh_bc": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_char_p), C.POINTER(C.c_void_p), I64P]),
+    "scg_hmesh_bc_rename": (C.c_int, [C.c_void_p, C.c_int64, C.c_char_p]),
+    "scg_hmesh_drop_retired": (C.c_int, [C.c_void_p]),
     "scg_hmesh_build_boundary": (C.c_int, [C.c_void_p]),
     "scg_hmesh_build_ghost": (C.c_int, [C.c_void_p]),
     # multidim
@@ -190,17 +192,6 @@ class Timer:
         check(load().scg_timer_stop(C.byref(v)))
         self.ms = v.value
         return False
-
-
-def pinned_empty(shape, dtype=np.float64):
-    """A numpy array backed by page-locked host memory (cudaHostAlloc)."""
-    dtype = np.dtype(dtype)
-    n = int(np.prod(shape)) * dtype.itemsize
-    p = C.c_void_p()
-    check(load().scg_host_alloc(C.byref(p), max(n, 1)))
-    buf = (C.c_char * max(n, 1)).from_address(p.value)
-    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
-    return arr, p
 
 
 def pinned_zeros(shape, dtype=np.float64):

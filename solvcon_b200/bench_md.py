@@ -30,6 +30,34 @@ def dims_3d(ncell_target):
     return nx, ny, nz, 2 * nx // 3, 3 * nz // 4
 
 
+GAMMA, RHO0, P0, MACH_U = 1.4, 1.4, 1.0, 3.0   # sound speed 1, so the inlet speed IS the Mach number
+
+
+def pocket_at_rest(so0n_body, clcnd_body, z_level):
+    """Initial condition of the stepped channel on top of the uniform Mach-3 stream of ``init_solution``: the gas above
+    the step level (``z > z_level``: the tetrahedral block C, which lies in the lee of the solid block) starts AT REST
+    at the stream's density and pressure.  Round 1 started it at Mach 3 too; that gas then runs away from the solid
+    block's back wall, evacuates the corner (rho -> 5e-4, then negative) and the reference's scheme -- whose only guard
+    is the pressure clamp of ``euler_solution.cpp:106-160`` -- goes to NaN after ~105 steps (reproduced on the compiled
+    reference).  With the pocket at rest the stream expands round the corner into still gas: rho >= 0.33, p >= 0.37,
+    cfl <= 0.64 over 600 steps on the compiled reference at 6e4 and 2.5e5 cells.  Both arms (device, CPU reference)
+    call this same function on their own ``so0n`` view, like a reference front end writing its IC through the array
+    views (``tests/multidim/euler/test_field.py:60-62``)."""
+    m = clcnd_body[:, 2] > z_level
+    so0n_body[m, 1:4] = 0.0
+    so0n_body[m, 4] = P0 / (GAMMA - 1.0)
+    return int(m.sum())
+
+
+def field_health(svr):
+    """(cflo max, min density, min pressure) of the newest solution, from the device (derived fields + reduction)."""
+    rho = svr.derived("density")
+    prs = svr.derived("pressure")
+    cfl = svr.derived("cfl")
+    return {"cflo_max": float(cfl.max()), "rho_min": float(rho.min()), "p_min": float(prs.min()),
+            "finite": bool(np.isfinite(rho).all() and np.isfinite(prs).all() and np.isfinite(cfl).all())}
+
+
 def build_case_3d(ncell_target, order="morton", kinds="hpt", log=None):
     t0 = time.perf_counter()
     nx, ny, nz, x1, z1 = dims_3d(ncell_target)
@@ -47,15 +75,18 @@ def build_case_3d(ncell_target, order="morton", kinds="hpt", log=None):
     if os.environ.get("SCG_MD_FUSED"):
         svr.set_fused(int(os.environ["SCG_MD_FUSED"]))
     t3 = time.perf_counter()
-    # IC / BC of SURVEY.md 8d config 4: Mach-3 stream, inlet / non-reflective outlet / slip walls
-    svr.resident(True)
-    svr.init_solution(1.4, 1.4, [3.0, 0.0, 0.0], 1.0)
-    svr.add_inlet(inlet, [1.4, 3.0, 0.0, 0.0, 1.0, 1.4])
+    # IC / BC of SURVEY.md 8d config 4: Mach-3 stream (pocket above the step at rest), inlet / non-reflective outlet /
+    # slip walls
+    svr.init_solution(GAMMA, RHO0, [MACH_U, 0.0, 0.0], P0)
+    npocket = pocket_at_rest(svr.so0n.body, mesh.clcnd.body, z1 * h) if kinds == "hpt" else 0
+    svr.add_inlet(inlet, [RHO0, MACH_U, 0.0, 0.0, P0, GAMMA])
     svr.add_nonrefl(outlet)
     svr.add_slipwall(wall)
+    svr.resident(True)
     svr.bc_soln()
     svr.bc_dsoln()
     info = {"boxes": [nx, ny, nz], "x1": x1, "z1": z1, "h": h, "dt": dt, "ncell": int(mesh.ncell),
+            "cells_at_rest": npocket,
             "nface": int(mesh.nface), "ngstcell": int(mesh.ngstcell),
             "cells_by_type": {"hex": int((cltpn == 5).sum()), "tet": int((cltpn == 6).sum()),
                               "prism": int((cltpn == 7).sum())},
@@ -83,10 +114,14 @@ def build_case_3d_dist(ncell_target, rank, world, local_device, order="morton", 
     hi = np.array([nx * h, world * ny * h, nz * h])
     inlet, outlet, wall = part.physical_boundary_groups(lo, hi)
     core = svr.core
-    core.init_solution(1.4, 1.4, [3.0, 0.0, 0.0], 1.0)
-    core.add_inlet(inlet, [1.4, 3.0, 0.0, 0.0, 1.0, 1.4])
+    core.resident(False)
+    core.init_solution(GAMMA, RHO0, [MACH_U, 0.0, 0.0], P0)
+    if kinds == "hpt":
+        pocket_at_rest(core.so0n.body, mesh.clcnd.body, z1 * h)
+    core.add_inlet(inlet, [RHO0, MACH_U, 0.0, 0.0, P0, GAMMA])
     core.add_nonrefl(outlet)
     core.add_slipwall(wall)
+    core.resident(True)
     core.bc_soln()
     core.bc_dsoln()
     svr.transport = TorchExchange(svr, f"cuda:{local_device}")
@@ -224,6 +259,13 @@ class MD3DWorkload:
         import bench_cpu   # repo root, next to bench.py: the only code on the bench path that touches oracle/
         return bench_cpu.cpu_reference_3d(budget_s, self.kinds)
 
+    def parity(self):
+        import bench_cpu
+        return bench_cpu.parity_3d(self.order, self.kinds)
+
+    def health(self):
+        return field_health(self.dev)
+
 
 
 # ------------------------------------------------------------------------------------------ 2D ---
@@ -252,8 +294,8 @@ def build_case_2d(ncell_target, order="morton"):
         svr.set_fused(int(os.environ["SCG_MD_FUSED"]))
     t3 = time.perf_counter()
     svr.resident(True)
-    svr.init_solution(1.4, 1.4, [3.0, 0.0], 1.0)
-    svr.add_inlet(inlet, [1.4, 3.0, 0.0, 1.0, 1.4])
+    svr.init_solution(GAMMA, RHO0, [MACH_U, 0.0], P0)
+    svr.add_inlet(inlet, [RHO0, MACH_U, 0.0, P0, GAMMA])
     svr.add_nonrefl(outlet)
     svr.add_slipwall(wall)
     svr.bc_soln()
@@ -307,6 +349,10 @@ class MD2DWorkload(MD3DWorkload):
     def cpu_run(self, budget_s=15.0):
         import bench_cpu
         return bench_cpu.cpu_reference_2d(budget_s)
+
+    def parity(self):
+        import bench_cpu
+        return bench_cpu.parity_2d(self.order)
 
 
 def make(args):

@@ -76,6 +76,7 @@ void timing_begin(char const * key)
     cudaEventCreate(&r.a);
     cudaEventCreate(&r.b);
     cudaEventRecord(r.a, g_stream);
+    if (g_timing.size() >= (size_t(1) << 16)) { scg_timing_dump(); } // bounded: flush the records of a long run
     g_timing.push_back(r);
 }
 

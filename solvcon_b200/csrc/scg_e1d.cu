@@ -611,7 +611,7 @@ int scg_e1d_phase(scg_e1d * s, int phase, int odd_plane, int alpha)
 int scg_e1d_march(scg_e1d * s, int alpha, int64_t steps)
 {
     SCG_REQUIRE(alpha == 1 || alpha == 2, "scg_e1d_march: alpha must be 1 or 2");
-    SCG_REQUIRE(steps >= 0, "scg_e1d_march: negative step count");
+    if (steps <= 0) { return 0; } // a non-positive count is a no-op, like the reference's `for (it = 0; it < steps; ++it)`
     // Small grids are launch-latency bound (config 1: 10^4 points, 2000 half steps): replay one
     // captured step as a CUDA graph.  Large grids launch directly.
     bool const use_graph = s->N <= (int64_t(1) << 22) && steps >= 8;

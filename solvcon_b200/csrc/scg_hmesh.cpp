@@ -45,13 +45,41 @@ struct Tab
     std::vector<T> v;
     int64_t rows = 0, cols = 1, ngh = 0;
     bool one_d = false;
+    // A caller may hold zero-copy views of `v` (scg_hmesh_table).  In the reference an ndarray view keeps the old
+    // SimpleArray buffer alive across build_* calls (python/common.hpp:209-215); here a buffer that has been handed
+    // out is RETIRED instead of freed when the table is re-made, so stale views stay readable (they show the old
+    // generation, like the reference's) and writes through them cannot corrupt the heap.
+    bool exported = false;
+    std::vector<std::vector<T>> retired;
+    void retire()
+    {
+        if (exported && !v.empty()) { retired.emplace_back(std::move(v)); }
+        v = std::vector<T>();
+        exported = false;
+    }
     void make(int64_t r, int64_t c, T init, bool is1d = false)
     {
+        retire();
         rows = r;
         cols = c;
         ngh = 0;
         one_d = is1d;
         v.assign(static_cast<size_t>(r * c), init);
+    }
+    // prepend `ng` ghost rows filled with `init` (StaticMesh_boundary.cpp:219-234)
+    void grow_front(int64_t ng, T init)
+    {
+        std::vector<T> nv(static_cast<size_t>((rows + ng) * cols), init);
+        std::copy(v.begin(), v.end(), nv.begin() + ng * cols);
+        retire();
+        v = std::move(nv);
+        rows += ng;
+        ngh = ng;
+    }
+    void drop_retired()
+    {
+        retired.clear();
+        retired.shrink_to_fit();
     }
     T * body() { return v.data() + ngh * cols; }
     T const * body() const { return v.data() + ngh * cols; }
@@ -72,8 +100,8 @@ struct FaceDef
 // StaticMesh_interior.cpp:61-330 (add_quadrilateral .. add_pyramid)
 FaceDef const FACEDEF[9] = {
     {0, {0}, {{0}}},
-    {0, {0}, {{0}}},
-    {0, {0}, {{0}}},
+    /* 1 point (StaticMesh_interior.cpp:27-39) */ {1, {1}, {{1}}},
+    /* 2 line  (StaticMesh_interior.cpp:41-60) */ {2, {1, 1}, {{1}, {2}}},
     /* 3 quadrilateral */ {4, {2, 2, 2, 2}, {{1, 2}, {2, 3}, {3, 4}, {4, 1}}},
     /* 4 triangle      */ {3, {2, 2, 2}, {{1, 2}, {2, 3}, {3, 1}}},
     /* 5 hexahedron    */ {6, {4, 4, 4, 4, 4, 4}, {{1, 4, 3, 2}, {2, 3, 7, 6}, {5, 6, 7, 8}, {1, 5, 8, 4}, {1, 2, 6, 5}, {3, 4, 8, 7}}},
@@ -82,7 +110,11 @@ FaceDef const FACEDEF[9] = {
     /* 8 pyramid       */ {5, {3, 3, 3, 3, 4}, {{1, 5, 4}, {2, 5, 1}, {3, 5, 2}, {4, 5, 3}, {1, 4, 3, 2}}},
 };
 
-inline int face_type_of(int ndim, int nnd) { return 2 == ndim ? 2 /*LINE*/ : (3 == nnd ? 4 /*TRIANGLE*/ : 3 /*QUADRILATERAL*/); }
+inline int face_type_of(int ndim, int nnd)
+{
+    if (1 == nnd) { return 1; /*POINT: the faces of a line cell*/ }
+    return 2 == ndim ? 2 /*LINE*/ : (3 == nnd ? 4 /*TRIANGLE*/ : 3 /*QUADRILATERAL*/);
+}
 inline int cell_nface(int t) { return (t >= 0 && t <= 8) ? FACEDEF[t].nface : 0; }
 
 void parallel_for(int64_t n, std::function<void(int64_t, int64_t)> const & fn)
@@ -359,16 +391,21 @@ void scg_hmesh::cell_centroid(int64_t icl)
 
 void scg_hmesh::calc_metric()
 {
-    parallel_for(nface, [&](int64_t b, int64_t e)
-                 {
-                     for (int64_t f = b; f < e; ++f) { face_centroid_normal(f); }
-                 });
-    // incenter variants (StaticMesh_interior.cpp:771-797, 841-886) are unreachable: m_use_incenter is
-    // never set (StaticMesh.hpp:409)
-    parallel_for(ncell, [&](int64_t b, int64_t e)
-                 {
-                     for (int64_t c = b; c < e; ++c) { cell_centroid(c); }
-                 });
+    // one-dimensional meshes have no face / cell metric (the reference's loops are `if (2 == ndim) .. else if
+    // (3 == ndim)`, StaticMesh_interior.cpp:626-927); only the volume loop below runs, on zeros
+    if (ndim >= 2)
+    {
+        parallel_for(nface, [&](int64_t b, int64_t e)
+                     {
+                         for (int64_t f = b; f < e; ++f) { face_centroid_normal(f); }
+                     });
+        // incenter variants (StaticMesh_interior.cpp:771-797, 841-886) are unreachable: m_use_incenter is
+        // never set (StaticMesh.hpp:409)
+        parallel_for(ncell, [&](int64_t b, int64_t e)
+                     {
+                         for (int64_t c = b; c < e; ++c) { cell_centroid(c); }
+                     });
+    }
     // cell volumes and face orientation (sequential: a face may be re-oriented by the first cell that
     // sees it, StaticMesh_interior.cpp:930-976)
     for (int64_t icl = 0; icl < ncell; ++icl)
@@ -582,6 +619,7 @@ int scg_hmesh_table(scg_hmesh * m, const char * name, void ** ptr, int64_t * row
     if (n == #N)                                       \
     {                                                  \
         *ptr = m->N.v.data();                          \
+        m->N.exported = true;                          \
         *rows = m->N.rows;                             \
         *cols = m->N.cols;                             \
         *nghost = m->N.ngh;                            \
@@ -602,7 +640,7 @@ int scg_hmesh_build_interior(scg_hmesh * m, int do_metric, int do_edge)
     for (int64_t icl = 0; icl < m->ncell; ++icl)
     {
         int const t = m->cltpn(icl);
-        int const nnd = (3 == t) ? 4 : (4 == t) ? 3 : (5 == t) ? 8 : (6 == t) ? 4 : (7 == t) ? 6 : (8 == t) ? 5 : 0;
+        int const nnd = (1 == t) ? 1 : (2 == t) ? 2 : (3 == t) ? 4 : (4 == t) ? 3 : (5 == t) ? 8 : (6 == t) ? 4 : (7 == t) ? 6 : (8 == t) ? 5 : 0;
         for (int q = 1; q <= nnd; ++q)
         {
             int32_t const ind = m->clnds(icl, q);
@@ -664,6 +702,28 @@ int scg_hmesh_bc(scg_hmesh * m, int64_t ibc, const char ** name, int32_t ** facn
     *name = b.name.c_str();
     *facn = b.facn.v.data();
     *nbound = b.facn.rows;
+    return 0;
+}
+
+// StaticMeshBc::set_name (StaticMesh.hpp:243; no validation, like the reference)
+int scg_hmesh_bc_rename(scg_hmesh * m, int64_t ibc, const char * name)
+{
+    HM_REQUIRE(m && name, "scg_hmesh_bc_rename: null argument");
+    HM_REQUIRE(ibc >= 0 && ibc < static_cast<int64_t>(m->bcs.size()), "StaticMesh::bc: index %lld out of range",
+               static_cast<long long>(ibc));
+    m->bcs[static_cast<size_t>(ibc)]->name = name;
+    return 0;
+}
+
+// Free the table generations that were handed out as views and have since been re-made.  Only for callers that
+// know no view of an earlier generation is alive (the bulk path of make_mesh()).
+int scg_hmesh_drop_retired(scg_hmesh * m)
+{
+    HM_REQUIRE(m, "scg_hmesh_drop_retired: null mesh");
+    m->ndcrd.drop_retired(); m->fccnd.drop_retired(); m->fcnml.drop_retired(); m->fcara.drop_retired();
+    m->clcnd.drop_retired(); m->clvol.drop_retired(); m->fctpn.drop_retired(); m->cltpn.drop_retired();
+    m->clgrp.drop_retired(); m->fcnds.drop_retired(); m->fccls.drop_retired(); m->clnds.drop_retired();
+    m->clfcs.drop_retired(); m->ednds.drop_retired(); m->bndfcs.drop_retired();
     return 0;
 }
 
@@ -746,22 +806,8 @@ int scg_hmesh_build_ghost(scg_hmesh * m)
     m->ngstnode = gn;
     m->ngstface = gf;
     m->ngstcell = m->nbound;
-    auto grow_d = [](Tab<double> & t, int64_t ng, double init)
-    {
-        Tab<double> a;
-        a.make(t.rows + ng, t.cols, init, t.one_d);
-        a.ngh = ng;
-        std::copy(t.v.begin(), t.v.end(), a.v.begin() + ng * t.cols);
-        t = std::move(a);
-    };
-    auto grow_i = [](Tab<int32_t> & t, int64_t ng, int32_t init)
-    {
-        Tab<int32_t> a;
-        a.make(t.rows + ng, t.cols, init, t.one_d);
-        a.ngh = ng;
-        std::copy(t.v.begin(), t.v.end(), a.v.begin() + ng * t.cols);
-        t = std::move(a);
-    };
+    auto grow_d = [](Tab<double> & t, int64_t ng, double init) { t.grow_front(ng, init); };
+    auto grow_i = [](Tab<int32_t> & t, int64_t ng, int32_t init) { t.grow_front(ng, init); };
     grow_d(m->ndcrd, gn, 0.0);
     grow_d(m->fccnd, gf, 0.0);
     grow_d(m->fcnml, gf, 0.0);

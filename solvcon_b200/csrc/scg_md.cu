@@ -1956,7 +1956,7 @@ int scg_md_phase(scg_md * s, int phase)
 int scg_md_march(scg_md * s, int64_t steps)
 {
     SCG_REQUIRE(s, "scg_md_march: null solver");
-    SCG_REQUIRE(steps >= 0, "scg_md_march: negative step count");
+    if (steps <= 0) { return 0; } // a non-positive count is a no-op, like the reference's `for (it = 0; it < steps; ++it)`
     for (int64_t it = 0; it < steps; ++it)
     {
         for (int sub = 0; sub < 2; ++sub) // SUBSTEP_RUN, euler.hpp:165

@@ -536,7 +536,7 @@ int scg_st_phase(scg_st * s, int phase, int odd_plane, int alpha)
 int scg_st_march(scg_st * s, int alpha, int64_t steps)
 {
     SCG_REQUIRE(alpha >= 0 && alpha <= 2, "scg_st_march: alpha must be 0, 1 or 2");
-    SCG_REQUIRE(steps >= 0, "scg_st_march: negative step count");
+    if (steps <= 0) { return 0; } // a non-positive count is a no-op, like the reference's `for (it = 0; it < steps; ++it)`
     int const bc = s->halo_mode ? 0 : (F_BC0 | F_BC1);
     for (int64_t it = 0; it < steps; ++it)
     {

@@ -49,14 +49,28 @@ from . import _lib as _libmod
 
 
 class StaticMeshBc:
-    """Mirror of ``StaticMeshBc`` (``StaticMesh.hpp:146-246``): ``name``, ``nbound``, ``facn`` [n,3]."""
+    """Mirror of ``StaticMeshBc`` (``StaticMesh.hpp:146-246``, binding ``wrap_StaticMesh.cpp:33-43``): ``name`` (rw),
+    ``nbound``, ``facn`` [n,3]; one Python object per group, like the reference's ``shared_ptr`` holder."""
 
-    def __init__(self, name, facn):
+    NONAME = "<NONAME>"
+
+    def __init__(self, name, facn, mesh=None, index=-1):
         from .simplearray import SimpleArray
-        self.name = name
+        self._name = name
+        self._mesh, self._index = mesh, index
         # a SimpleArray like in the reference binding, so that ``bc.facn.ndarray[:, 0]`` (obsrefl _driver.py:489-491)
         # and ``bc.facn[i, 0]`` both work
         self.facn = facn if isinstance(facn, SimpleArray) else SimpleArray(array=np.ascontiguousarray(facn))
+
+    @property
+    def name(self):
+        return self._name
+
+    @name.setter
+    def name(self, value):
+        if self._mesh is not None:
+            _libmod.check(self._mesh._lib.scg_hmesh_bc_rename(self._mesh._h, self._index, str(value).encode()))
+        self._name = str(value)
 
     def __len__(self):
         return self.nbound
@@ -81,6 +95,7 @@ class StaticMesh:
         if self._lib.scg_hmesh_create(_C.byref(self._h), int(ndim), int(nnode), int(nface), int(ncell)):
             raise ValueError(self._lib.scg_last_error().decode())
         self._cache = {}
+        self._bcobj = []
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -162,14 +177,23 @@ class StaticMesh:
                 if b.name == key:
                     return b
             raise KeyError(key)
+        key = int(key)
         name, facn, n = _C.c_char_p(), _C.c_void_p(), _C.c_int64()
-        if self._lib.scg_hmesh_bc(self._h, int(key), _C.byref(name), _C.byref(facn), _C.byref(n)):
+        if self._lib.scg_hmesh_bc(self._h, key, _C.byref(name), _C.byref(facn), _C.byref(n)):
             raise IndexError(self._lib.scg_last_error().decode())
-        if n.value:
-            a = np.ctypeslib.as_array(_C.cast(facn, _C.POINTER(_C.c_int32)), shape=(n.value * 3,)).reshape(n.value, 3)
-        else:
-            a = np.zeros((0, 3), dtype=np.int32)
-        return StaticMeshBc(name.value.decode(), a)
+        # one Python object per group (``assertIs(bottom, mh.bc(0))``, tests/test_mesh.py:247-253); the facn rows are a
+        # view of the group's native storage, which is never re-made
+        while len(self._bcobj) <= key:
+            self._bcobj.append(None)
+        if self._bcobj[key] is None:
+            if n.value:
+                a = np.ctypeslib.as_array(_C.cast(facn, _C.POINTER(_C.c_int32)), shape=(n.value * 3,)).reshape(n.value, 3)
+            else:
+                a = np.zeros((0, 3), dtype=np.int32)
+            b = StaticMeshBc(name.value.decode(), a, self, key)
+            b.facn._owner = self
+            self._bcobj[key] = b
+        return self._bcobj[key]
 
     @property
     def bcs(self):
@@ -192,4 +216,6 @@ def make_mesh(ndim, ndcrd, cltpn, clnds, bcs=(), build_edge=False):
         m.add_bc(name, faces)
     m.build_boundary()
     m.build_ghost()
+    # no view of an earlier table generation has left this function: free the generations retired by the builds
+    _libmod.check(m._lib.scg_hmesh_drop_retired(m._h))
     return m

@@ -111,6 +111,8 @@ class Selm:
         s._svr, s._k = self._svr, self._k
         return s
 
+    dup = property(lambda s: s.duplicate())  # wrap_spacetime.hpp:61-62
+
     def _x(self, off=0):
         return float(self._svr.grid.xcoord.ndarray[self._k + off])
 
@@ -132,12 +134,8 @@ class Selm:
 
     def __str__(self):
         plane = "odd" if self.on_odd_plane else "even"
-        return (f"Selm({plane}, index={self.index}, x={_fmt(self.x)}, "
+        return (f"{self._svr._elm_prefix}Selm({plane}, index={self.index}, x={_fmt(self.x)}, "
                 f"xneg={_fmt(self.xneg)}, xpos={_fmt(self.xpos)})")
-
-    def move(self, offset):
-        self._k += int(offset)
-        return self
 
     def move_at(self, offset):
         k = self._k + int(offset)
@@ -148,21 +146,26 @@ class Selm:
         self._k = k
         return self
 
-    def move_left(self): return self.move(-2)
-    def move_right(self): return self.move(2)
-    def move_neg(self): return self.move(-1)
-    def move_pos(self): return self.move(1)
+    # the Python names bind the range-checked forms (wrap_spacetime.hpp:77-91)
+    def move(self, offset): return self.move_at(offset)
+    def move_left(self): return self.move_at(-2)
+    def move_right(self): return self.move_at(2)
+    def move_neg(self): return self.move_at(-1)
+    def move_pos(self): return self.move_at(1)
     def move_left_at(self): return self.move_at(-2)
     def move_right_at(self): return self.move_at(2)
     def move_neg_at(self): return self.move_at(-1)
     def move_pos_at(self): return self.move_at(1)
 
-    def __eq__(self, o): return self._svr is o._svr and self._k == o._k
-    def __ne__(self, o): return not self.__eq__(o)
-    def __lt__(self, o): return self._svr is o._svr and self._k < o._k
-    def __le__(self, o): return self._svr is o._svr and self._k <= o._k
-    def __gt__(self, o): return self._svr is o._svr and self._k > o._k
-    def __ge__(self, o): return self._svr is o._svr and self._k >= o._k
+    # py::self <op> py::self (wrap_spacetime.hpp:54-60): defined between cursors of one kind only; cursors of
+    # different solvers are unordered and unequal (ElementBase comparisons, core.hpp)
+    def _same(self, o): return type(o) is type(self) and self._svr is o._svr
+    def __eq__(self, o): return (self._same(o) and self._k == o._k) if isinstance(o, (Selm, Celm)) else NotImplemented
+    def __ne__(self, o): return (not (self._same(o) and self._k == o._k)) if isinstance(o, (Selm, Celm)) else NotImplemented
+    def __lt__(self, o): return (self._svr is o._svr and self._k < o._k) if type(o) is type(self) else NotImplemented
+    def __le__(self, o): return (self._svr is o._svr and self._k <= o._k) if type(o) is type(self) else NotImplemented
+    def __gt__(self, o): return (self._svr is o._svr and self._k > o._k) if type(o) is type(self) else NotImplemented
+    def __ge__(self, o): return (self._svr is o._svr and self._k >= o._k) if type(o) is type(self) else NotImplemented
     __hash__ = None
 
     def _iv(self, iv):
@@ -240,6 +243,13 @@ class Celm:
         self._svr = svr
         self._k = 3 + 2 * int(index) + (1 if odd_plane else 0)
 
+    def duplicate(self):
+        c = type(self).__new__(type(self))
+        c._svr, c._k = self._svr, self._k
+        return c
+
+    dup = property(lambda s: s.duplicate())
+
     def _x(self, off=0):
         return float(self._svr.grid.xcoord.ndarray[self._k + off])
 
@@ -259,12 +269,8 @@ class Celm:
 
     def __str__(self):
         plane = "odd" if self.on_odd_plane else "even"
-        return (f"Celm({plane}, index={self.index}, x={_fmt(self.x)}, "
+        return (f"{self._svr._elm_prefix}Celm({plane}, index={self.index}, x={_fmt(self.x)}, "
                 f"xneg={_fmt(self.xneg)}, xpos={_fmt(self.xpos)})")
-
-    def move(self, offset):
-        self._k += int(offset)
-        return self
 
     def move_at(self, offset):
         k = self._k + int(offset)
@@ -275,17 +281,26 @@ class Celm:
         self._k = k
         return self
 
-    def move_left(self): return self.move(-2)
-    def move_right(self): return self.move(2)
-    def move_neg(self): return self.move(-1)
-    def move_pos(self): return self.move(1)
+    # the Python names bind the range-checked forms (wrap_spacetime.hpp:77-91)
+    def move(self, offset): return self.move_at(offset)
+    def move_left(self): return self.move_at(-2)
+    def move_right(self): return self.move_at(2)
+    def move_neg(self): return self.move_at(-1)
+    def move_pos(self): return self.move_at(1)
     def move_left_at(self): return self.move_at(-2)
     def move_right_at(self): return self.move_at(2)
     def move_neg_at(self): return self.move_at(-1)
     def move_pos_at(self): return self.move_at(1)
 
-    def __eq__(self, o): return self._svr is o._svr and self._k == o._k
-    def __ne__(self, o): return not self.__eq__(o)
+    # py::self <op> py::self (wrap_spacetime.hpp:54-60): defined between cursors of one kind only; cursors of
+    # different solvers are unordered and unequal (ElementBase comparisons, core.hpp)
+    def _same(self, o): return type(o) is type(self) and self._svr is o._svr
+    def __eq__(self, o): return (self._same(o) and self._k == o._k) if isinstance(o, (Selm, Celm)) else NotImplemented
+    def __ne__(self, o): return (not (self._same(o) and self._k == o._k)) if isinstance(o, (Selm, Celm)) else NotImplemented
+    def __lt__(self, o): return (self._svr is o._svr and self._k < o._k) if type(o) is type(self) else NotImplemented
+    def __le__(self, o): return (self._svr is o._svr and self._k <= o._k) if type(o) is type(self) else NotImplemented
+    def __gt__(self, o): return (self._svr is o._svr and self._k > o._k) if type(o) is type(self) else NotImplemented
+    def __ge__(self, o): return (self._svr is o._svr and self._k >= o._k) if type(o) is type(self) else NotImplemented
     __hash__ = None
 
     def _selm_at_k(self, k):
@@ -319,6 +334,32 @@ class Celm:
     def calc_so1_alpha0(self, iv): return self._calc_so1(iv, 0)
     def calc_so1_alpha1(self, iv): return self._calc_so1(iv, 1)
     def calc_so1_alpha2(self, iv): return self._calc_so1(iv, 2)
+
+
+class SolverElementIterator:
+    """``SolverElementIterator`` (wrap_spacetime.hpp:184-263): walks the cursors of one plane."""
+
+    def __init__(self, svr, odd_plane, selm):
+        self._svr, self._odd, self._selm, self._cur = svr, bool(odd_plane), bool(selm), 0
+
+    @property
+    def nelem(self):
+        g = self._svr.grid
+        return (g.nselm if self._selm else g.ncelm) - (1 if self._odd else 0)
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self._cur >= self.nelem:
+            raise StopIteration
+        e = (self._svr.selm if self._selm else self._svr.celm)(self._cur, self._odd)
+        self._cur += 1
+        return e
+
+    def __str__(self):
+        return (f"SolverElementIterator({'selm' if self._selm else 'celm'}, "
+                f"{'on_odd_plane' if self._odd else 'on_even_plane'}, current={self._cur}, nelem={self.nelem})")
 
 
 class _ScalarSolver:
@@ -457,12 +498,16 @@ class _ScalarSolver:
         return c
 
     def selms(self, odd_plane=False):
-        for it in range(self._grid.nselm - (1 if odd_plane else 0)):
-            yield Selm(self, it, odd_plane)
+        return SolverElementIterator(self, odd_plane, True)
 
     def celms(self, odd_plane=False):
-        for it in range(self._grid.ncelm - (1 if odd_plane else 0)):
-            yield Celm(self, it, odd_plane)
+        return SolverElementIterator(self, odd_plane, False)
+
+    _elm_prefix = ""
+
+    def __str__(self):
+        # operator<<, spacetime/io.cpp:28-32,48-52,68-72
+        return f"{type(self).__name__}(grid={self._grid})"
 
     # -- coherence ------------------------------------------------------------------
     def resident(self, flag=True):
@@ -546,6 +591,7 @@ _add_alpha_methods(_ScalarSolver)
 class LinearScalarSolver(_ScalarSolver):
     """``spacetime::LinearScalarSolver`` (kernel/linear_scalar.hpp:29-43) on the device."""
     _eq = 0
+    _elm_prefix = "LinearScalar"
 
     def __init__(self, grid, time_increment):
         super().__init__(grid, time_increment)
@@ -554,6 +600,7 @@ class LinearScalarSolver(_ScalarSolver):
 class InviscidBurgersSolver(_ScalarSolver):
     """``spacetime::InviscidBurgersSolver`` (kernel/inviscid_burgers.hpp:33-47) on the device."""
     _eq = 1
+    _elm_prefix = "InviscidBurgers"
 
     def __init__(self, grid, time_increment):
         super().__init__(grid, time_increment)
