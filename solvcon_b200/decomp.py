@@ -238,25 +238,45 @@ class TorchExchange:
         import torch.distributed as dist
         self.torch, self.dist, self.s, self.device = torch, dist, solver, torch.device(device)
         self.recvbuf = {}
+        self.cuda = self.device.type == "cuda"
 
     def _view(self, ptr, n):
+        """A tensor over ``n`` doubles at ``ptr`` without a copy: device memory of the library on a GPU, host memory
+        of the solver object when the process group is gloo (the CPU tests of the exchange logic)."""
+        if not self.cuda:
+            import ctypes as C
+            return self.torch.from_numpy(np.ctypeslib.as_array((C.c_double * int(n)).from_address(int(ptr))))
+
         class _Dev:
             pass
         d = _Dev()
         d.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False), "version": 3}
         return self.torch.as_tensor(d, device=self.device)
 
+    def _recvbuf(self, what, n):
+        """Receive buffer of message kind ``what``; allocated once, and the allocation (made on torch's current
+        stream) is complete before the library's stream or the communication stream may touch it."""
+        if what not in self.recvbuf:
+            self.recvbuf[what] = self.torch.zeros(max(1, n), dtype=self.torch.float64, device=self.device)
+            if self.cuda:
+                self.torch.cuda.current_stream(self.device).synchronize()
+        return self.recvbuf[what]
+
+    def _sync_library(self):
+        if self.cuda:
+            from . import _lib
+            _lib.sync()  # the library packs on its own stream
+
     def exchange(self, what):
-        from . import _lib
+        ptr, n = self.s.core.halo_pack(what)
+        return self._exchange_packed(what, ptr, n)
+
+    def _exchange_packed(self, what, ptr, n):
         torch, dist, s = self.torch, self.dist, self.s
         w = s.core.halo_width(what)
-        ptr, n = s.core.halo_pack(what)
-        _lib.sync()  # the library packs on its own stream
-        ops, total = [], 0
-        key = what
-        if key not in self.recvbuf:
-            self.recvbuf[key] = torch.empty(max(1, s.nrecv * w), dtype=torch.float64, device=self.device)
-        rb = self.recvbuf[key]
+        self._sync_library()
+        ops = []
+        rb = self._recvbuf(what, s.nrecv * w)
         sendall = self._view(ptr, max(1, n)) if n else None
         ro = 0
         for q in s.part.neighbours:
@@ -270,7 +290,8 @@ class TorchExchange:
         if ops:
             for req in dist.batch_isend_irecv(ops):
                 req.wait()
-            torch.cuda.synchronize(self.device)
+            if self.cuda:
+                torch.cuda.synchronize(self.device)
         if s.nrecv:
             s.core.halo_unpack(rb.data_ptr(), what)
 
@@ -278,9 +299,11 @@ class TorchExchange:
         """Overlapped exchange (CUDA only): pack on the library stream -> event -> NCCL on a communication stream
         while ``rest()`` (the interior march) is enqueued on the library stream -> event -> unpack."""
         torch, dist, s = self.torch, self.dist, self.s
-        if self.device.type != "cuda":
+        if not self.cuda:
+            # no streams on the CPU: same order of operations, run back to back
+            ptr, n = s.core.halo_pack(what)
             rest()
-            return self.exchange(what)
+            return self._exchange_packed(what, ptr, n)
         if getattr(self, "_lib_stream", None) is None:
             from . import _lib
             self._lib_stream = torch.cuda.ExternalStream(int(_lib.load().scg_stream_handle()), device=self.device)
@@ -291,9 +314,7 @@ class TorchExchange:
         ptr, n = s.core.halo_pack(what)
         self._ev_packed.record(self._lib_stream)
         rest()  # interior cells + boundary kernels, enqueued behind the pack on the library stream
-        if what not in self.recvbuf:
-            self.recvbuf[what] = torch.empty(max(1, s.nrecv * w), dtype=torch.float64, device=self.device)
-        rb = self.recvbuf[what]
+        rb = self._recvbuf(what, s.nrecv * w)
         sendall = self._view(ptr, max(1, n)) if n else None
         ops, ro = [], 0
         for q in s.part.neighbours:
@@ -317,20 +338,16 @@ class TorchExchange:
 
 # ------------------------------------------------------------------------------------- solver ---
 
-class DistEulerCore:
-    """``EulerCore`` of one partition: the device solver of the local mesh plus the halo bookkeeping.
+class HaloSolver:
+    """One partition's solver plus its halo bookkeeping.  ``core`` is anything with the halo interface of
+    :class:`solvcon_b200.multidim.EulerCore` (``halo_set, halo_width, halo_pack, halo_unpack, substep_local,
+    substep_interface, substep_rest``): the device core in the product (:class:`DistEulerCore`), a host-memory double
+    over the CPU checker in the gloo tests of the exchange logic.
     ``march(steps)`` = per substep: local substep on the owned cells, then the halo exchange."""
 
-    def __init__(self, part: Partition, time_increment, order="morton"):
-        from .multidim import EulerCore
+    def __init__(self, part: Partition, core):
         self.part = part
-        mesh = part.build_mesh()
-        own = part.owned.astype(np.int8).copy()
-        snd0 = part.send_list()
-        if len(snd0):
-            own[snd0] = 2  # interface cells: marched first so that their message travels during the interior march
-        self.core = EulerCore(mesh, time_increment, order=order, owned=own)
-        self.core.resident(True)
+        self.core = core
         snd, rcv = part.send_list(), part.recv_list()
         self.nsend, self.nrecv = len(snd), len(rcv)
         self.core.halo_set(snd, rcv)
@@ -341,6 +358,31 @@ class DistEulerCore:
             o += k
         self.transport = None
         self._scratch = None
+
+    def march(self, steps):
+        split = getattr(self.transport, "exchange_split", None)
+        for _ in range(2 * int(steps)):
+            if split is not None:
+                self.core.substep_interface()
+                split(0, self.core.substep_rest)
+            else:
+                self.core.substep_local()
+                self.transport.exchange(0)
+
+
+class DistEulerCore(HaloSolver):
+    """``EulerCore`` of one partition: the device solver of the local mesh plus the halo bookkeeping."""
+
+    def __init__(self, part: Partition, time_increment, order="morton"):
+        from .multidim import EulerCore
+        mesh = part.build_mesh()
+        own = part.owned.astype(np.int8).copy()
+        snd0 = part.send_list()
+        if len(snd0):
+            own[snd0] = 2  # interface cells: marched first so that their message travels during the interior march
+        core = EulerCore(mesh, time_increment, order=order, owned=own)
+        core.resident(True)
+        super().__init__(part, core)
 
     def unpack_segments(self, segs, what):
         """LocalExchange helper: unpack from several source buffers (one per neighbour, in neighbour order)."""
@@ -368,13 +410,3 @@ class DistEulerCore:
 
     def download_state(self):
         self.core.sync_to_host()
-
-    def march(self, steps):
-        split = getattr(self.transport, "exchange_split", None)
-        for _ in range(2 * int(steps)):
-            if split is not None:
-                self.core.substep_interface()
-                split(0, self.core.substep_rest)
-            else:
-                self.core.substep_local()
-                self.transport.exchange(0)

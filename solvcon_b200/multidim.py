@@ -96,14 +96,20 @@ class EulerCore:
     def __init__(self, mesh, time_increment, order="morton", owned=None):
         self._lib = _lib.load()
         self._mesh = mesh
-        self._dmesh = mesh if isinstance(mesh, DeviceMesh) else DeviceMesh(mesh, order, owned)
-        dm = self._dmesh
-        self._ndim, self._ncell, self._ngst = dm.ndim, dm.ncell, dm.ngstcell
-        self._neq = self._ndim + 2
         self._dt = float(time_increment)
         self._h = C.c_void_p()
-        if self._lib.scg_md_create(C.byref(self._h), dm._h, self._dt):
-            _raise(_lib.ScgError)
+        if not isinstance(mesh, DeviceMesh) and int(mesh.ncell) == 0:
+            # an empty mesh constructs (tests/test_euler.py:12-13 of the reference): zero-row arrays, nothing to march
+            self._dmesh = None
+            self._ndim, self._ncell, self._ngst = int(mesh.ndim), 0, 0
+            self._neq = self._ndim + 2
+        else:
+            self._dmesh = mesh if isinstance(mesh, DeviceMesh) else DeviceMesh(mesh, order, owned)
+            dm = self._dmesh
+            self._ndim, self._ncell, self._ngst = dm.ndim, dm.ncell, dm.ngstcell
+            self._neq = self._ndim + 2
+            if self._lib.scg_md_create(C.byref(self._h), dm._h, self._dt):
+                _raise(_lib.ScgError)
         T, nd, neq, nc, ng = self._ncell + self._ngst, self._ndim, self._neq, self._ncell, self._ngst
         # allocation shapes: euler_ce.cpp:31-60, euler_solution.cpp:19-41.  Host arrays are materialised
         # on first access (a 10^8-cell mesh never needs the padded host geometry unless the caller asks).
@@ -124,9 +130,9 @@ class EulerCore:
         a = self._a.get(name)
         if a is None:
             shape, ng = self._shapes[name]
-            a = SimpleArray(shape, 0.0, nghost=ng, pinned=name in ARRAY_IDS)
+            a = SimpleArray(shape, 0.0, nghost=ng, pinned=name in ARRAY_IDS and self._h.value is not None)
             self._a[name] = a
-            if name in ARRAY_IDS:
+            if name in ARRAY_IDS and self._h.value is not None:
                 _lib.check(self._lib.scg_md_download(self._h, ARRAY_IDS[name], _lib.ptr(a.ndarray)))
             if name in _GEOMETRY:
                 self._geo_seen[name] = a.ndarray.copy()

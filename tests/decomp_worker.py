@@ -1,7 +1,9 @@
-"""Worker of tests/test_decomp_gloo.py: one rank of a world_size-N gloo job.  Each rank marches ITS partition
-with the CPU checker (oracle port) as the compute engine and exchanges halos through torch.distributed, then
-compares its owned cells with the undecomposed run.  Exercises the host side of solvcon_b200.decomp:
-partitioning, the two halo layers, list ordering on both sides of every rank pair, and the exchange."""
+"""Worker of tests/test_decomp_gloo.py: one rank of a world_size-N gloo job.  Each rank marches ITS partition through
+the PRODUCT's ``solvcon_b200.decomp.HaloSolver`` + ``TorchExchange`` (gloo): the very classes, message layout
+(neighbour order, send offsets, one grouped isend/irecv per exchange) and march loop (``exchange`` and the two-stage
+``exchange_split`` ordering) that run over NCCL on the GPUs.  Only the compute engine differs: a host-memory double of
+the device core's halo interface over the CPU checker (``HostHaloCore`` below; test infrastructure).  Every rank
+compares its owned cells with the undecomposed run, bit for bit."""
 import os
 import sys
 
@@ -37,20 +39,73 @@ def setup(b, svr, mesh, groups, ndim, ctr, span):
     svr.phase(b.MD_BC_DSOLN)
 
 
+class HostHaloCore:
+    """The halo interface of ``solvcon_b200.multidim.EulerCore`` (halo_set / halo_width / halo_pack / halo_unpack /
+    substep_local / substep_interface / substep_rest) over the CPU checker, buffers in host memory."""
+
+    def __init__(self, b, svr, ndim, owned):
+        self.b, self.svr, self.ndim, self.neq = b, svr, ndim, ndim + 2
+        self.owned = np.asarray(owned)
+        self.calls = []
+
+    def halo_set(self, send_cells, recv_cells):
+        self.snd, self.rcv = np.asarray(send_cells, dtype=np.int64), np.asarray(recv_cells, dtype=np.int64)
+        self.buf = {w: np.zeros(max(1, len(self.snd) * self.halo_width(w))) for w in (0, 1)}
+
+    def halo_width(self, what=0):
+        return self.neq * (1 + self.ndim) if what == 0 else self.ndim + 1
+
+    def _fields(self, what):
+        if what == 0:
+            return [("so0n", slice(None)), ("so1n", slice(None))]
+        return [("cecnd", slice(0, self.ndim)), ("gamma", slice(None))]
+
+    def halo_pack(self, what=0):
+        rows = np.concatenate([self.svr.body(n)[self.snd].reshape(len(self.snd), -1)[:, sl] for n, sl in self._fields(what)], axis=1)
+        self.buf[what][:rows.size] = rows.ravel()
+        self.calls.append(("pack", what))
+        return self.buf[what].ctypes.data, rows.size
+
+    def halo_unpack(self, ptr, what=0):
+        import ctypes as C
+        w = self.halo_width(what)
+        a = np.ctypeslib.as_array((C.c_double * (len(self.rcv) * w)).from_address(int(ptr))).reshape(len(self.rcv), w)
+        col = 0
+        for n, sl in self._fields(what):
+            tgt = self.svr.body(n)
+            k = tgt[self.rcv].reshape(len(self.rcv), -1)[:, sl].shape[1]
+            tgt.reshape(len(tgt), -1)[self.rcv, sl] = a[:, col:col + k]
+            col += k
+        self.calls.append(("unpack", what))
+
+    def substep_local(self):
+        self.svr.phase(self.b.MD_SUBSTEP)
+        self.calls.append(("substep",))
+
+    # the checker has no cell ranges: the whole substep runs in the first stage, the second is empty.  What the test
+    # pins is the ORDER the product's march drives (interface -> pack -> rest -> exchange -> unpack).
+    def substep_interface(self):
+        self.svr.phase(self.b.MD_SUBSTEP)
+        self.calls.append(("iface",))
+
+    def substep_rest(self):
+        self.calls.append(("rest",))
+
+
 def main():
     import torch
     import torch.distributed as dist
     from cases import md_mesh_case
     from oracle import bridge as b
     from solvcon_b200 import meshgen
-    from solvcon_b200.decomp import make_partitions, rcb_partition
+    from solvcon_b200.decomp import HaloSolver, TorchExchange, make_partitions, rcb_partition
     from solvcon_b200.mesh import make_mesh
 
     name, steps = sys.argv[1], int(sys.argv[2])
+    split = len(sys.argv) > 3 and sys.argv[3] == "split"
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
     ndim, ndcrd, cltpn, clnds = md_mesh_case(name)
-    neq = ndim + 2
     lo, hi = ndcrd.min(axis=0), ndcrd.max(axis=0)
     h = (np.prod(hi - lo) / len(cltpn)) ** (1.0 / ndim)
     dt = 0.05 * h
@@ -61,41 +116,29 @@ def main():
     ref.phase(b.MD_PREPARE_CE)
     setup(b, ref, gm, meshgen.boundary_groups(ndim, gm.fccnd.body, gm.fccls.body, gm.nface, lo, hi), ndim, ctr, span)
     ref.march(steps)
-    # my partition
+    # my partition, marched by the product's HaloSolver over the product's TorchExchange
     part = rcb_partition(gm.clcnd.body, world)
     p = make_partitions(ndim, ndcrd, cltpn, clnds, part, ranks=[rank])[rank]
     lm = p.build_mesh()
     svr = b.PortEuler(lm.tables(), ndim, dt)
     svr.phase(b.MD_PREPARE_CE)
     setup(b, svr, lm, p.physical_boundary_groups(lo, hi), ndim, ctr, span)
-
-    def exchange(fields):
-        """fields: list of (array name, column slice or None); one message per neighbour."""
-        reqs, recvs = [], []
-        for q in p.neighbours:
-            snd = np.concatenate([svr.body(n)[p.send[q]].reshape(len(p.send[q]), -1)[:, sl] for n, sl in fields], axis=1)
-            t = torch.from_numpy(np.ascontiguousarray(snd))
-            reqs.append(dist.isend(t, q))
-            r = torch.empty((len(p.recv[q]), snd.shape[1]), dtype=torch.float64)
-            reqs.append(dist.irecv(r, q))
-            recvs.append((q, r, t))
-        for r in reqs:
-            r.wait()
-        for q, r, _ in recvs:
-            a, col = r.numpy(), 0
-            for n, sl in fields:
-                tgt = svr.body(n)
-                w = tgt[p.recv[q]].reshape(len(p.recv[q]), -1)[:, sl].shape[1]
-                tgt.reshape(len(tgt), -1)[p.recv[q], sl] = a[:, col:col + w]
-                col += w
-
-    exchange([("cecnd", slice(0, ndim)), ("gamma", slice(None))])   # what = 1: solution point + gamma
-    exchange([("so0n", slice(None)), ("so1n", slice(None))])          # what = 0: state
-    for _ in range(2 * steps):
-        svr.phase(b.MD_SUBSTEP)
-        exchange([("so0n", slice(None)), ("so1n", slice(None))])
+    core = HostHaloCore(b, svr, ndim, p.owned)
+    hs = HaloSolver(p, core)
+    hs.transport = TorchExchange(hs, "cpu")
+    hs.transport.exchange(1)   # solution point + gamma of the halo copies, once
+    hs.transport.exchange(0)   # state
+    if not split:
+        hs.transport.exchange_split = None   # plain path: substep_local + exchange
+    core.calls.clear()
+    hs.march(steps)
+    want = ([("iface",), ("pack", 0), ("rest",), ("unpack", 0)] if split else [("substep",), ("pack", 0), ("unpack", 0)])
+    if not p.recv:
+        want = [c for c in want if c[0] != "unpack"]
+    ok = core.calls == want * (2 * steps)
+    if not ok:
+        print(f"rank {rank}: unexpected call order {core.calls[:8]}", flush=True)
     own = p.owned.astype(bool)
-    ok = True
     for n in ("so0n", "so1n", "cflo", "cflc"):
         if not np.array_equal(svr.body(n)[own], ref.body(n)[p.gid[own]]):
             ok = False

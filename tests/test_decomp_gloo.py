@@ -1,5 +1,7 @@
-"""World_size-2/3 gloo jobs on the CPU: the domain decomposition + halo exchange reproduce the undecomposed
-march bit for bit (compute engine: the CPU checker; the GPU twin of this test is tests/test_gpu_decomp.py)."""
+"""World_size-2/3 gloo jobs on the CPU: the product's HaloSolver + TorchExchange (solvcon_b200/decomp.py: the classes
+that run over NCCL on the GPUs) reproduce the undecomposed march bit for bit, plain and two-stage (overlap) order.
+Compute engine: the CPU checker behind a host double of the device core's halo interface (tests/decomp_worker.py);
+the single-GPU twin of this test is tests/test_gpu_decomp.py, the NCCL one is bench.py's multi-rank parity leg."""
 import os
 import subprocess
 import sys
@@ -46,12 +48,12 @@ def test_partition_lists_are_consistent():
     assert owned_total == len(cltpn)
 
 
-@pytest.mark.parametrize("name,world", [("mixed3d", 2), ("mixed2d", 3)])
-def test_gloo_march_bit_identical(bridge, name, world):
+@pytest.mark.parametrize("name,world,mode", [("mixed3d", 2, "plain"), ("mixed2d", 3, "plain"), ("mixed3d", 3, "split")])
+def test_gloo_march_bit_identical(bridge, name, world, mode):
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-           "--master-addr", "127.0.0.1", "--master-port", str(29400 + world + len(name)),
-           os.path.join(HERE, "decomp_worker.py"), name, "6"]
+           "--master-addr", "127.0.0.1", "--master-port", str(29400 + world + len(name) + (7 if mode == "split" else 0)),
+           os.path.join(HERE, "decomp_worker.py"), name, "6", mode]
     res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
 

@@ -240,25 +240,26 @@ def test_scalar_slabs_bit_identical(gpu, bridge, eq, nparts):
 
 
 def test_celm_selm_cursors_known_answers(gpu):
-    """tests/test_spacetime_solution.py:75-152 of the reference: cursor strings and the bounds messages."""
+    """tests/test_spacetime_solution.py:75-152 of the reference: cursor strings (with the solver kind's prefix,
+    spacetime/io.cpp:74-86) and the bounds messages."""
     from solvcon_b200 import spacetime as st
     sol = st.LinearScalarSolver(st.Grid(xmin=0.0, xmax=10.0, nelm=10), 0.2)
     with pytest.raises(IndexError, match=r"Field::celm_at\(ielm=-1, odd_plane=0\): xindex = 1 outside the interval \[2, 23\)"):
         sol.celm(-1, odd_plane=False)
-    assert str(sol.celm(-1, odd_plane=True)) == "Celm(odd, index=-1, x=0, xneg=-0.5, xpos=0.5)"
-    assert str(sol.celm(0)) == "Celm(even, index=0, x=0.5, xneg=0, xpos=1)"
-    assert str(sol.celm(ielm=0, odd_plane=True)) == "Celm(odd, index=0, x=1, xneg=0.5, xpos=1.5)"
-    assert str(sol.celm(9, odd_plane=False)) == "Celm(even, index=9, x=9.5, xneg=9, xpos=10)"
-    assert str(sol.celm(9, odd_plane=True)) == "Celm(odd, index=9, x=10, xneg=9.5, xpos=10.5)"
+    assert str(sol.celm(-1, odd_plane=True)) == "LinearScalarCelm(odd, index=-1, x=0, xneg=-0.5, xpos=0.5)"
+    assert str(sol.celm(0)) == "LinearScalarCelm(even, index=0, x=0.5, xneg=0, xpos=1)"
+    assert str(sol.celm(ielm=0, odd_plane=True)) == "LinearScalarCelm(odd, index=0, x=1, xneg=0.5, xpos=1.5)"
+    assert str(sol.celm(9, odd_plane=False)) == "LinearScalarCelm(even, index=9, x=9.5, xneg=9, xpos=10)"
+    assert str(sol.celm(9, odd_plane=True)) == "LinearScalarCelm(odd, index=9, x=10, xneg=9.5, xpos=10.5)"
     with pytest.raises(IndexError, match=r"Field::celm_at\(ielm=10, odd_plane=0\): xindex = 23 outside the interval \[2, 23\)"):
         sol.celm(10)
     with pytest.raises(IndexError, match=r"Field::selm_at\(ielm=-1, odd_plane=0\): xindex = 0 outside the interval \[1, 24\)"):
         sol.selm(-1, odd_plane=False)
-    assert str(sol.selm(-1, odd_plane=True)) == "Selm(odd, index=-1, x=-0.5, xneg=-1, xpos=0)"
-    assert str(sol.selm(0, odd_plane=False)) == "Selm(even, index=0, x=0, xneg=-0.5, xpos=0.5)"
-    assert str(sol.selm(0, odd_plane=True)) == "Selm(odd, index=0, x=0.5, xneg=0, xpos=1)"
-    assert str(sol.selm(10, odd_plane=False)) == "Selm(even, index=10, x=10, xneg=9.5, xpos=10.5)"
-    assert str(sol.selm(10, odd_plane=True)) == "Selm(odd, index=10, x=10.5, xneg=10, xpos=11)"
+    assert str(sol.selm(-1, odd_plane=True)) == "LinearScalarSelm(odd, index=-1, x=-0.5, xneg=-1, xpos=0)"
+    assert str(sol.selm(0, odd_plane=False)) == "LinearScalarSelm(even, index=0, x=0, xneg=-0.5, xpos=0.5)"
+    assert str(sol.selm(0, odd_plane=True)) == "LinearScalarSelm(odd, index=0, x=0.5, xneg=0, xpos=1)"
+    assert str(sol.selm(10, odd_plane=False)) == "LinearScalarSelm(even, index=10, x=10, xneg=9.5, xpos=10.5)"
+    assert str(sol.selm(10, odd_plane=True)) == "LinearScalarSelm(odd, index=10, x=10.5, xneg=10, xpos=11)"
     with pytest.raises(IndexError, match=r"Field::selm_at\(ielm=11, odd_plane=0\): xindex = 24 outside the interval \[1, 24\)"):
         sol.selm(11)
     nx = (sol.grid.ncelm + sol.grid.BOUND_COUNT) * 2 + 1
