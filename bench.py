@@ -189,9 +189,15 @@ class E1DWorkload:
 def make_workload(args):
     if args.workload == "e1d":
         return E1DWorkload(args.size or 100_000_001, args.chunk)
+    if args.workload == "sod":
+        # BASELINE.json configs[0]: 1e4 points x 1000 steps -- launch-latency bound, reported as a latency figure
+        wl = E1DWorkload(args.size or 10_001, args.chunk if args.chunk >= 100 else 1000)
+        wl.name = "e1d_sod_config0"
+        wl.dt = 1.6e-4
+        return wl
     if args.workload in ("st1d", "st1d_burgers"):
         return ST1DWorkload(args.size or 1_000_000_001, args.chunk, eq=1 if args.workload.endswith("burgers") else 0)
-    if args.workload in ("md3d", "md2d"):
+    if args.workload in ("md3d", "md2d", "md3d_strong"):
         from solvcon_b200 import bench_md  # noqa
         return bench_md.make(args)
     raise SystemExit(f"unknown workload {args.workload}")
@@ -418,6 +424,142 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def measure(wl, steps, warmup, args, rank, world, local, dist, e2e=True, cpu=False):
+    """Build the workload and measure it: device-resident arm (CUDA events on the library stream, max over ranks),
+    roofline of the dominant kernel, end-to-end arm with host arrays, field health, optional CPU baseline."""
+    from solvcon_b200 import _lib
+    wl.build_device()
+    barrier(dist, local)
+    steps_marched = 0
+    chunk = wl.chunk
+
+    # ---- device-resident arm
+    wl.resident_begin()
+    for _ in range(warmup):
+        wl.resident_step()
+    _lib.sync()
+    barrier(dist, local)
+    _lib.launch_count(reset=True)
+    with ClockSampler(local) as clk:
+        with _lib.Timer() as t:
+            for _ in range(steps):
+                wl.resident_step()
+        _lib.sync()
+    barrier(dist, local)
+    launches = _lib.launch_count()
+    steps_marched += (warmup + steps) * chunk
+    ms = max_over_ranks(dist, t.ms, local)
+    upd_total = sum_over_ranks(dist, float(wl.updates_per_step()), local) * steps
+    value = upd_total / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (this rank's launches, timed above on the library stream)
+    peak, peak_src = measured_peak()
+    n_dom = wl.launches_per_step() * steps
+    ach = wl.alg_bytes_per_launch() / (t.ms * 1e-3 / n_dom) / 1e9
+    roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            "traffic": getattr(wl, "ncu_traffic", None), "peak_source": peak_src,
+            "kernel": getattr(wl, "dominant_kernel", "e1d_half_kernel"),
+            "alg_bytes_per_launch": wl.alg_bytes_per_launch(),
+            "avg_launch_ms": t.ms / n_dom}
+    clocks = clk.summary()
+    roof64 = wl.roofline_fp64(t.ms * 1e-3 / n_dom, clocks) if callable(getattr(wl, "roofline_fp64", None)) else None
+
+    # ---- end-to-end arm through the public class with host arrays
+    e2e_res = None
+    if e2e:
+        if hasattr(wl.dev, "materialise"):
+            wl.dev.materialise()
+        if getattr(wl, "dist_svr", None) is None:
+            wl.dev.resident(False)
+        wl.e2e_step()
+        n_e2e = max(1, min(steps, 3))
+        barrier(dist, local)
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            wl.e2e_step()
+        _lib.sync()
+        barrier(dist, local)
+        el = max_over_ranks(dist, time.perf_counter() - t0, local)
+        hi, lo = wl.e2e_bytes()
+        steps_marched += (1 + n_e2e) * chunk
+        e2e_res = {"value": sum_over_ranks(dist, float(wl.updates_per_step()), local) * n_e2e / el, "unit": UNIT,
+                   "h2d_bytes_per_step": hi, "d2h_bytes_per_step": lo, "steps": n_e2e,
+                   "check": wl.result_check()}
+
+    # ---- the field every timed step ran on must still be a flow field: finite everywhere, density positive
+    check = sum_over_ranks(dist, wl.result_check(), local)
+    health = None
+    if hasattr(wl, "health"):
+        health = wl.health()
+        health["cflo_max"] = max_over_ranks(dist, health["cflo_max"], local)
+        health["rho_min"] = -max_over_ranks(dist, -health["rho_min"], local)
+        health["p_min"] = -max_over_ranks(dist, -health["p_min"], local)
+        health["finite"] = bool(max_over_ranks(dist, 0.0 if health["finite"] else 1.0, local) == 0.0)
+        health["steps_marched"] = steps_marched
+    bad = (not np.isfinite(check)) or (health is not None and (not health["finite"] or not health["rho_min"] > 0.0))
+
+    cpu_res = None
+    if cpu:
+        cpu_res, _, _ = wl.cpu_run(budget_s=args.ref_budget)
+    config = wl.describe(world)
+    if health is not None and "mesh" in config:
+        config["mesh"].update(health)
+    return {"value": value, "ms_per_step": ms / steps, "scaling": "strong" if getattr(wl, "strong", False) else "weak",
+            "dtype": wl.dtype, "config": config, "clocks": clocks, "e2e": e2e_res, "gpu_launches": int(launches),
+            "roofline": roof, "roofline_fp64": roof64, "cpu_baseline": cpu_res, "check": check, "health": health,
+            "bad": bool(bad)}
+
+
+def run_subs(args, rank, world, local, dist):
+    """The other configurations BASELINE.json names, measured in the same run right after the headline workload and
+    attached to its JSON line as ``sub_results`` (device-resident arm + roofline; each bounded to a few steps).
+    One GPU: configs[1] (1D scalar, 1e9 points, linear and Burgers), the 1D Euler core at 1e8 points, configs[0]
+    (Sod tube, 1e4 points x 1000 steps, a latency number: wall time of the whole march), configs[2] (2D, 2e7 cells).
+    More than one GPU: configs[3], the strong-scaling case (ONE 1e8-cell mesh cut into one part per rank)."""
+    import copy
+    import gc
+    out = []
+
+    def one(workload, steps, chunk, size=0, e2e=False, extra=None):
+        a = copy.copy(args)
+        a.workload, a.size, a.chunk = workload, size, chunk
+        t0 = time.perf_counter()
+        try:
+            wl = make_workload(a)
+            wl.rank, wl.world, wl.dist, wl.local = rank, world, dist, local
+            par = wl.parity() if (rank == 0 and world == 1 and hasattr(wl, "parity") and not args.no_parity) else None
+            r = measure(wl, steps, 3, a, rank, world, local, dist, e2e=e2e, cpu=False)
+            entry = {"workload": wl.name, "value": r["value"], "unit": UNIT, "ms_per_step": r["ms_per_step"],
+                     "steps": steps, "warmup": 3, "scaling": r["scaling"], "n_gpus": world,
+                     "roofline": {k: r["roofline"][k] for k in ("achieved", "peak", "frac", "unit", "kernel")},
+                     "clocks": r["clocks"], "check": r["check"], "config": r["config"], "gpu_launches": r["gpu_launches"],
+                     "bad": r["bad"]}
+            if r.get("roofline_fp64"):
+                entry["roofline_fp64"] = r["roofline_fp64"]
+            if r["e2e"]:
+                entry["e2e"] = r["e2e"]
+            if par is not None:
+                entry["parity"] = par
+            if extra:
+                entry.update(extra(wl))
+            del wl
+        except Exception as exc:   # a sub-result that cannot run says so; the headline line is still printed
+            entry = {"workload": workload, "error": f"{type(exc).__name__}: {exc}"}
+        entry["wall_s"] = round(time.perf_counter() - t0, 1)
+        gc.collect()
+        out.append(entry)
+
+    if world == 1:
+        one("st1d", 4, 5)
+        one("st1d_burgers", 4, 5)
+        one("e1d", 4, 5)
+        one("sod", 3, 1000)
+        one("md2d", 6, 5)
+    else:
+        one("md3d_strong", max(4, min(args.steps, 10)), args.chunk)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -434,6 +576,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the in-run parity leg (profiling runs)")
+    ap.add_argument("--no-subs", action="store_true", help="default workload only: skip the sub_results legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
@@ -458,90 +601,47 @@ def main():
         if not parity["bit_equal"] and parity.get("build", "").startswith("strict"):
             print(json.dumps({"error": "parity leg failed", "parity": parity}), file=sys.stderr)
             sys.exit(4)
-    wl.build_device()
-    barrier(dist, local)
-    steps_marched = 0
+    # ---- multi-rank parity leg: a small case cut into one part per rank, marched over the real NCCL transport
+    # (overlapped exchange), every rank's cells compared on rank 0 with the undecomposed device run
+    if world > 1 and not args.no_parity and args.workload in ("md3d", "md3d_strong"):
+        from solvcon_b200 import bench_md
+        nccl_parity, ok = bench_md.nccl_parity_3d(rank, world, local, dist, args.order)
+        if rank == 0:
+            parity = {"single_rank": parity, "decomposed": nccl_parity}
+        if not ok and bool(lib.scg_build_is_strict()):
+            if rank == 0:
+                print(json.dumps({"error": "multi-rank parity leg failed", "parity": parity}), file=sys.stderr)
+            dist.destroy_process_group()
+            sys.exit(4)
+    res = measure(wl, args.steps, args.warmup, args, rank, world, local, dist, e2e=not args.no_e2e,
+                  cpu=(rank == 0 and world == 1 and not args.no_cpu))
+    bad = res["bad"]
 
-    # ---- device-resident arm
-    wl.resident_begin()
-    for _ in range(args.warmup):
-        wl.resident_step()
-    _lib.sync()
-    barrier(dist, local)
-    _lib.launch_count(reset=True)
-    with ClockSampler(local) as clk:
-        with _lib.Timer() as t:
-            for _ in range(args.steps):
-                wl.resident_step()
-        _lib.sync()
-    barrier(dist, local)
-    launches = _lib.launch_count()
-    steps_marched += (args.warmup + args.steps) * args.chunk
-    ms = max_over_ranks(dist, t.ms, local)
-    upd_total = sum_over_ranks(dist, float(wl.updates_per_step()), local) * args.steps
-    value = upd_total / (ms * 1e-3)
-
-    # ---- roofline of the dominant kernel (this rank's launches, timed above on the library stream)
-    peak, peak_src = measured_peak()
-    n_dom = wl.launches_per_step() * args.steps
-    ach = wl.alg_bytes_per_launch() / (t.ms * 1e-3 / n_dom) / 1e9
-    roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-            "traffic": getattr(wl, "ncu_traffic", None), "peak_source": peak_src,
-            "kernel": getattr(wl, "dominant_kernel", "e1d_half_kernel"),
-            "alg_bytes_per_launch": wl.alg_bytes_per_launch(),
-            "avg_launch_ms": t.ms / n_dom}
-
-    # ---- end-to-end arm through the public class with host arrays
-    e2e = None
-    if not args.no_e2e:
-        if hasattr(wl.dev, "materialise"):
-            wl.dev.materialise()
-        if getattr(wl, "dist_svr", None) is None:
-            wl.dev.resident(False)
-        wl.e2e_step()
-        n_e2e = max(1, min(args.steps, 3))
-        barrier(dist, local)
-        t0 = time.perf_counter()
-        for _ in range(n_e2e):
-            wl.e2e_step()
-        _lib.sync()
-        barrier(dist, local)
-        el = max_over_ranks(dist, time.perf_counter() - t0, local)
-        hi, lo = wl.e2e_bytes()
-        steps_marched += (1 + n_e2e) * args.chunk
-        e2e = {"value": sum_over_ranks(dist, float(wl.updates_per_step()), local) * n_e2e / el, "unit": UNIT,
-               "h2d_bytes_per_step": hi, "d2h_bytes_per_step": lo, "steps": n_e2e,
-               "check": wl.result_check()}
-
-    # ---- the field every timed step ran on must still be a flow field: finite everywhere, density positive
-    check = sum_over_ranks(dist, wl.result_check(), local)
-    health = None
-    if hasattr(wl, "health"):
-        health = wl.health()
-        health["cflo_max"] = max_over_ranks(dist, health["cflo_max"], local)
-        health["rho_min"] = -max_over_ranks(dist, -health["rho_min"], local)
-        health["p_min"] = -max_over_ranks(dist, -health["p_min"], local)
-        health["finite"] = bool(max_over_ranks(dist, 0.0 if health["finite"] else 1.0, local) == 0.0)
-        health["steps_marched"] = steps_marched
-    bad = (not np.isfinite(check)) or (health is not None and (not health["finite"] or not health["rho_min"] > 0.0))
-
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        cpu, _, _ = wl.cpu_run(budget_s=args.ref_budget)
+    # ---- the other named configurations (BASELINE.json configs[0..3]) in the same run, bounded: one entry each
+    subs = None
+    if not bad and args.workload == "md3d" and not args.no_subs and args.size == 0:
+        del wl
+        import gc
+        gc.collect()
+        subs = run_subs(args, rank, world, local, dist)
+        bad = bad or any(sr.get("bad") for sr in subs)
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic",
-                "config": wl.describe(world), "clocks": clk.summary(), "e2e": e2e,
-                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
-                "strict_fp": bool(lib.scg_build_is_strict()), "parity": parity, "check": check}
-        if health is not None:
-            line["config"]["mesh"].update(health)
+        line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+                "scaling": res["scaling"], "vs_baseline": None, "dtype": res["dtype"], "data": "synthetic",
+                "config": res["config"], "clocks": res["clocks"], "e2e": res["e2e"],
+                "gpu_launches": res["gpu_launches"], "roofline": res["roofline"], "cpu_baseline": res["cpu_baseline"],
+                "strict_fp": bool(lib.scg_build_is_strict()), "parity": parity, "check": res["check"]}
+        if res.get("roofline_fp64"):
+            line["roofline_fp64"] = res["roofline_fp64"]
+        if subs is not None:
+            line["sub_results"] = subs
         if bad:
             # a march that left the physical regime (NaN / non-positive density) is not a measurement
-            print(json.dumps({"error": "the marched field is not finite and positive", "check": repr(check),
-                              "health": {k: repr(v) for k, v in (health or {}).items()}}), file=sys.stderr)
+            print(json.dumps({"error": "a marched field is not finite and positive", "check": repr(res["check"]),
+                              "health": {k: repr(v) for k, v in (res["health"] or {}).items()},
+                              "subs": [sr.get("workload") for sr in (subs or []) if sr.get("bad")]}), file=sys.stderr)
         else:
             print(json.dumps(line, allow_nan=False))
         if os.environ.get("SCG_TIMING") == "1":   # diagnostics: per-kernel device times to stderr

@@ -96,28 +96,17 @@ def build_case_3d(ncell_target, order="morton", kinds="hpt", log=None):
     return mesh, svr, info
 
 
-def build_case_3d_dist(ncell_target, rank, world, local_device, order="morton", kinds="hpt"):
-    """Weak-scaling case (SURVEY.md 8d config 5): the channel is extended in y with the number of ranks; rank r
-    owns ny box layers and builds only those plus two halo layers per side (solvcon_b200.decomp)."""
-    from .decomp import DistEulerCore, TorchExchange, slab_partition_3d
-    t0 = time.perf_counter()
-    nx, ny, nz, x1, z1 = dims_3d(ncell_target)
-    h = 1.0 / ny
-    part = slab_partition_3d(rank, world, nx, ny, nz, h, x1, z1, kinds=kinds, jitter=0.1)
-    t1 = time.perf_counter()
+def _finish_dist_case(part, dt, order, lo, hi, z_level, local_device, kinds, device="cuda"):
+    """Device solver of one partition with the bench's IC / BCs, halo geometry and state exchanged once."""
+    from .decomp import DistEulerCore, TorchExchange
     mesh = part.build_mesh()
-    t2 = time.perf_counter()
-    dt = 0.05 * h
     svr = DistEulerCore(part, dt, order=order)
-    t3 = time.perf_counter()
-    lo = np.array([0.0, 0.0, 0.0])
-    hi = np.array([nx * h, world * ny * h, nz * h])
     inlet, outlet, wall = part.physical_boundary_groups(lo, hi)
     core = svr.core
     core.resident(False)
     core.init_solution(GAMMA, RHO0, [MACH_U, 0.0, 0.0], P0)
     if kinds == "hpt":
-        pocket_at_rest(core.so0n.body, mesh.clcnd.body, z1 * h)
+        pocket_at_rest(core.so0n.body, mesh.clcnd.body, z_level)
     core.add_inlet(inlet, [RHO0, MACH_U, 0.0, 0.0, P0, GAMMA])
     core.add_nonrefl(outlet)
     core.add_slipwall(wall)
@@ -127,15 +116,119 @@ def build_case_3d_dist(ncell_target, rank, world, local_device, order="morton", 
     svr.transport = TorchExchange(svr, f"cuda:{local_device}")
     svr.transport.exchange(1)
     svr.transport.exchange(0)
+    return mesh, svr
+
+
+def _dist_info(part, mesh, svr, extra):
     own = part.owned.astype(bool)
-    info = {"boxes_per_rank": [nx, ny, nz], "x1": x1, "z1": z1, "h": h, "dt": dt, "ncell": int(own.sum()),
-            "ncell_local_mesh": int(mesh.ncell), "halo_send_cells": int(svr.nsend), "halo_recv_cells": int(svr.nrecv),
-            "halo_bytes_per_substep": int(svr.nsend * core.halo_width(0) * 8),
+    core = svr.core
+    info = {"ncell": int(own.sum()), "ncell_local_mesh": int(mesh.ncell), "halo_send_cells": int(svr.nsend),
+            "halo_recv_cells": int(svr.nrecv), "halo_bytes_per_substep": int(svr.nsend * core.halo_width(0) * 8),
+            "neighbour_ranks": [int(q) for q in part.neighbours],
             "nface": int(mesh.nface), "ngstcell": int(mesh.ngstcell),
             "cells_by_type": {"hex": int((part.cltpn[own] == 5).sum()), "tet": int((part.cltpn[own] == 6).sum()),
-                              "prism": int((part.cltpn[own] == 7).sum())},
-            "setup_s": {"generate": round(t1 - t0, 2), "tables": round(t2 - t1, 2), "device": round(t3 - t2, 2)}}
+                              "prism": int((part.cltpn[own] == 7).sum())}}
+    info.update(extra)
+    return info
+
+
+def build_case_3d_dist(ncell_target, rank, world, local_device, order="morton", kinds="hpt"):
+    """Weak-scaling case (SURVEY.md 8d config 5): the channel is extended in y with the number of ranks; rank r
+    owns ny box layers and builds only those plus two halo layers per side (solvcon_b200.decomp)."""
+    from .decomp import slab_partition_3d
+    t0 = time.perf_counter()
+    nx, ny, nz, x1, z1 = dims_3d(ncell_target)
+    h = 1.0 / ny
+    part = slab_partition_3d(rank, world, nx, ny, nz, h, x1, z1, kinds=kinds, jitter=0.1)
+    t1 = time.perf_counter()
+    part.build_mesh()
+    t2 = time.perf_counter()
+    dt = 0.05 * h
+    lo = np.array([0.0, 0.0, 0.0])
+    hi = np.array([nx * h, world * ny * h, nz * h])
+    mesh, svr = _finish_dist_case(part, dt, order, lo, hi, z1 * h, local_device, kinds)
+    t3 = time.perf_counter()
+    info = _dist_info(part, mesh, svr, {"boxes_per_rank": [nx, ny, nz], "x1": x1, "z1": z1, "h": h, "dt": dt,
+                                        "setup_s": {"generate": round(t1 - t0, 2), "tables": round(t2 - t1, 2),
+                                                    "device": round(t3 - t2, 2)}})
     return mesh, svr, info
+
+
+def build_case_3d_strong(ncell_total, rank, world, local_device, order="morton", kinds="hpt"):
+    """Strong-scaling case (BASELINE.json configs[3]): ONE stepped channel of ``ncell_total``
+    cells cut into ``world`` parts by cost-weighted recursive coordinate bisection of its box lattice
+    (``decomp.lattice_rcb``); every rank generates only its own box range plus two layers
+    (``decomp.lattice_partition_3d``), orders its cells (Morton / RCM) inside the part, and exchanges the state of
+    the cells on its cuts after every substep, overlapped with the interior march."""
+    from .decomp import CELL_COST, lattice_partition_3d, lattice_rcb
+    t0 = time.perf_counter()
+    nx, ny, nz, x1, z1 = dims_3d(ncell_total)
+    h = 1.0 / ny
+    ranges = lattice_rcb(nx, ny, nz, x1, z1, world, cost=CELL_COST)
+    part = lattice_partition_3d(rank, ranges, nx, ny, nz, h, x1, z1, kinds=kinds, jitter=0.1)   # builds the local mesh
+    t2 = time.perf_counter()
+    dt = 0.05 * h
+    lo = np.array([0.0, 0.0, 0.0])
+    hi = np.array([nx * h, ny * h, nz * h])
+    mesh, svr = _finish_dist_case(part, dt, order, lo, hi, z1 * h, local_device, kinds)
+    t3 = time.perf_counter()
+    info = _dist_info(part, mesh, svr, {"boxes": [nx, ny, nz], "x1": x1, "z1": z1, "h": h, "dt": dt,
+                                        "box_range_of_rank0": [list(r) for r in ranges[0]],
+                                        "setup_s": {"generate+tables": round(t2 - t0, 2), "device": round(t3 - t2, 2)}})
+    return mesh, svr, info
+
+
+def nccl_parity_3d(rank, world, local_device, dist, order, ncell_target=120_000, steps=6):
+    """Multi-rank parity leg of bench.py (before anything is timed): a small stepped channel cut by ``lattice_rcb``
+    into one part per rank and marched through the REAL transport (``TorchExchange.exchange_split``: NCCL send/recv on
+    the communication stream, overlapped with the interior march); every rank's owned cells are gathered on rank 0 and
+    compared, bit for bit, with the undecomposed device run of the same case (which the single-rank parity leg and the
+    GPU tests hold bit-equal to the compiled reference)."""
+    import torch
+    from . import _lib
+    from .decomp import CELL_COST, lattice_partition_3d, lattice_rcb
+    nx, ny, nz, x1, z1 = dims_3d(ncell_target)
+    h = 1.0 / ny
+    dt = 0.05 * h
+    ranges = lattice_rcb(nx, ny, nz, x1, z1, world, cost=CELL_COST)
+    part = lattice_partition_3d(rank, ranges, nx, ny, nz, h, x1, z1, jitter=0.1)
+    lo, hi = np.array([0.0, 0.0, 0.0]), np.array([nx * h, ny * h, nz * h])
+    mesh, svr = _finish_dist_case(part, dt, order, lo, hi, z1 * h, local_device, "hpt")
+    svr.march(steps)
+    _lib.sync()
+    svr.core.materialise(("so0n", "so1n", "cflo", "cflc"))
+    svr.core.sync_to_host()
+    own = part.owned.astype(bool)
+    mine = {"key": part.gid[own]}
+    for n in ("so0n", "so1n", "cflo", "cflc"):
+        mine[n] = getattr(svr.core, n).body[own].copy()
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object(mine, gathered, dst=0)
+    result = None
+    if rank == 0:
+        ndcrd, cltpn, clnds, box = meshgen.mixed_3d(nx, ny, nz, lx=nx * h, ly=ny * h, lz=nz * h, x1=x1, z1=z1, jitter=0.1,
+                                                    return_box=True)
+        key = meshgen.cell_key(box, ny, nz)
+        _, ref, info = build_case_3d(ncell_target, order)
+        assert info["ncell"] == len(cltpn)
+        ref.march(steps)
+        ref.materialise(("so0n", "so1n", "cflo", "cflc"))
+        ref.sync_to_host()
+        equal, seen, worst = True, np.zeros(len(cltpn), dtype=np.int64), 0.0
+        for g in gathered:
+            gid = np.searchsorted(key, g["key"])
+            seen[gid] += 1
+            for n in ("so0n", "so1n", "cflo", "cflc"):
+                a, c = g[n], getattr(ref, n).body[gid]
+                equal = equal and bool(np.array_equal(a, c))
+                worst = max(worst, float(np.abs(a - c).max()) / (float(np.abs(c).max()) + 1e-300))
+        result = {"cells": int(len(cltpn)), "parts": world, "steps": steps, "bit_equal": bool(equal and (seen == 1).all()),
+                  "max_rel_linf": worst, "transport": "TorchExchange.exchange_split over NCCL (overlapped)",
+                  "against": "undecomposed device march of the same case",
+                  "halo_cells_sent_by_rank0": int(svr.nsend)}
+    flag = torch.tensor([1 if (result is None or result["bit_equal"]) else 0], device=f"cuda:{local_device}")
+    dist.broadcast(flag, src=0)
+    return result, bool(flag.item())
 
 
 class MD3DWorkload:
@@ -143,15 +236,22 @@ class MD3DWorkload:
     dtype = "f64"
     dominant_kernel = "one substep = md_solt + md_solncfl_staged<hex|prism|tet> + md_dsoln_eqo<hex|prism|tet> + boundary kernels"
 
-    def __init__(self, ncell, chunk, order="morton", kinds="hpt"):
+    def __init__(self, ncell, chunk, order="morton", kinds="hpt", strong=False):
         self.ncell_target = int(ncell)
         self.chunk = chunk
         self.order = order
         self.kinds = kinds
+        self.strong = bool(strong)      # True: ncell is the TOTAL, cut into one part per rank (configs[3])
+        if self.strong:
+            self.name = "md3d_strong"
 
     def build_device(self):
         world = getattr(self, "world", 1)
-        if world > 1:
+        if world > 1 and self.strong:
+            self.mesh, self.dist_svr, self.info = build_case_3d_strong(self.ncell_target, self.rank, world, self.local,
+                                                                       self.order, self.kinds)
+            self.dev = self.dist_svr.core
+        elif world > 1:
             # every rank builds its own slab on the host (~0.85 KB of host memory per cell at the peak of the table
             # construction): keep the ranks of one box inside its RAM
             try:
@@ -200,15 +300,20 @@ class MD3DWorkload:
             ncell, info, balg = self.ncell, self.info, float(self.balg_substep)
         else:
             ncell, info, balg = self._planned()
+        size = (f"{self.ncell_target} cells in total, {ncell} on rank 0" if self.strong and world > 1
+                else f"{ncell} cells per GPU")
         d = {"workload": f"3D Euler CESE (multidim EulerCore.march), synthetic mixed tet/hex/prism stepped channel, "
-                         f"{ncell} cells per GPU ({info['cells_by_type']}), Mach-3 inlet / nonrefl outlet / "
-                         f"slip walls, march({self.chunk}) per step, {self.order} cell ordering",
+                         f"{size} ({info['cells_by_type']}), Mach-3 inlet (gas above the step at rest) / nonrefl "
+                         f"outlet / slip walls, march({self.chunk}) per step, {self.order} cell ordering",
              "cells_per_gpu": ncell, "chunk_steps": self.chunk, "ordering": self.order,
              "alg_bytes_per_cell_substep": balg / ncell,
              "l2_policy": "inputs larger than L2 (%.1f GB streamed per substep)" % (balg / 1e9),
              "decomposition": "none" if world == 1 else
-             f"y-slabs, one per GPU, domain extended in y with the rank count; halo exchange of so0n+so1n after every "
-             f"substep by NCCL isend/irecv ({info.get('halo_bytes_per_substep', 0)} B sent per rank per substep)",
+             (f"ONE mesh of {self.ncell_target} cells cut into {world} parts by cost-weighted recursive coordinate "
+              f"bisection of the box lattice, {self.order} ordering inside each part; " if self.strong else
+              f"y-slabs, one per GPU, domain extended in y with the rank count; ") +
+             f"halo exchange of so0n+so1n after every substep by NCCL isend/irecv, overlapped with the interior march "
+             f"({info.get('halo_bytes_per_substep', 0)} B sent by rank 0 per substep)",
              "mesh": info}
         if getattr(self, "size_note", None):
             d["size_note"] = self.size_note
@@ -266,6 +371,38 @@ class MD3DWorkload:
     def health(self):
         return field_health(self.dev)
 
+    # fp64-pipe warp-instruction lanes one cell-substep executes in the default kernels, from the committed dynamic
+    # instruction mix (profiles/r01g_sass_mix.txt: executed instructions per cell x share issued to the fp64 pipe,
+    # md_solncfl_staged + md_dsoln_eqo): hex 7.78k*0.651 + 7.84k*0.512, tet 4.57k*0.610 + 4.51k*0.505, prism
+    # 6.84k*0.620 + 6.20k*0.506.  The arithmetic is the reference's, operation for operation (no FMA contraction).
+    FP64_INSTR_PER_CELL = {"hex": 9080.0, "tet": 5070.0, "prism": 7380.0}
+
+    def roofline_fp64(self, substep_s, clocks):
+        """Second roofline of the 3D march: the fp64 pipe.  B200 issues 64 fp64 lanes per SM per clock (16 per
+        sub-partition: one warp instruction every 2 cycles), so a substep of this rank's cells cannot run faster than
+        ``sum_type n_type * instr_type / (148 * 64 * f_clk)``; reported at the maximum SM clock and at the median clock
+        measured during the timed region (the board is power-capped under this kernel mix)."""
+        by = self.info["cells_by_type"]
+        lanes = sum(self.FP64_INSTR_PER_CELL[k] * by.get(k, 0) for k in self.FP64_INSTR_PER_CELL)
+        if lanes <= 0:
+            return None
+        sm = 148
+        fmax = (clocks.get("sm_max_mhz") or 1965.0) * 1e6
+        fmeas = (clocks.get("sm_mhz") or 0.0) * 1e6
+        floor_max = lanes / (sm * 64.0 * fmax)
+        out = {"bound": "fp64 pipe (64 lanes/clk/SM)", "fp64_instr_per_cell": self.FP64_INSTR_PER_CELL,
+               "source": "profiles/r01g_sass_mix.txt (dynamic mix of the ncu --set full capture)",
+               "floor_substep_ms_at_max_clock": floor_max * 1e3,
+               "ceiling_updates_per_s_at_max_clock": self.ncell / floor_max,
+               "frac_of_ceiling_at_max_clock": floor_max / substep_s,
+               "hbm_frac_at_fp64_ceiling": (self.balg_substep / floor_max / 1e9) / 6555.5}
+        if fmeas > 0:
+            floor_meas = lanes / (sm * 64.0 * fmeas)
+            out["ceiling_updates_per_s_at_measured_clock"] = self.ncell / floor_meas
+            out["frac_of_ceiling_at_measured_clock"] = floor_meas / substep_s
+            out["measured_sm_mhz"] = clocks.get("sm_mhz")
+        return out
+
 
 
 # ------------------------------------------------------------------------------------------ 2D ---
@@ -309,6 +446,7 @@ def build_case_2d(ncell_target, order="morton"):
 
 class MD2DWorkload(MD3DWorkload):
     name = "md2d"
+    roofline_fp64 = None
     dominant_kernel = "one substep = md_solt + md_solncfl_staged<quad|tri> + md_dsoln_eqo<quad|tri> + boundary kernels"
 
     def build_device(self):
@@ -358,6 +496,8 @@ class MD2DWorkload(MD3DWorkload):
 def make(args):
     if args.workload == "md3d":
         return MD3DWorkload(args.size or 50_000_000, args.chunk, order=getattr(args, "order", "morton"))
+    if args.workload == "md3d_strong":
+        return MD3DWorkload(args.size or 100_000_000, args.chunk, order=getattr(args, "order", "morton"), strong=True)
     if args.workload == "md2d":
         return MD2DWorkload(args.size or 20_000_000, args.chunk, order=getattr(args, "order", "morton"))
     raise SystemExit(f"workload {args.workload} not available")

@@ -176,6 +176,106 @@ def slab_partition_3d(rank, nparts, nx, ny_per_rank, nz, h, x1, z1, kinds="hpt",
     return p
 
 
+# Relative cost of one cell-substep by cell type (measured kernel times per cell, profiles/r01f_md3d_launches_summary:
+# hexahedron 0.92 us, prism 0.78 us, tetrahedron 0.58 us per 148-SM wave): the weights the strong-scaling cut balances.
+CELL_COST = {"hex": 1.0, "prism": 0.85, "tet": 0.63}
+
+
+def lattice_weight(rng, x1, z1, cost=None):
+    """Cost-weighted cell count of the boxes ``rng = ((i0,i1),(j0,j1),(k0,k1))`` of the stepped channel of
+    ``meshgen.mixed_3d`` (closed form: the cell kind of a box depends on ``i < x1`` and ``k < z1`` only)."""
+    c = cost or {"hex": 1.0, "prism": 1.0, "tet": 1.0}
+    (i0, i1), (j0, j1), (k0, k1) = rng
+    ilo, ihi = max(0, min(i1, x1) - i0), max(0, i1 - max(i0, x1))      # boxes with i < x1 / i >= x1
+    klo, khi = max(0, min(k1, z1) - k0), max(0, k1 - max(k0, z1))      # boxes with k < z1 / k >= z1
+    dj = max(0, j1 - j0)
+    return dj * (c["hex"] * ilo * klo + 2.0 * c["prism"] * ihi * klo + 6.0 * c["tet"] * ihi * khi)
+
+
+def lattice_rcb(nx, ny, nz, x1, z1, nparts, cost=None, spacing=(1.0, 1.0, 1.0)):
+    """Recursive coordinate bisection of the stepped channel's box lattice into ``nparts`` box ranges of (nearly)
+    equal cost-weighted cell count: the RCB of SURVEY.md 8d config 4 at box granularity, evaluated in closed form so
+    that every rank can compute all cuts without any rank holding the global mesh.  Cuts are perpendicular to the
+    physically longest axis of the range being cut.  Returns ``[((i0,i1),(j0,j1),(k0,k1)), ...]`` (index = rank)."""
+    out = [None] * int(nparts)
+
+    def bbox(rng):
+        """Shrink a range to the non-solid boxes it contains (the region i < x1, k >= z1 holds no cells)."""
+        (i0, i1), (j0, j1), (k0, k1) = rng
+        if k0 >= z1:
+            i0 = max(i0, x1)
+        if i1 <= x1:
+            k1 = min(k1, z1)
+        return ((i0, i1), (j0, j1), (k0, k1))
+
+    def split(rng, p0, np_):
+        rng = bbox(rng)
+        if np_ == 1:
+            out[p0] = rng
+            return
+        nl = np_ // 2
+        total = lattice_weight(rng, x1, z1, cost)
+        target = total * nl / np_
+        ext = [(b - a) * sp for (a, b), sp in zip(rng, spacing)]
+        for axis in sorted(range(3), key=lambda a: -ext[a]):
+            a0, a1 = rng[axis]
+            if a1 - a0 < 2:
+                continue
+            best, bestd = None, None
+            for c in range(a0 + 1, a1):
+                lo = list(rng)
+                lo[axis] = (a0, c)
+                d = abs(lattice_weight(tuple(lo), x1, z1, cost) - target)
+                if bestd is None or d < bestd:
+                    best, bestd = c, d
+            lo, hi = list(rng), list(rng)
+            lo[axis], hi[axis] = (a0, best), (best, a1)
+            if lattice_weight(tuple(lo), x1, z1, cost) > 0 and lattice_weight(tuple(hi), x1, z1, cost) > 0:
+                split(tuple(lo), p0, nl)
+                split(tuple(hi), p0 + nl, np_ - nl)
+                return
+        raise ValueError(f"lattice_rcb: cannot cut {rng} into {np_} non-empty parts")
+
+    split(((0, nx), (0, ny), (0, nz)), 0, int(nparts))
+    return out
+
+
+def lattice_partition_3d(rank, ranges, nx, ny, nz, h, x1, z1, kinds="hpt", jitter=0.1):
+    """Partition ``rank`` of the stepped channel cut into the box ranges ``ranges`` (``lattice_rcb``).  The rank
+    generates its own boxes plus two box layers around them (the exchanged halo layer and the passive one) straight
+    from the lattice formula; send / receive lists are the cells that really share a face across a cut (found in the
+    LOCAL face table), ordered by ``meshgen.cell_key`` -- the same ascending global order on both sides of a rank
+    pair.  No rank ever holds the global mesh."""
+    (i0, i1), (j0, j1), (k0, k1) = ranges[rank]
+    grow = ((i0 - 2, i1 + 2), (j0 - 2, j1 + 2), (k0 - 2, k1 + 2))
+    ndcrd, cltpn, clnds, box = meshgen.mixed_3d(nx, ny, nz, lx=nx * h, ly=ny * h, lz=nz * h, x1=x1, z1=z1, kinds=kinds,
+                                                jitter=jitter, box_range=grow, return_box=True)
+    bi, bj, bk, _ = box
+    key = meshgen.cell_key(box, ny, nz)
+
+    def inside(r):
+        (a0, a1), (b0, b1), (c0, c1) = r
+        return (bi >= a0) & (bi < a1) & (bj >= b0) & (bj < b1) & (bk >= c0) & (bk < c1)
+
+    owner = np.full(len(cltpn), -1, dtype=np.int32)
+    for q, r in enumerate(ranges):
+        owner[inside(r)] = q
+    owned = (owner == rank).astype(np.int8)
+    p = Partition(rank=rank, ndim=3, ndcrd=ndcrd, cltpn=cltpn, clnds=clnds, owned=owned, gid=key)
+    fccls = p.build_mesh().fccls.body
+    a, b = fccls[:, 0], fccls[:, 1]
+    inner = b >= 0
+    a, b = a[inner], b[inner]
+    cut = (owner[a] == rank) != (owner[b] == rank)
+    mine = np.where(owner[a[cut]] == rank, a[cut], b[cut])
+    theirs = np.where(owner[a[cut]] == rank, b[cut], a[cut])
+    for q in np.unique(owner[theirs]):
+        m = owner[theirs] == q
+        p.recv[int(q)] = np.unique(theirs[m]).astype(np.int32)      # ascending local id == ascending key
+        p.send[int(q)] = np.unique(mine[m]).astype(np.int32)
+    return p
+
+
 # ----------------------------------------------------------------------------------- transport ---
 
 class LocalExchange:

@@ -100,16 +100,21 @@ for perm in ((0, 1, 2), (0, 2, 1), (1, 0, 2), (1, 2, 0), (2, 0, 1), (2, 1, 0)):
 
 
 def mixed_3d(nx, ny, nz, lx=None, ly=None, lz=None, x1=None, z1=None, kinds="hpt", jitter=0.0, j_range=None,
-             return_box_j=False):
+             return_box_j=False, box_range=None, return_box=False):
     """Stepped channel of ``nx`` x ``ny`` x ``nz`` boxes: block A hexahedra
     (``i < x1, k < z1``), block B z-axis prisms (``i >= x1, k < z1``; each box split on its vertical
     ll-ur diagonal plane), block C tetrahedra (``i >= x1, k >= z1``; Kuhn split, 6 per box); the
     region ``i < x1, k >= z1`` is solid.  All interfaces conform without pyramids (hex|prism share
     quads at ``i = x1``, prism|tet share triangles at ``k = z1``).  ``kinds`` selects the blocks:
     ``"h"`` = hex box only (``x1 = nx, z1 = nz``), ``"hp"``, ``"hpt"``; ``"t"`` / ``"p"`` = one kind
-    everywhere.  ``j_range=(j0, j1)`` generates only the boxes with ``j0 <= j < j1`` of the SAME global lattice
-    (coordinates, jitter and relative cell order are those of the full mesh -- used by the slab domain
-    decomposition); ``return_box_j`` also returns the global box index j of every cell.
+    everywhere.
+
+    Sub-lattices (domain decomposition: no rank ever generates the global mesh): ``box_range=((i0, i1), (j0, j1),
+    (k0, k1))`` generates only the boxes of that index range of the SAME global lattice -- coordinates, jitter, cell
+    kinds and the relative order of nodes and cells are those of the full mesh (both are lexicographic in the global
+    lattice indices).  ``j_range=(j0, j1)`` is the y-only form.  ``return_box_j`` also returns the global box index j
+    of every cell; ``return_box`` returns ``(bi, bj, bk, sub)`` per cell (global box indices and the cell's position
+    inside its box), from which ``cell_key`` makes an id that ascends with the global cell order.
     Returns ``(ndcrd[nnode,3], cltpn, clnds)``."""
     lx = float(nx) if lx is None else lx
     ly = float(ny) if ly is None else ly
@@ -124,8 +129,10 @@ def mixed_3d(nx, ny, nz, lx=None, ly=None, lz=None, x1=None, z1=None, kinds="hpt
     else:
         x1 = nx // 2 if x1 is None else x1
         z1 = nz // 2 if z1 is None else z1
-    j0, j1 = (0, ny) if j_range is None else (max(0, int(j_range[0])), min(ny, int(j_range[1])))
-    ii, jj, kk = np.meshgrid(np.arange(nx + 1), np.arange(j0, j1 + 1), np.arange(nz + 1), indexing="ij")
+    if box_range is None:
+        box_range = ((0, nx), (0, ny) if j_range is None else j_range, (0, nz))
+    (i0, i1), (j0, j1), (k0, k1) = [(max(0, int(a)), min(n, int(b))) for (a, b), n in zip(box_range, (nx, ny, nz))]
+    ii, jj, kk = np.meshgrid(np.arange(i0, i1 + 1), np.arange(j0, j1 + 1), np.arange(k0, k1 + 1), indexing="ij")
     x = ii * (lx / nx)
     y = jj * (ly / ny)
     z = kk * (lz / nz)
@@ -135,18 +142,20 @@ def mixed_3d(nx, ny, nz, lx=None, ly=None, lz=None, x1=None, z1=None, kinds="hpt
         x = x + np.where(inner, jitter * np.sin(12.9898 * ii + 78.233 * jj + 37.719 * kk), 0.0) * (lx / nx)
         y = y + np.where(inner, jitter * np.cos(26.651 * ii + 41.347 * jj + 11.135 * kk), 0.0) * (ly / ny)
         z = z + np.where(inner, jitter * np.sin(63.7264 * ii + 10.873 * jj + 53.127 * kk), 0.0) * (lz / nz)
-    nyl = j1 - j0
-    nid = ((ii * (nyl + 1) + (jj - j0)) * (nz + 1) + kk).astype(np.int64)  # local lattice id, same relative order
-    bi, bj, bk = [a.ravel() for a in np.meshgrid(np.arange(nx), np.arange(nyl), np.arange(nz), indexing="ij")]
+    nxl, nyl, nzl = i1 - i0, j1 - j0, k1 - k0
+    # local lattice id, same relative order as the global one
+    nid = (((ii - i0) * (nyl + 1) + (jj - j0)) * (nzl + 1) + (kk - k0)).astype(np.int64)
+    li, lj, lk = [a.ravel() for a in np.meshgrid(np.arange(nxl), np.arange(nyl), np.arange(nzl), indexing="ij")]
+    bi, bj, bk = li + i0, lj + j0, lk + k0
     solid = (bi < x1) & (bk >= z1)
-    bi, bj, bk = bi[~solid], bj[~solid], bk[~solid]
+    li, lj, lk, bi, bj, bk = (a[~solid] for a in (li, lj, lk, bi, bj, bk))
     # box corners c = 4*dx + 2*dy + dz
-    cor = np.stack([nid[bi + dx, bj + dy, bk + dz] for dx in (0, 1) for dy in (0, 1) for dz in (0, 1)], axis=1)
+    cor = np.stack([nid[li + dx, lj + dy, lk + dz] for dx in (0, 1) for dy in (0, 1) for dz in (0, 1)], axis=1)
     is_hex = (bi < x1) & (bk < z1)
     is_pri = (bi >= x1) & (bk < z1)
     is_tet = (bi >= x1) & (bk >= z1)
     ncl = np.where(is_hex, 1, np.where(is_pri, 2, 6))
-    first = np.concatenate(([0], np.cumsum(ncl)[:-1]))
+    first = np.concatenate(([0], np.cumsum(ncl)[:-1])) if len(ncl) else np.zeros(0, dtype=np.int64)
     ncell = int(ncl.sum())
     cltpn = np.empty(ncell, dtype=np.int32)
     clnds = np.full((ncell, CLMND + 1), -1, dtype=np.int32)
@@ -181,9 +190,20 @@ def mixed_3d(nx, ny, nz, lx=None, ly=None, lz=None, x1=None, z1=None, kinds="hpt
         n[neg, 2], n[neg, 3] = n[neg, 3].copy(), n[neg, 2].copy()
         clnds[tets, 1:5] = n
     ndcrd, clnds = _compact_nodes(ndcrd, clnds)
+    out = (np.ascontiguousarray(ndcrd), cltpn, clnds)
     if return_box_j:
-        return np.ascontiguousarray(ndcrd), cltpn, clnds, np.repeat(bj + j0, ncl)
-    return np.ascontiguousarray(ndcrd), cltpn, clnds
+        out += (np.repeat(bj, ncl),)
+    if return_box:
+        sub = np.arange(ncell, dtype=np.int64) - np.repeat(first, ncl)
+        out += ((np.repeat(bi, ncl), np.repeat(bj, ncl), np.repeat(bk, ncl), sub),)
+    return out
+
+
+def cell_key(box, ny, nz):
+    """An int64 id per cell that ascends with the GLOBAL cell order of ``mixed_3d`` (lexicographic in the global box
+    indices, then the position inside the box): equal on every rank that generates the cell."""
+    bi, bj, bk, sub = box
+    return ((bi.astype(np.int64) * ny + bj) * nz + bk) * 6 + sub
 
 
 def boundary_groups(ndim, fccnd, fccls, nface, lo, hi, tol=1e-9):

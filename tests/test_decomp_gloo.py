@@ -76,3 +76,41 @@ def test_gloo_1d_ring_bit_identical(bridge, eq, world):
            os.path.join(HERE, "decomp1d_worker.py"), str(eq), "2003", "30"]
     res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+def test_lattice_rcb_covers_and_balances():
+    """The closed-form box-lattice RCB: parts tile the lattice, every part holds cells, cost-weighted sizes agree
+    within a box layer, and the result does not depend on who computes it."""
+    from solvcon_b200.bench_md import dims_3d
+    from solvcon_b200.decomp import CELL_COST, lattice_rcb, lattice_weight
+    for target, nparts in ((40_000, 3), (1_000_000, 8), (100_000_000, 8), (100_000_000, 2)):
+        nx, ny, nz, x1, z1 = dims_3d(target)
+        rs = lattice_rcb(nx, ny, nz, x1, z1, nparts, cost=CELL_COST)
+        assert rs == lattice_rcb(nx, ny, nz, x1, z1, nparts, cost=CELL_COST)
+        cells = [lattice_weight(r, x1, z1) for r in rs]
+        assert sum(cells) == lattice_weight(((0, nx), (0, ny), (0, nz)), x1, z1) and min(cells) > 0
+        cost = [lattice_weight(r, x1, z1, CELL_COST) for r in rs]
+        assert max(cost) / (sum(cost) / nparts) < (1.01 if target >= 100_000_000 else 1.05 if target >= 1_000_000 else 1.25)
+
+
+def test_lattice_partition_lists_are_consistent():
+    from solvcon_b200 import meshgen
+    from solvcon_b200.bench_md import dims_3d
+    from solvcon_b200.decomp import CELL_COST, lattice_partition_3d, lattice_rcb
+    nx, ny, nz, x1, z1 = dims_3d(30000)
+    h = 1.0 / ny
+    rs = lattice_rcb(nx, ny, nz, x1, z1, 5, cost=CELL_COST)
+    ps = [lattice_partition_3d(r, rs, nx, ny, nz, h, x1, z1) for r in range(5)]
+    nd, tp, cl, box = meshgen.mixed_3d(nx, ny, nz, lx=nx * h, ly=1.0, lz=nz * h, x1=x1, z1=z1, jitter=0.1, return_box=True)
+    key = meshgen.cell_key(box, ny, nz)
+    gm = __import__("solvcon_b200.mesh", fromlist=["make_mesh"]).make_mesh(3, nd, tp, cl)
+    assert sum(int(p.owned.sum()) for p in ps) == len(tp)
+    for p in ps:
+        assert np.all(np.diff(p.gid) > 0)
+        for q in p.neighbours:
+            assert np.array_equal(p.gid[p.send[q]], ps[q].gid[ps[q].recv[p.rank]])
+            assert p.owned[p.send[q]].all() and not p.owned[p.recv[q]].any()
+        # mesh centroids of the owned cells and of the exchanged copies carry the global mesh's bits
+        first = np.concatenate([p.recv[q] for q in p.neighbours])
+        chk = np.concatenate([np.nonzero(p.owned)[0], first])
+        assert np.array_equal(p.build_mesh().clcnd.body[chk], gm.clcnd.body[np.searchsorted(key, p.gid[chk])])
