@@ -141,6 +141,7 @@ def test_lattice_rcb_partitions_bit_identical(gpu, nparts, split):
     for p in parts.values():
         for q in p.neighbours:     # what I send is what q expects, in the same order
             assert np.array_equal(p.gid[p.send[q]], parts[q].gid[parts[q].recv[p.rank]])
+    for p in parts.values():
         p.gid = np.searchsorted(key, p.gid)     # cell_key -> dense global id of the undecomposed mesh
     res = _run_parts(parts, dt, steps, geo, split)
     seen = np.zeros(len(cltpn), dtype=int)
