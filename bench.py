@@ -326,6 +326,12 @@ def dist_setup(n_gpus):
         torch.cuda.set_device(local)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # the data path's communicator lives in the library (csrc/scg_comm.cu); torch.distributed carries its unique
+        # id and keeps the bench's own plumbing (barrier, max over ranks)
+        from solvcon_b200 import _lib
+        from solvcon_b200.decomp import comm_init
+        _lib.init(local)
+        comm_init(rank, world, dist=dist)
         return rank, world, local, dist
     return rank, world, local, None
 
@@ -467,11 +473,16 @@ def measure(wl, steps, warmup, args, rank, world, local, dist, e2e=True, cpu=Fal
     # ---- end-to-end arm through the public class with host arrays
     e2e_res = None
     if e2e:
-        if hasattr(wl.dev, "materialise"):
-            wl.dev.materialise()
-        if getattr(wl, "dist_svr", None) is None:
-            wl.dev.resident(False)
+        if hasattr(wl, "e2e_begin"):
+            wl.e2e_begin()
+        else:
+            if hasattr(wl.dev, "materialise"):
+                wl.dev.materialise()
+            if getattr(wl, "dist_svr", None) is None:
+                wl.dev.resident(False)
         wl.e2e_step()
+        if hasattr(wl, "e2e_begin"):
+            wl._b0, wl._e2e_steps = (wl.dev.h2d_bytes, wl.dev.d2h_bytes), 0     # count the timed steps only
         n_e2e = max(1, min(steps, 3))
         barrier(dist, local)
         t0 = time.perf_counter()
@@ -605,9 +616,11 @@ def main():
     # (overlapped exchange), every rank's cells compared on rank 0 with the undecomposed device run
     if world > 1 and not args.no_parity and args.workload in ("md3d", "md3d_strong"):
         from solvcon_b200 import bench_md
-        nccl_parity, ok = bench_md.nccl_parity_3d(rank, world, local, dist, args.order)
+        nccl_parity, ok = bench_md.nccl_parity_3d(rank, world, local, dist, args.order, transport="lib")
+        torch_parity, ok2 = bench_md.nccl_parity_3d(rank, world, local, dist, args.order, transport="torch")
+        ok = ok and ok2
         if rank == 0:
-            parity = {"single_rank": parity, "decomposed": nccl_parity}
+            parity = {"single_rank": parity, "decomposed": nccl_parity, "decomposed_torch_transport": torch_parity}
         if not ok and bool(lib.scg_build_is_strict()):
             if rank == 0:
                 print(json.dumps({"error": "multi-rank parity leg failed", "parity": parity}), file=sys.stderr)

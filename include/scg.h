@@ -295,6 +295,25 @@ SCG_API int scg_md_halo_set(scg_md * s, const int32_t * send_cells, int64_t nsen
 SCG_API int scg_md_halo_pack(scg_md * s, int what, double ** dev_buffer, int64_t * ndouble);
 SCG_API int scg_md_halo_unpack(scg_md * s, int what, const double * dev_buffer);
 
+/* ---- the library's own communicator (csrc/scg_comm.cu) ----------------------------------------------------------
+ * No counterpart in the reference (it is single-process).  NCCL point-to-point calls are issued by the
+ * library on its own communication stream; libnccl is dlopen'ed (`libnccl_path` or the default soname; a copy already
+ * mapped into the process is reused), so the library links neither NCCL nor torch.  The caller only carries the
+ * 128-byte unique id from rank 0 to the other ranks (file, socket, MPI, torch.distributed ...). */
+SCG_API int scg_comm_unique_id(void * id128, int64_t nbytes, const char * libnccl_path); /* rank 0: ncclGetUniqueId */
+SCG_API int scg_comm_init(int rank, int nranks, const void * id128, const char * libnccl_path); /* ncclCommInitRank */
+SCG_API int scg_comm_info(int * rank, int * nranks, int * nccl_version);
+SCG_API int scg_comm_finalize(void);
+/* Neighbour table of a partition: for peer q its rank and its segment [begin, end) of the lists given to
+ * scg_md_halo_set (cells).  scg_md_halo_exchange = pack -> one ncclGroup of ncclSend/ncclRecv with every peer ->
+ * unpack, stream-ordered (no host synchronisation).  scg_md_march_dist(steps) = EulerCore::march of one partition:
+ * per substep the interface cells, the exchange on the communication stream overlapped with the interior cells and
+ * the boundary kernels, the unpack (euler_march.cpp:339-359 per partition; bit-identical for any number of parts). */
+SCG_API int scg_md_halo_peers(scg_md * s, int npeer, const int32_t * peer_rank, const int64_t * send_begin,
+                              const int64_t * send_end, const int64_t * recv_begin, const int64_t * recv_end);
+SCG_API int scg_md_halo_exchange(scg_md * s, int what);
+SCG_API int scg_md_march_dist(scg_md * s, int64_t steps);
+
 #ifdef __cplusplus
 }
 #endif

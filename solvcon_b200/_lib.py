@@ -84,6 +84,13 @@ _SIGNATURES = {
     "scg_hmesh_build_edge": (C.c_int, [C.c_void_p]),
     "scg_hmesh_add_bc": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]),
     "scg_hmesh_bc": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_char_p), C.POINTER(C.c_void_p), I64P]),
+    "scg_comm_unique_id": (C.c_int, [C.c_void_p, C.c_int64, C.c_char_p]),
+    "scg_comm_init": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_char_p]),
+    "scg_comm_info": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "scg_comm_finalize": (C.c_int, []),
+    "scg_md_halo_peers": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scg_md_halo_exchange": (C.c_int, [C.c_void_p, C.c_int]),
+    "scg_md_march_dist": (C.c_int, [C.c_void_p, C.c_int64]),
     "scg_hmesh_bc_rename": (C.c_int, [C.c_void_p, C.c_int64, C.c_char_p]),
     "scg_hmesh_drop_retired": (C.c_int, [C.c_void_p]),
     "scg_hmesh_build_boundary": (C.c_int, [C.c_void_p]),

@@ -96,9 +96,10 @@ def build_case_3d(ncell_target, order="morton", kinds="hpt", log=None):
     return mesh, svr, info
 
 
-def _finish_dist_case(part, dt, order, lo, hi, z_level, local_device, kinds, device="cuda"):
-    """Device solver of one partition with the bench's IC / BCs, halo geometry and state exchanged once."""
-    from .decomp import DistEulerCore, TorchExchange
+def _finish_dist_case(part, dt, order, lo, hi, z_level, local_device, kinds, transport="lib"):
+    """Device solver of one partition with the bench's IC / BCs, halo geometry and state exchanged once.
+    ``transport``: "lib" = the library's own NCCL communicator (NcclExchange), "torch" = torch.distributed."""
+    from .decomp import DistEulerCore, NcclExchange, TorchExchange
     mesh = part.build_mesh()
     svr = DistEulerCore(part, dt, order=order)
     inlet, outlet, wall = part.physical_boundary_groups(lo, hi)
@@ -113,7 +114,7 @@ def _finish_dist_case(part, dt, order, lo, hi, z_level, local_device, kinds, dev
     core.resident(True)
     core.bc_soln()
     core.bc_dsoln()
-    svr.transport = TorchExchange(svr, f"cuda:{local_device}")
+    svr.transport = NcclExchange(svr) if transport == "lib" else TorchExchange(svr, f"cuda:{local_device}")
     svr.transport.exchange(1)
     svr.transport.exchange(0)
     return mesh, svr
@@ -178,7 +179,7 @@ def build_case_3d_strong(ncell_total, rank, world, local_device, order="morton",
     return mesh, svr, info
 
 
-def nccl_parity_3d(rank, world, local_device, dist, order, ncell_target=120_000, steps=6):
+def nccl_parity_3d(rank, world, local_device, dist, order, ncell_target=120_000, steps=6, transport="lib"):
     """Multi-rank parity leg of bench.py (before anything is timed): a small stepped channel cut by ``lattice_rcb``
     into one part per rank and marched through the REAL transport (``TorchExchange.exchange_split``: NCCL send/recv on
     the communication stream, overlapped with the interior march); every rank's owned cells are gathered on rank 0 and
@@ -193,7 +194,7 @@ def nccl_parity_3d(rank, world, local_device, dist, order, ncell_target=120_000,
     ranges = lattice_rcb(nx, ny, nz, x1, z1, world, cost=CELL_COST)
     part = lattice_partition_3d(rank, ranges, nx, ny, nz, h, x1, z1, jitter=0.1)
     lo, hi = np.array([0.0, 0.0, 0.0]), np.array([nx * h, ny * h, nz * h])
-    mesh, svr = _finish_dist_case(part, dt, order, lo, hi, z1 * h, local_device, "hpt")
+    mesh, svr = _finish_dist_case(part, dt, order, lo, hi, z1 * h, local_device, "hpt", transport)
     svr.march(steps)
     _lib.sync()
     svr.core.materialise(("so0n", "so1n", "cflo", "cflc"))
@@ -223,7 +224,10 @@ def nccl_parity_3d(rank, world, local_device, dist, order, ncell_target=120_000,
                 equal = equal and bool(np.array_equal(a, c))
                 worst = max(worst, float(np.abs(a - c).max()) / (float(np.abs(c).max()) + 1e-300))
         result = {"cells": int(len(cltpn)), "parts": world, "steps": steps, "bit_equal": bool(equal and (seen == 1).all()),
-                  "max_rel_linf": worst, "transport": "TorchExchange.exchange_split over NCCL (overlapped)",
+                  "max_rel_linf": worst,
+                  "transport": ("scg_md_march_dist: ncclSend/ncclRecv issued by the library on its communication "
+                                "stream, overlapped with the interior march" if transport == "lib" else
+                                "TorchExchange.exchange_split: torch.distributed isend/irecv over NCCL, overlapped"),
                   "against": "undecomposed device march of the same case",
                   "halo_cells_sent_by_rank0": int(svr.nsend)}
     flag = torch.tensor([1 if (result is None or result["bit_equal"]) else 0], device=f"cuda:{local_device}")
@@ -337,25 +341,38 @@ class MD3DWorkload:
         else:
             self.dev.march(self.chunk)
 
+    E2E_IN = ("so0n", "so1n", "gamma")      # the host arrays a march() reads: solution, gradient, gamma
+    E2E_OUT = ("so0n", "so1n", "cflo")      # what the caller gets back: the new solution + gradient and the CFL table
+
+    def e2e_begin(self):
+        """The caller's side of the end-to-end arm: a front end that HOLDS views of its field arrays, like the
+        reference's (``tests/multidim/euler/test_field.py:50-83``, ``solvcon/multidim/euler/_field.py:53-54,124-125``).
+        Held views are what makes ``EulerCore.march`` move bytes: it uploads every held array it reads and refreshes
+        every held array it wrote (solvcon_b200/multidim.py, "coherence")."""
+        d = self.dev
+        d.materialise(tuple(set(self.E2E_IN + self.E2E_OUT)))
+        if self.dist_svr is None:
+            d.resident(False)
+            self._views = [getattr(d, n).ndarray for n in set(self.E2E_IN + self.E2E_OUT)]
+        self._b0 = (d.h2d_bytes, d.d2h_bytes)
+        self._e2e_steps = 0
+
     def e2e_step(self):
+        d = self.dev
         if self.dist_svr is not None:
-            # host arrays in, host arrays out, around the distributed march
-            self.dev._push(force=True)
+            # the distributed march keeps the field resident; the same arrays travel through the explicit calls
+            d.upload(self.E2E_IN)
             self.dist_svr.march(self.chunk)
-            self.dev.sync_to_host()
+            d.download(self.E2E_OUT)
         else:
-            self.dev.march(self.chunk)
+            d.march(self.chunk)
+        self._e2e_steps += 1
 
     def e2e_bytes(self):
-        # EulerCore.march with host arrays: so0n, so1n, gamma go up in full and the ghost rows of so0c, so1c, cflo,
-        # cflc; every state array but gamma comes back (the distributed arm moves the whole state both ways)
-        T, ng = self.ncell + self.info["ngstcell"], self.info["ngstcell"]
-        nd = 3
-        neq = nd + 2
-        per_row = 8 * (3 * neq + 2 * neq * nd + 3)
-        if self.dist_svr is not None:
-            return T * per_row, T * per_row
-        return 8 * (T * (neq + neq * nd + 1) + ng * (neq + neq * nd + 2)), T * (per_row - 8)
+        """Bytes per step actually copied by the library during the end-to-end arm (counted at every transfer)."""
+        d = self.dev
+        n = max(1, self._e2e_steps)
+        return (d.h2d_bytes - self._b0[0]) // n, (d.d2h_bytes - self._b0[1]) // n
 
     def result_check(self):
         return float(self.dev.so0n.body[:, 0].sum())
@@ -476,13 +493,6 @@ class MD2DWorkload(MD3DWorkload):
                 "alg_bytes_per_cell_substep": balg / ncell,
                 "l2_policy": "inputs larger than L2 (%.1f GB streamed per substep)" % (balg / 1e9),
                 "decomposition": "none", "mesh": info}
-
-    def e2e_bytes(self):
-        T, ng = self.ncell + self.info["ngstcell"], self.info["ngstcell"]
-        nd = 2
-        neq = nd + 2
-        per_row = 8 * (3 * neq + 2 * neq * nd + 3)
-        return 8 * (T * (neq + neq * nd + 1) + ng * (neq + neq * nd + 2)), T * (per_row - 8)
 
     def cpu_run(self, budget_s=15.0):
         import bench_cpu

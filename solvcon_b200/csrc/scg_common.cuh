@@ -56,6 +56,16 @@ int sm_count();
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// ---- communicator (scg_comm.cu): NCCL send/recv on the library's communication stream ---------------------------
+bool comm_ready();
+int comm_rank();
+int comm_nranks();
+cudaStream_t comm_stream();
+int comm_group_start();
+int comm_group_end();
+int comm_send(double const * buf, int64_t count, int peer);
+int comm_recv(double * buf, int64_t count, int peer);
+
 // device buffer with RAII; move-only
 template <typename T>
 struct DevBuf

@@ -1258,8 +1258,21 @@ struct scg_md
     DevBuf<double> bc_mat, bc_val;
     // halo
     DevBuf<int32_t> halo_send, halo_recv;
-    DevBuf<double> halo_buf;
+    DevBuf<double> halo_buf, halo_rbuf;
     int64_t nsend = 0, nrecv = 0;
+    // neighbour ranks of the partition: segment [begin, end) of each peer in the send list and in the recv list
+    struct Peer
+    {
+        int rank;
+        int64_t sb, se, rb, re;
+    };
+    std::vector<Peer> peers;
+    cudaEvent_t ev_packed = nullptr, ev_recv = nullptr;
+    ~scg_md()
+    {
+        if (ev_packed) { cudaEventDestroy(ev_packed); }
+        if (ev_recv) { cudaEventDestroy(ev_recv); }
+    }
 };
 
 namespace
@@ -2145,6 +2158,96 @@ int scg_md_halo_unpack(scg_md * s, int what, const double * dev_buffer)
             s->so0[1 - s->cur].p, s->so1[1 - s->cur].p, s->solpt.p, s->gamma.p, what, s->halo_recv.p, s->nrecv, s->neq, s->ndim,
             s->mesh->stride, dev_buffer);
         count_launch();
+    }
+    SCG_CUDA(cudaGetLastError());
+    return 0;
+}
+
+
+// ---- halo exchange issued by the library itself (scg_comm.cu): stream-ordered, no host synchronisation ------------
+// pack on the compute stream -> event -> grouped ncclSend / ncclRecv with every neighbour rank on the communication
+// stream -> event -> unpack on the compute stream.  Between begin and end the caller may enqueue the interior march on
+// the compute stream: it runs while the messages travel.
+static int halo_exchange_begin(scg_md * s, int what)
+{
+    SCG_REQUIRE(comm_ready(), "scg_md_halo_exchange: no communicator (call scg_comm_init first)");
+    int64_t const width = (0 == what) ? s->neq * (1 + s->ndim) : s->ndim + 1;
+    if (!s->ev_packed)
+    {
+        SCG_CUDA(cudaEventCreateWithFlags(&s->ev_packed, cudaEventDisableTiming));
+        SCG_CUDA(cudaEventCreateWithFlags(&s->ev_recv, cudaEventDisableTiming));
+    }
+    double * sendbuf = nullptr;
+    int64_t nd = 0;
+    if (int rc = scg_md_halo_pack(s, what, &sendbuf, &nd)) { return rc; }
+    SCG_CUDA(cudaEventRecord(s->ev_packed, stream()));
+    SCG_CUDA(cudaStreamWaitEvent(comm_stream(), s->ev_packed, 0));
+    if (int rc = comm_group_start()) { return rc; }
+    for (auto const & p : s->peers)
+    {
+        if (p.se > p.sb)
+        {
+            if (int rc = comm_send(sendbuf + p.sb * width, (p.se - p.sb) * width, p.rank)) { return rc; }
+        }
+        if (p.re > p.rb)
+        {
+            if (int rc = comm_recv(s->halo_rbuf.p + p.rb * width, (p.re - p.rb) * width, p.rank)) { return rc; }
+        }
+    }
+    if (int rc = comm_group_end()) { return rc; }
+    SCG_CUDA(cudaEventRecord(s->ev_recv, comm_stream()));
+    return 0;
+}
+
+static int halo_exchange_end(scg_md * s, int what)
+{
+    SCG_CUDA(cudaStreamWaitEvent(stream(), s->ev_recv, 0));
+    return scg_md_halo_unpack(s, what, s->halo_rbuf.p);
+}
+
+int scg_md_halo_peers(scg_md * s, int npeer, const int32_t * peer_rank, const int64_t * send_begin, const int64_t * send_end,
+                      const int64_t * recv_begin, const int64_t * recv_end)
+{
+    SCG_REQUIRE(s && npeer >= 0, "scg_md_halo_peers: bad argument");
+    SCG_REQUIRE(0 == npeer || (peer_rank && send_begin && send_end && recv_begin && recv_end), "scg_md_halo_peers: null table");
+    std::vector<scg_md::Peer> peers;
+    for (int q = 0; q < npeer; ++q)
+    {
+        SCG_REQUIRE(0 <= send_begin[q] && send_begin[q] <= send_end[q] && send_end[q] <= s->nsend,
+                    "scg_md_halo_peers: send segment of peer %d outside the send list", q);
+        SCG_REQUIRE(0 <= recv_begin[q] && recv_begin[q] <= recv_end[q] && recv_end[q] <= s->nrecv,
+                    "scg_md_halo_peers: recv segment of peer %d outside the recv list", q);
+        peers.push_back({peer_rank[q], send_begin[q], send_end[q], recv_begin[q], recv_end[q]});
+    }
+    s->peers = std::move(peers);
+    int64_t const width = s->neq * (1 + s->ndim);
+    SCG_CUDA(s->halo_rbuf.alloc_zero((s->nrecv > 0 ? s->nrecv : 1) * width));
+    SCG_CUDA(cudaStreamSynchronize(stream()));
+    return 0;
+}
+
+int scg_md_halo_exchange(scg_md * s, int what)
+{
+    SCG_REQUIRE(s, "scg_md_halo_exchange: null solver");
+    if (int rc = halo_exchange_begin(s, what)) { return rc; }
+    return halo_exchange_end(s, what);
+}
+
+// march of one partition: per substep the interface cells first, their message packed and handed to
+// the communication stream, the interior cells and the boundary kernels meanwhile, then the unpack.  Same kernels and
+// the same order as the two-stage substep the caller can drive through scg_md_phase; bit-identical to scg_md_march of
+// the undecomposed mesh for any number of parts.
+int scg_md_march_dist(scg_md * s, int64_t steps)
+{
+    SCG_REQUIRE(s, "scg_md_march_dist: null solver");
+    SCG_REQUIRE(3 == s->fused, "scg_md_march_dist: needs march mode 3");
+    if (steps <= 0) { return 0; }
+    for (int64_t it = 0; it < 2 * steps; ++it) // SUBSTEP_RUN = 2, euler.hpp:165
+    {
+        if (int rc = substep_split(s, 0)) { return rc; }
+        if (int rc = halo_exchange_begin(s, 0)) { return rc; }
+        if (int rc = substep_split(s, 1)) { return rc; }
+        if (int rc = halo_exchange_end(s, 0)) { return rc; }
     }
     SCG_CUDA(cudaGetLastError());
     return 0;

@@ -22,9 +22,10 @@ passive layer behind it:
 Results are bit-identical to the single-domain run for any number of parts
 (``tests/test_gpu_decomp.py``, ``tests/test_decomp_gloo.py``).
 
-Transport: :class:`LocalExchange` (all partitions in one process: tests, one GPU) or
-:class:`TorchExchange` (``torch.distributed``: NCCL send/recv of the packed device buffers between GPUs over
-NVLink, gloo for the CPU tests).
+Transport: :class:`NcclExchange` (the product path: the library's own communicator, ``csrc/scg_comm.cu`` -- ncclSend /
+ncclRecv issued from C++ on the library's communication stream, the whole overlapped march one C call, no torch),
+:class:`TorchExchange` (``torch.distributed`` isend/irecv of the packed buffers: NCCL between GPUs, gloo for the
+CPU tests of the exchange logic) or :class:`LocalExchange` (all partitions in one process: tests, one GPU).
 
 Overlap: the owned cells whose state a neighbour needs (*interface* cells, ``owned == 2``) are stored first in
 their type group and marched first (``EulerCore.substep_interface``); their message is packed on the compute
@@ -436,6 +437,90 @@ class TorchExchange:
             s.core.halo_unpack(rb.data_ptr(), what)
 
 
+def _libnccl_path():
+    """Where this environment keeps libnccl (the wheel torch depends on), for ``scg_comm_*``'s dlopen; None lets the
+    library try the default soname (a copy already mapped into the process is reused either way)."""
+    import glob
+    import os
+    import sys
+    for root in sys.path:
+        hits = glob.glob(os.path.join(root, "nvidia", "nccl", "lib", "libnccl.so*"))
+        if hits:
+            return sorted(hits)[0]
+    return None
+
+
+def comm_init(rank, world, dist=None, id_file=None, timeout=120.0):
+    """Create the LIBRARY's communicator (``scg_comm_init``: NCCL inside libscg_cuda, csrc/scg_comm.cu).  Only the
+    128-byte unique id travels out of band: through ``torch.distributed`` if a process group is given (any backend),
+    else through ``id_file`` (rank 0 writes it, the others poll) -- the product path needs no torch."""
+    import ctypes as C
+    import os
+    import time
+    from . import _lib
+    lib = _lib.load()
+    path = _libnccl_path()
+    cpath = path.encode() if path else None
+    buf = (C.c_char * 128)()
+    if rank == 0:
+        _lib.check(lib.scg_comm_unique_id(buf, 128, cpath))
+    if dist is not None:
+        box = [bytes(buf.raw) if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        raw = box[0]
+    else:
+        if id_file is None:
+            raise ValueError("comm_init: give a torch.distributed module or an id_file")
+        if rank == 0:
+            with open(id_file + ".tmp", "wb") as f:
+                f.write(bytes(buf.raw))
+            os.replace(id_file + ".tmp", id_file)
+            raw = bytes(buf.raw)
+        else:
+            t0 = time.monotonic()
+            while not os.path.exists(id_file):
+                if time.monotonic() - t0 > timeout:
+                    raise TimeoutError(f"comm_init: {id_file} did not appear")
+                time.sleep(0.05)
+            with open(id_file, "rb") as f:
+                raw = f.read()
+    idbuf = (C.c_char * 128).from_buffer_copy(raw)
+    _lib.check(lib.scg_comm_init(int(rank), int(world), idbuf, cpath))
+    ver = C.c_int()
+    lib.scg_comm_info(None, None, C.byref(ver))
+    return int(ver.value)
+
+
+class NcclExchange:
+    """Transport through the library's own communicator: every exchange is ONE C call (pack kernel, one ncclGroup of
+    ncclSend / ncclRecv with all neighbour ranks on the library's communication stream, unpack kernel; stream-ordered,
+    no host synchronisation), and ``march`` is ``scg_md_march_dist`` -- the whole overlapped march in C++.  No torch
+    on this path.  Bit-identical to :class:`TorchExchange` and to the undecomposed march."""
+
+    def __init__(self, solver):
+        from . import _lib
+        self.s = solver
+        self._lib = _lib.load()
+        nb = solver.part.neighbours
+        ranks = np.array(nb, dtype=np.int32)
+        sb = np.array([solver.send_offsets[q][0] for q in nb], dtype=np.int64)
+        se = np.array([solver.send_offsets[q][1] for q in nb], dtype=np.int64)
+        rl = np.array([len(solver.part.recv.get(q, ())) for q in nb], dtype=np.int64)
+        re = np.cumsum(rl)
+        rb = re - rl
+        p = lambda a: _lib.ptr(a) if len(a) else None  # noqa: E731
+        _lib.check(self._lib.scg_md_halo_peers(solver.core._h, len(nb), p(ranks), p(sb), p(se), p(rb), p(re)))
+
+    def exchange(self, what):
+        from . import _lib
+        _lib.check(self._lib.scg_md_halo_exchange(self.s.core._h, int(what)))
+
+    def march(self, steps):
+        from . import _lib
+        _lib.check(self._lib.scg_md_march_dist(self.s.core._h, int(steps)))
+        self.s.core._pull()     # the device holds newer data than any host copy
+
+
 # ------------------------------------------------------------------------------------- solver ---
 
 class HaloSolver:
@@ -460,6 +545,8 @@ class HaloSolver:
         self._scratch = None
 
     def march(self, steps):
+        if hasattr(self.transport, "march"):       # the library marches the partition itself (NcclExchange)
+            return self.transport.march(steps)
         split = getattr(self.transport, "exchange_split", None)
         for _ in range(2 * int(steps)):
             if split is not None:

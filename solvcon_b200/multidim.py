@@ -17,6 +17,7 @@ raises.
 from __future__ import annotations
 
 import ctypes as C
+import sys
 
 import numpy as np
 
@@ -34,6 +35,17 @@ ARRAY_IDS = {"cevol": 0, "cecnd": 1, "sfcnd": 2, "sfnml": 3, "so0c": 4, "so0n": 
 _GEOMETRY = ("cevol", "cecnd", "sfcnd", "sfnml")
 _STATE = ("so0c", "so0n", "so0t", "so1c", "so1n", "cflo", "cflc", "gamma")
 CLMFC, FCMND = 6, 4
+
+
+def _refcount_baseline():
+    """Reference counts of a SimpleArray held only by a dict, and of its ndarray, measured the way
+    ``EulerCore._held`` reads them."""
+    d = {"x": SimpleArray((1,))}
+    sa = d.get("x")
+    return sys.getrefcount(sa), sys.getrefcount(sa._a)
+
+
+_REF_SA, _REF_ND = _refcount_baseline()
 
 
 def _raise(exc=None):
@@ -124,16 +136,24 @@ class EulerCore:
         self._sigma0, self._taumin, self._tauscale = 3.0, 0.0, 1.0  # euler.hpp:184-188
         self._resident = False
         self._geo_seen = {}
+        self._stale, self._exposed = set(), set()   # see "coherence" below
+        self.h2d_bytes = self.d2h_bytes = 0
 
-    def _get(self, name):
-        """The host SimpleArray of ``name``; on first access it is allocated and filled from the device."""
+    def _get(self, name, expose=True):
+        """The host SimpleArray of ``name``; on first access it is allocated and filled from the device, later it is
+        refreshed when the device holds newer data.  ``expose``: the caller receives it and may write into it."""
         a = self._a.get(name)
+        if a is not None and name in self._stale:
+            self._download(name)
+        if expose and name in ARRAY_IDS:
+            self._exposed.add(name)
         if a is None:
             shape, ng = self._shapes[name]
             a = SimpleArray(shape, 0.0, nghost=ng, pinned=name in ARRAY_IDS and self._h.value is not None)
             self._a[name] = a
             if name in ARRAY_IDS and self._h.value is not None:
                 _lib.check(self._lib.scg_md_download(self._h, ARRAY_IDS[name], _lib.ptr(a.ndarray)))
+                self.d2h_bytes += a.ndarray.nbytes
             if name in _GEOMETRY:
                 self._geo_seen[name] = a.ndarray.copy()
         return a
@@ -176,12 +196,50 @@ class EulerCore:
     gamma = property(lambda self: self._get("gamma"))
 
     # -- coherence ---------------------------------------------------------------------------------
-    def _push(self, names=_STATE, force=False):
+    # Host arrays are the API-visible storage, but only bytes somebody can observe travel:
+    #   * a host array is UPLOADED before a compute call iff the caller may have written it since the last upload:
+    #     it was handed out by its property since then (``_exposed``) or the caller still holds it / a view of it
+    #     (reference count of the SimpleArray or of its ndarray, ``_held``);
+    #   * after a compute call every array the device wrote is marked STALE; it is DOWNLOADED at once iff the caller
+    #     holds it or a view of it (the reference's views alias live solver memory: held views stay current), else
+    #     at the next access through its property.
+    # So ``march(); svr.so0n`` moves so0n and nothing else, and a front end that holds views of everything gets
+    # everything, exactly as it would read it from the reference's memory.  ``h2d_bytes`` / ``d2h_bytes`` count the
+    # bytes actually copied.  ``resident(True)`` suspends all implicit transfers (the caller promises not to write the
+    # host arrays); arrays are still refreshed when accessed through their property.
+    def _held(self, name):
+        sa = self._a.get(name)
+        if sa is None:
+            return False
+        return sys.getrefcount(sa) > _REF_SA or sys.getrefcount(sa._a) > _REF_ND
+
+    def _upload(self, name, rows=None):
+        a = self._a[name].ndarray
+        if rows is None:
+            _lib.check(self._lib.scg_md_upload(self._h, ARRAY_IDS[name], _lib.ptr(a)))
+            self.h2d_bytes += a.nbytes
+        elif rows[1] > rows[0]:
+            _lib.check(self._lib.scg_md_upload_rows(self._h, ARRAY_IDS[name], _lib.ptr(a), rows[0], rows[1]))
+            self.h2d_bytes += (rows[1] - rows[0]) * (a.nbytes // max(a.shape[0], 1))
+
+    def _download(self, name):
+        a = self._a[name].ndarray
+        _lib.check(self._lib.scg_md_download(self._h, ARRAY_IDS[name], _lib.ptr(a)))
+        self.d2h_bytes += a.nbytes
+        self._stale.discard(name)
+
+    def _dirty(self, name):
+        return name in self._a and name not in self._stale and (name in self._exposed or self._held(name))
+
+    def _push(self, names=_STATE, force=False, ghost_only=()):
+        """Before a compute call: upload what the caller may have written (``force``: every host copy that is not
+        older than the device's).  ``ghost_only``: arrays whose body rows the call overwrites before reading them."""
         if self._resident and not force:
             return
         for n in names:
-            if n in self._a:
-                _lib.check(self._lib.scg_md_upload(self._h, ARRAY_IDS[n], _lib.ptr(self._a[n].ndarray)))
+            if n in self._a and n not in self._stale and (force or self._dirty(n)):
+                self._upload(n, (0, self._ngst) if n in ghost_only else None)
+                self._exposed.discard(n)
         # the CE geometry only travels when the caller wrote into it
         for n in _GEOMETRY:
             if n not in self._a:
@@ -189,36 +247,66 @@ class EulerCore:
             cur = self._a[n].ndarray
             if not np.array_equal(cur, self._geo_seen[n]):
                 _lib.check(self._lib.scg_md_upload(self._h, ARRAY_IDS[n], _lib.ptr(cur)))
+                self.h2d_bytes += cur.nbytes
                 self._geo_seen[n] = cur.copy()
 
     def _pull(self, names=_STATE, force=False):
-        if self._resident and not force:
-            return
+        """After a compute call that wrote ``names`` on the device: held arrays are refreshed now, the others when
+        they are next accessed.  ``force``: refresh every materialised one now."""
         for n in names:
-            if n in self._a:
-                _lib.check(self._lib.scg_md_download(self._h, ARRAY_IDS[n], _lib.ptr(self._a[n].ndarray)))
+            if n not in self._a:
+                continue
+            self._stale.add(n)
+            self._exposed.discard(n)
+            if force or (not self._resident and self._held(n)):
+                self._download(n)
+
+    def upload(self, names=_STATE):
+        """Additive API: push the named host arrays to the device now (resident mode: after host-side edits)."""
+        for n in names:
+            if n in self._a and n not in self._stale:
+                self._upload(n)
+                self._exposed.discard(n)
+
+    def download(self, names=_STATE):
+        """Additive API: bring the named arrays to the host now."""
+        for n in names:
+            self._get(n)
+            if n in self._stale:
+                self._download(n)
 
     def resident(self, flag=True):
-        """Keep the field on the device between calls (uploads once now)."""
+        """Keep the field on the device between calls: no implicit transfers until ``resident(False)`` /
+        ``sync_to_host()`` (uploads the host copies once now)."""
         if flag and not self._resident:
             self._push(force=True)
-        if not flag and self._resident:
-            self.sync_to_host()
         self._resident = bool(flag)
+        if not flag:
+            self.sync_to_host()
         return self
 
     def sync_to_host(self):
-        self._pull(force=True)
+        for n in list(self._stale):
+            if n in self._a:
+                self._download(n)
 
     def _swap_host(self):
         a = self._a
         for c, n in (("so0c", "so0n"), ("so1c", "so1n")):
             a[c], a[n] = a[n], a[c]
+            for flags in (self._stale, self._exposed):
+                hc, hn = c in flags, n in flags
+                flags.discard(c)
+                flags.discard(n)
+                if hc:
+                    flags.add(n)
+                if hn:
+                    flags.add(c)
 
     def materialise(self, names=_STATE):
         """Allocate (and fill from the device) the named host arrays now."""
         for n in names:
-            self._get(n)
+            self._get(n, expose=False)
         return self
 
     def _phase(self, phase):
@@ -232,10 +320,12 @@ class EulerCore:
         self._push()
         if self._lib.scg_md_phase(self._h, MD_PREPARE_CE):
             _raise()
-        self._pull(_GEOMETRY, force=True)
         for n in _GEOMETRY:
             if n in self._a:
-                self._geo_seen[n] = self._a[n].ndarray.copy()
+                a = self._a[n].ndarray
+                _lib.check(self._lib.scg_md_download(self._h, ARRAY_IDS[n], _lib.ptr(a)))
+                self.d2h_bytes += a.nbytes
+                self._geo_seen[n] = a.copy()
 
     def init_solution(self, gamma, rho, v, p):
         v = list(v)
@@ -249,22 +339,19 @@ class EulerCore:
 
     # -- march (wrap_multidim.cpp:309-327) -----------------------------------------------------------------
     def march(self, steps):
-        if int(steps) < 1 or self._resident:
+        if int(steps) < 1:
             self._push()
         else:
             # march(steps >= 1) reads so0n / so1n (they become so0c / so1c at the first update()) and gamma; every
-            # body row of the other state arrays is overwritten before it is read, and so0t on all rows.  Their
-            # ghost rows are not all rewritten (unregistered ghosts, cflo / cflc), so those still travel.
-            for n in ("so0n", "so1n", "gamma"):
-                if n in self._a:
-                    _lib.check(self._lib.scg_md_upload(self._h, ARRAY_IDS[n], _lib.ptr(self._a[n].ndarray)))
-            for n in ("so0c", "so1c", "cflo", "cflc"):
-                if n in self._a and self._ngst:
-                    _lib.check(self._lib.scg_md_upload_rows(self._h, ARRAY_IDS[n], _lib.ptr(self._a[n].ndarray), 0, self._ngst))
-            self._push(names=())   # the CE geometry, when the caller wrote into it
+            # body row of so0c / so1c / cflo / cflc is overwritten before it is read (their ghost rows are not all
+            # rewritten: unregistered ghosts), and so0t on all rows
+            self._push(names=("so0n", "so1n", "gamma", "so0c", "so1c", "cflo", "cflc"),
+                       ghost_only=("so0c", "so1c", "cflo", "cflc"))
+            self._exposed.discard("so0t")
         if self._lib.scg_md_march(self._h, int(steps)):
             _raise()
-        self._pull(tuple(n for n in _STATE if n != "gamma") if int(steps) >= 1 else _STATE)
+        if int(steps) >= 1:
+            self._pull(tuple(n for n in _STATE if n != "gamma"))
 
     def march_substep(self):
         self.materialise(("so0c", "so0n", "so1c", "so1n"))
@@ -277,6 +364,7 @@ class EulerCore:
     def update(self):
         # pointer swap on both sides (euler.hpp:123-127): views taken earlier alias the other buffer
         self.materialise(("so0c", "so0n", "so1c", "so1n"))
+        self._push(names=("so0c", "so0n", "so1c", "so1n"))
         _lib.check(self._lib.scg_md_phase(self._h, MD_UPDATE))
         self._swap_host()
 
@@ -379,22 +467,33 @@ class EulerCore:
 
     def halo_unpack(self, dev_ptr, what=0):
         _lib.check(self._lib.scg_md_halo_unpack(self._h, int(what), C.c_void_p(dev_ptr)))
+        self._device_wrote()
+
+    def _device_wrote(self):
+        """A resident-mode call changed the state on the device: every materialised host copy is now older."""
+        for n in _STATE:
+            if n in self._a:
+                self._stale.add(n)
+                self._exposed.discard(n)
 
     def substep_local(self):
         """One march_substep of this partition without any host transfer (resident mode only)."""
         if self._lib.scg_md_phase(self._h, MD_SUBSTEP):
             _raise()
+        self._device_wrote()
 
     def substep_interface(self):
         """First stage of a split substep: update(), calc_solt, then the owned INTERFACE cells (``owned == 2``);
         their state may be packed and sent as soon as this returns (stream order)."""
         if self._lib.scg_md_phase(self._h, MD_SUBSTEP_IFACE):
             _raise()
+        self._device_wrote()
 
     def substep_rest(self):
         """Second stage of a split substep: the interior cells and the boundary kernels."""
         if self._lib.scg_md_phase(self._h, MD_SUBSTEP_REST):
             _raise()
+        self._device_wrote()
 
     def algorithmic_bytes(self):
         """Algorithmic bytes one substep moves on this mesh."""

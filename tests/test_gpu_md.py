@@ -352,6 +352,51 @@ def test_march_sees_host_edits_between_calls(gpu, bridge):
     c.same("march after host edits", STATE, _strict(gpu))
 
 
+def test_only_observable_bytes_travel(gpu, bridge):
+    """The coherence protocol of EulerCore (solvcon_b200/multidim.py): an array crosses the bus only when somebody can
+    observe it -- uploaded iff the caller may have written it (handed out since the last upload, or still held),
+    downloaded at once iff the caller holds it or a view of it, else at the next access.  Results never depend on it."""
+    b = bridge
+    c = Case(b, "mixed3d", order="morton")
+    dev, chk = c.dev, c.chk
+    chk.phase(b.MD_BC_SOLN)
+    chk.phase(b.MD_BC_DSOLN)
+    dev.bc_soln()
+    dev.bc_dsoln()
+    T = dev.ncell + dev.ngstcell
+    # 1. nothing held, nothing handed out: march() moves no bytes at all
+    dev.sync_to_host()
+    dev._exposed.clear()
+    h0, d0 = dev.h2d_bytes, dev.d2h_bytes
+    chk.march(2)
+    dev.march(2)
+    assert (dev.h2d_bytes, dev.d2h_bytes) == (h0, d0)
+    # 2. the next access refreshes exactly the array asked for
+    rho = dev.so0n.ndarray
+    assert dev.d2h_bytes - d0 == rho.nbytes == T * 5 * 8
+    assert np.array_equal(rho, chk.arr("so0n"))
+    # 3. a HELD view is uploaded before and refreshed after every march, like a view of the reference's live memory
+    d1, h1 = dev.d2h_bytes, dev.h2d_bytes
+    rho[dev.ngstcell + 3, 0] *= 1.001
+    chk.arr("so0n")[dev.ngstcell + 3, 0] *= 1.001
+    chk.march(2)
+    dev.march(2)
+    assert dev.h2d_bytes - h1 == rho.nbytes and dev.d2h_bytes - d1 == rho.nbytes
+    assert np.array_equal(rho, chk.arr("so0n"))
+    del rho
+    # 4. arrays nobody looked at are still right when finally read
+    c.same("lazy refresh", STATE, _strict(gpu))
+    # 5. resident mode: no implicit transfer in either direction, property access still returns current data
+    dev.resident(True)
+    h2, d2 = dev.h2d_bytes, dev.d2h_bytes
+    chk.march(1)
+    dev.march(1)
+    assert (dev.h2d_bytes, dev.d2h_bytes) == (h2, d2)
+    assert np.array_equal(dev.cflo.ndarray, chk.arr("cflo"))
+    dev.resident(False)
+    c.same("after resident", STATE, _strict(gpu))
+
+
 @pytest.mark.parametrize("name", ["one_quad", "two_tri", "one_hex", "six_tet", "two_prism", "six_pyramid"])
 @pytest.mark.parametrize("fused", [3, 0])
 def test_md_smallest_meshes(gpu, bridge, name, fused):
