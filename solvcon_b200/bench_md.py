@@ -368,6 +368,26 @@ class MD3DWorkload:
             d.march(self.chunk)
         self._e2e_steps += 1
 
+    def e2e_fields_only(self, steps=2):
+        """Second end-to-end pattern, reported next to the full-state one: the reference's own session loop
+        (``solvcon/pilot/apps/obsrefl/_session.py:123-140``: march a chunk, then read the CFL range and the overall
+        mass through EulerField, i.e. ``cflo`` and ``so0n``) -- the caller holds views of those two arrays only, so
+        the gradient never crosses the bus.  Single-GPU arm; returns updates/s and the bytes per step."""
+        if self.dist_svr is not None:
+            return None
+        d = self.dev
+        self._views = [d.so0n.ndarray, d.cflo.ndarray]
+        d.march(self.chunk)
+        b0 = (d.h2d_bytes, d.d2h_bytes)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            d.march(self.chunk)
+            chk = float(self._views[1].max())
+        el = time.perf_counter() - t0
+        return {"value": self.updates_per_step() * steps / el, "unit": UNIT, "steps": steps,
+                "h2d_bytes_per_step": (d.h2d_bytes - b0[0]) // steps, "d2h_bytes_per_step": (d.d2h_bytes - b0[1]) // steps,
+                "pattern": "caller holds views of so0n and cflo only (the reference's session loop)", "cflo_max": chk}
+
     def e2e_bytes(self):
         """Bytes per step actually copied by the library during the end-to-end arm (counted at every transfer)."""
         d = self.dev
