@@ -226,7 +226,7 @@ class ST1DWorkload:
                 "l2_policy": "inputs larger than L2 (%.1f GB state per GPU)" % (self.ncelm * 2 * 32 / 1e9),
                 "decomposition": "none" if world == 1 else
                 "contiguous slabs on a ring, one per GPU; {so0, so1} of the two odd-plane end points exchanged with "
-                "both neighbours by NCCL send/recv once per step (32 B per rank per step)"}
+                "both neighbours by ncclSend/ncclRecv from the library once per step (32 B per rank per step)"}
 
     def updates_per_step(self):
         return (2 * self.ncelm + 1) * self.chunk
@@ -254,9 +254,9 @@ class ST1DWorkload:
         if world > 1:
             # weak scaling: the ring is `world` copies of the span; every rank generates its own slab's coordinates
             # (bit-parity of the decomposition against one global grid is what tests/test_gpu_1d.py checks)
-            from solvcon_b200.decomp1d import TorchRing
+            from solvcon_b200.decomp1d import NcclRing
             xs = st.Grid(rank * span, (rank + 1) * span, n).xcoord.ndarray
-            self.ring = TorchRing(self.eq, xs, 0, n, self.dt, f"cuda:{self.local}")
+            self.ring = NcclRing(self.eq, xs, 0, n, self.dt, rank, world)   # the library's own communicator
             self.dev = self.ring.slab.svr
         else:
             grid = st.Grid(0.0, span, n)

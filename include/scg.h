@@ -107,6 +107,10 @@ SCG_API int scg_st_march_half(scg_st * s, int half, int alpha);
 /* dev_send_left / right: 2 doubles each on the device ({so0, so1} of the first / last odd-plane point) */
 SCG_API int scg_st_halo_pack(scg_st * s, int odd_plane, double * dev_send_left, double * dev_send_right);
 SCG_API int scg_st_halo_unpack(scg_st * s, int odd_plane, const double * dev_recv_left, const double * dev_recv_right);
+/* march_alpha<A>(steps) of one slab of the periodic ring over the library's communicator (scg_comm_init): per step
+ * half 1, the two boundary points to / from the ring neighbours by ncclSend/ncclRecv on the communication stream,
+ * half 2.  core.hpp:1006-1036 with treat_boundary_so0/so1 (core.hpp:982-1004) done across ranks. */
+SCG_API int scg_st_march_ring(scg_st * s, int alpha, int64_t steps, int left_rank, int right_rank);
 
 /* ---------------------------------------------------------------- 1D Euler
  * replaces onedim::Euler1DCore (cpp/solvcon/onedim/Euler1DCore.hpp:41-145,

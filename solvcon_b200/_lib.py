@@ -84,6 +84,7 @@ _SIGNATURES = {
     "scg_hmesh_build_edge": (C.c_int, [C.c_void_p]),
     "scg_hmesh_add_bc": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]),
     "scg_hmesh_bc": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_char_p), C.POINTER(C.c_void_p), I64P]),
+    "scg_st_march_ring": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int]),
     "scg_comm_unique_id": (C.c_int, [C.c_void_p, C.c_int64, C.c_char_p]),
     "scg_comm_init": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_char_p]),
     "scg_comm_info": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),

@@ -637,6 +637,19 @@ __device__ __forceinline__ void cp_async8(double * smem_dst, double const * gsrc
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// Ask L2 for the line holding *p: no register, no scoreboard.  Used for data THIS thread reads a few microseconds
+// later (later faces / later equations of its own cell), so that the staged copies and gathers meet L2 instead of HBM.
+__device__ __forceinline__ void l2_prefetch(void const * p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+#ifndef SCG_SOLN_L2PF
+#define SCG_SOLN_L2PF 0 // 1: geometry rows of faces >= 2 at the top of the cell; 2: + the neighbour rows of faces >= 2
+#endif
+#ifndef SCG_EQO_GSMEM_MASK
+#define SCG_EQO_GSMEM_MASK 0 // 3D cell types whose new gradient is parked in shared memory for the fused calc_solt: 1 hex, 2 tet, 4 prism
+#endif
+#ifndef SCG_EQO_L2PF
+#define SCG_EQO_L2PF 0 // 1: the neighbour rows of equations >= 1 (>= 2 with register prefetch) right after the geometry
+#endif
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
@@ -878,6 +891,44 @@ __device__ __forceinline__ void cell_soln_staged(MdField const & F, MdGeo const 
     for (int d = 0; d < ND; ++d) { cc[d] = F.solpt[d * F.S + G.beg + i]; }
     dist = DBL_MAX;
     dist_ok = true;
+#if SCG_SOLN_L2PF
+    // the staged copies run ONE face ahead; faces >= 2 are requested from HBM now so that their copies meet L2
+#pragma unroll
+    for (int f = 2; f < NFC; ++f)
+    {
+        int const q0 = ct_sfoff(TYPE, f);
+#pragma unroll
+        for (int d = 0; d < ND; ++d) { l2_prefetch(&G.cecnd[(f * ND + d) * n + i]); }
+        l2_prefetch(&G.cevol[(f + 1) * n + i]);
+#pragma unroll
+        for (int s = 0; s < ct_fnnd(TYPE, f); ++s)
+        {
+#pragma unroll
+            for (int d = 0; d < ND; ++d)
+            {
+                l2_prefetch(&G.sfcnd[((q0 + s) * ND + d) * n + i]);
+                l2_prefetch(&G.sfnml[((q0 + s) * ND + d) * n + i]);
+            }
+        }
+#if SCG_SOLN_L2PF >= 2
+        {
+            int64_t const j = G.nbr[f * n + i];
+            int64_t const S = F.S;
+#pragma unroll
+            for (int d = 0; d < ND; ++d) { l2_prefetch(&F.solpt[d * S + j]); }
+#pragma unroll
+            for (int e = 0; e < NEQ; ++e)
+            {
+                l2_prefetch(&F.so0c[e * S + j]);
+                l2_prefetch(&F.so0t[e * S + j]);
+#pragma unroll
+                for (int d = 0; d < ND; ++d) { l2_prefetch(&F.so1c[(e * ND + d) * S + j]); }
+            }
+            l2_prefetch(&F.gamma[j]);
+        }
+#endif
+    }
+#endif
 
 #pragma unroll 1
     for (int f = 0; f < NFC; ++f)
@@ -1171,7 +1222,7 @@ struct DsolnEqo
     // the cell's new gradient so1n[NEQ][ND] for the fused calc_solt: parked in shared memory in 2D (8 rows, 5 % faster
     // than reading it back); in 3D 15 more rows per thread would shrink L1 by as much and the gathers of the
     // equation loop live on L1 (tetrahedra: 318 -> 452 us), so there it is read back from L2
-    static constexpr bool G_IN_SMEM = (2 == ND);
+    static constexpr bool G_IN_SMEM = (2 == ND) || (0 != (SCG_EQO_GSMEM_MASK & (1 << (TYPE - CT_HEX))));
     static constexpr int R_G = NFGE * RPF;
     static constexpr int ROWS = R_G + (G_IN_SMEM ? (ND + 2) * ND : 0);
     static constexpr int BYTES = ROWS * TB * int(sizeof(double));
@@ -1298,6 +1349,23 @@ __device__ __forceinline__ void cell_dsoln_eqo(MdField const & F, MdGeo const & 
 #pragma unroll
         for (int f = 0; f < NFC; ++f) { rcl[f] = G.nbr[f * n + i]; }
         if (PF) { cur.load(F, rcl, k, 0); } // the first equation's gather travels while the geometry is worked out
+#if SCG_EQO_L2PF
+        // every later equation's gather is requested from HBM now; it is consumed e equations (microseconds) later
+#pragma unroll
+        for (int e = (PF ? 2 : 1); e < NEQ; ++e)
+        {
+            l2_prefetch(&F.so0n[e * S + k]);
+#pragma unroll
+            for (int f = 0; f < NFC; ++f)
+            {
+                int64_t const j = rcl[f];
+                l2_prefetch(&F.so0c[e * S + j]);
+                l2_prefetch(&F.so0t[e * S + j]);
+#pragma unroll
+                for (int d = 0; d < ND; ++d) { l2_prefetch(&F.so1c[(e * ND + d) * S + j]); }
+            }
+        }
+#endif
 #pragma unroll
         for (int f = 0; f < NFC; ++f)
         {

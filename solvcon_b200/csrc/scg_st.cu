@@ -316,6 +316,14 @@ struct scg_st
     DevBuf<double> red;
     Planes P{};
     bool halo_mode = false; // ghosts come from scg_st_halo_unpack instead of the periodic wrap
+    // ring of slabs over the library's communicator: [send left(2) | send right(2) | recv from left(2) | recv from right(2)]
+    DevBuf<double> ring;
+    cudaEvent_t ev_packed = nullptr, ev_recv = nullptr;
+    ~scg_st()
+    {
+        if (ev_packed) { cudaEventDestroy(ev_packed); }
+        if (ev_recv) { cudaEventDestroy(ev_recv); }
+    }
 };
 
 namespace
@@ -604,6 +612,50 @@ int scg_st_halo_unpack(scg_st * s, int odd_plane, const double * dev_recv_left, 
     if (0 == s->eq) { st_halo_unpack_kernel<0><<<1, 32, 0, stream()>>>(s->P, s->n, dev_recv_left, dev_recv_right, s->hdt); }
     else { st_halo_unpack_kernel<1><<<1, 32, 0, stream()>>>(s->P, s->n, dev_recv_left, dev_recv_right, s->hdt); }
     count_launch();
+    SCG_CUDA(cudaGetLastError());
+    return 0;
+}
+
+
+// One slab of the periodic ring: march_alpha over the library's communicator.  Per step: half 1 on the
+// slab, {so0, so1} of its first / last odd-plane point to the left / right ring neighbour (two 16-byte messages each way,
+// one ncclGroup on the communication stream), the neighbours' points into the ghosts (which also evaluates the ghosts'
+// cfl), half 2 -- the periodic copy of treat_boundary_so0/so1 (core.hpp:982-1004) done across ranks.  Stream-ordered.
+int scg_st_march_ring(scg_st * s, int alpha, int64_t steps, int left_rank, int right_rank)
+{
+    SCG_REQUIRE(s, "scg_st_march_ring: null solver");
+    SCG_REQUIRE(alpha >= 0 && alpha <= 2, "scg_st_march_ring: alpha must be 0, 1 or 2");
+    SCG_REQUIRE(comm_ready(), "scg_st_march_ring: no communicator (call scg_comm_init first)");
+    if (steps <= 0) { return 0; }
+    if (!s->ring.p)
+    {
+        SCG_CUDA(s->ring.alloc_zero(8));
+        SCG_CUDA(cudaEventCreateWithFlags(&s->ev_packed, cudaEventDisableTiming));
+        SCG_CUDA(cudaEventCreateWithFlags(&s->ev_recv, cudaEventDisableTiming));
+        SCG_CUDA(cudaStreamSynchronize(stream()));
+    }
+    s->halo_mode = true;
+    double * const b = s->ring.p;
+    for (int64_t it = 0; it < steps; ++it)
+    {
+        if (int rc = scg_st_march_half(s, 1, alpha)) { return rc; }
+        if (int rc = scg_st_halo_pack(s, 1, b, b + 2)) { return rc; }
+        SCG_CUDA(cudaEventRecord(s->ev_packed, stream()));
+        SCG_CUDA(cudaStreamWaitEvent(comm_stream(), s->ev_packed, 0));
+        if (int rc = comm_group_start()) { return rc; }
+        // with two ranks both messages go to the same peer: NCCL matches sends and receives per peer in issue order,
+        // so the order here (left message first, right message second) must mirror the peer's (its right, then left)
+        if (int rc = comm_send(b, 2, left_rank)) { return rc; }
+        if (int rc = comm_send(b + 2, 2, right_rank)) { return rc; }
+        if (int rc = comm_recv(b + 6, 2, right_rank)) { return rc; }
+        if (int rc = comm_recv(b + 4, 2, left_rank)) { return rc; }
+        if (int rc = comm_group_end()) { return rc; }
+        SCG_CUDA(cudaEventRecord(s->ev_recv, comm_stream()));
+        SCG_CUDA(cudaStreamWaitEvent(stream(), s->ev_recv, 0));
+        // my left ghost is the left neighbour's LAST odd-plane point (its "right" message), and vice versa
+        if (int rc = scg_st_halo_unpack(s, 1, b + 4, b + 6)) { return rc; }
+        if (int rc = scg_st_march_half(s, 2, alpha)) { return rc; }
+    }
     SCG_CUDA(cudaGetLastError());
     return 0;
 }

@@ -116,6 +116,20 @@ class LocalRing:
                 s.half(2, alpha)
 
 
+class NcclRing:
+    """One slab per process over the LIBRARY's communicator (``scg_comm_init``): the whole ring march is one C call
+    (``scg_st_march_ring``: half 1, ncclSend/ncclRecv of the two boundary points on the library's communication stream,
+    half 2); no torch on this path."""
+
+    def __init__(self, eq, xcoord_global, c0, c1, time_increment, rank, world):
+        self.rank, self.world = int(rank), int(world)
+        self.slab = ScalarSlab(eq, xcoord_global, c0, c1, time_increment)
+
+    def march(self, alpha, steps):
+        P, r = self.world, self.rank
+        _lib.check(_lib.load().scg_st_march_ring(self.slab.svr._h, int(alpha), int(steps), (r - 1) % P, (r + 1) % P))
+
+
 class TorchRing:
     """One slab per process: ``torch.distributed`` P2P of the two 2-double messages with the ring neighbours."""
 

@@ -4,7 +4,7 @@ SZ=$1; shift
 for lib in "$@"; do
   echo "== $lib"
   SCG_LIB=$lib timeout 900 python -m pytest tests/test_gpu_md.py -x -q -k "march_matches and (mixed3d or mixed2d or step2d) and morton and 3-" 2>&1 | tail -1
-  SCG_LIB=$lib SCG_TIMING=1 timeout 600 python bench.py --workload ${WL:-md3d} --size $SZ --steps 5 --warmup 3 --no-cpu --no-e2e 2>&1 | python -c "
+  SCG_LIB=$lib SCG_TIMING=1 timeout 600 python bench.py --workload ${WL:-md3d} --size $SZ --steps 5 --warmup 3 --no-cpu --no-e2e --no-parity 2>&1 | python -c "
 import sys,json
 for l in sys.stdin:
     try: d=json.loads(l)
