@@ -15,6 +15,8 @@
 //   * build_boundary looks faces up through an index table instead of std::find (O(n) not O(n^2));
 //   * face/cell metric loops that have no cross-iteration dependence run on all host threads.
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <cmath>
 #include <cstdarg>
 #include <cstdint>
@@ -137,6 +139,21 @@ void parallel_for(int64_t n, std::function<void(int64_t, int64_t)> const & fn)
     for (auto & t : th) { t.join(); }
 }
 
+// SCG_HMESH_TIMING=1: wall time of the builder's stages on stderr
+struct StageTimer
+{
+    bool on;
+    std::chrono::steady_clock::time_point t;
+    StageTimer() : on(std::getenv("SCG_HMESH_TIMING") && std::getenv("SCG_HMESH_TIMING")[0] == '1'), t(std::chrono::steady_clock::now()) {}
+    void lap(char const * what)
+    {
+        if (!on) { return; }
+        auto const n = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[hmesh] %-28s %8.3f s\n", what, std::chrono::duration<double>(n - t).count());
+        t = n;
+    }
+};
+
 struct Bc
 {
     std::string name;
@@ -167,6 +184,7 @@ struct scg_hmesh
 // --------------------------------------------------------------------------------------------------
 void scg_hmesh::build_faces_from_cells()
 {
+    StageTimer tm;
     int64_t mface = 0;
     for (int64_t icl = 0; icl < ncell; ++icl) { mface += cell_nface(cltpn(icl)); }
     std::vector<int32_t> tnds(static_cast<size_t>(mface) * (FCMND + 1), -1);
@@ -192,6 +210,7 @@ void scg_hmesh::build_faces_from_cells()
                          }
                      }
                  });
+    tm.lap("faces: populate");
     // sorted node tuple of every candidate
     std::vector<int32_t> key(static_cast<size_t>(mface) * 4);
     parallel_for(mface, [&](int64_t b, int64_t e)
@@ -205,12 +224,14 @@ void scg_hmesh::build_faces_from_cells()
                          std::memcpy(&key[f * 4], k, sizeof(k));
                      }
                  });
+    tm.lap("faces: keys");
     // counting sort of the candidates by smallest node id (stable: original order inside a bucket)
     std::vector<int64_t> bstart(static_cast<size_t>(nnode) + 2, 0);
     for (int64_t f = 0; f < mface; ++f) { bstart[key[f * 4] + 2] += 1; }
     for (int64_t n = 0; n < nnode; ++n) { bstart[n + 2] += bstart[n + 1]; }
     std::vector<int32_t> sorted(static_cast<size_t>(mface));
     for (int64_t f = 0; f < mface; ++f) { sorted[bstart[key[f * 4] + 1]++] = static_cast<int32_t>(f); }
+    tm.lap("faces: counting sort");
     // bstart[n] is now the start of bucket n, bstart[n+1] its end
     std::vector<int32_t> root(static_cast<size_t>(mface));
     for (int64_t f = 0; f < mface; ++f) { root[f] = static_cast<int32_t>(f); }
@@ -234,6 +255,7 @@ void scg_hmesh::build_faces_from_cells()
                          }
                      }
                  });
+    tm.lap("faces: match duplicates");
     // compact numbering of the roots in order of first appearance
     std::vector<int32_t> map2(static_cast<size_t>(mface));
     int64_t nf = 0;
@@ -266,6 +288,7 @@ void scg_hmesh::build_faces_from_cells()
     fccnd.make(nface, ndim, 0.0);
     fcnml.make(nface, ndim, 0.0);
     fcara.make(nface, 1, 0.0, true);
+    tm.lap("faces: number + tables");
 }
 
 // face centroid, unit normal and area of one face (body or ghost index):
@@ -391,6 +414,7 @@ void scg_hmesh::cell_centroid(int64_t icl)
 
 void scg_hmesh::calc_metric()
 {
+    StageTimer tm;
     // one-dimensional meshes have no face / cell metric (the reference's loops are `if (2 == ndim) .. else if
     // (3 == ndim)`, StaticMesh_interior.cpp:626-927); only the volume loop below runs, on zeros
     if (ndim >= 2)
@@ -406,6 +430,7 @@ void scg_hmesh::calc_metric()
                          for (int64_t c = b; c < e; ++c) { cell_centroid(c); }
                      });
     }
+    tm.lap("metric: face + cell centroids");
     // cell volumes and face orientation (sequential: a face may be re-oriented by the first cell that
     // sees it, StaticMesh_interior.cpp:930-976)
     for (int64_t icl = 0; icl < ncell; ++icl)
@@ -438,6 +463,7 @@ void scg_hmesh::calc_metric()
         }
         clvol(icl) /= ndim;
     }
+    tm.lap("metric: volumes + orientation");
 }
 
 // StaticMesh_interior.cpp:566-609: unique edges in order of first appearance over the faces
@@ -808,6 +834,7 @@ int scg_hmesh_build_ghost(scg_hmesh * m)
     m->ngstcell = m->nbound;
     auto grow_d = [](Tab<double> & t, int64_t ng, double init) { t.grow_front(ng, init); };
     auto grow_i = [](Tab<int32_t> & t, int64_t ng, int32_t init) { t.grow_front(ng, init); };
+    StageTimer tm;
     grow_d(m->ndcrd, gn, 0.0);
     grow_d(m->fccnd, gf, 0.0);
     grow_d(m->fcnml, gf, 0.0);
@@ -821,7 +848,9 @@ int scg_hmesh_build_ghost(scg_hmesh * m)
     grow_i(m->fccls, gf, -1);
     grow_i(m->clnds, m->ngstcell, -1);
     grow_i(m->clfcs, m->ngstcell, -1);
+    tm.lap("ghost: grow tables");
     m->fill_ghost();
+    tm.lap("ghost: fill");
     return 0;
 }
 

@@ -25,12 +25,15 @@ def test_reference_arm_json_line(workload, size):
     assert KEYS <= set(d), KEYS - set(d)
     assert d["impl"] == "reference" and d["unit"] == "updates/s" and d["value"] > 0 and d["higher_is_better"] is True
     assert d["vs_baseline"] is None and d["dtype"] == "f64" and d["data"] == "synthetic"
-    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] == 1
-    if workload in ("md3d", "st1d"):      # the all-host-threads figure: independent replicas of the single-threaded march
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["single_thread"] > 0
+    if workload in ("md3d", "st1d"):      # all the host threads the single-threaded reference can use: independent replicas
         allc = d["cpu_baseline"]["all_cores"]
         assert allc["cores"] == 2 and allc["value"] > 0 and allc["unit"] == d["unit"]
+        assert d["cpu_baseline"]["cores"] == 2 and d["value"] == allc["value"] == d["cpu_baseline"]["value"]
     else:
-        assert "all_cores" not in d["cpu_baseline"]
+        assert "all_cores" not in d["cpu_baseline"] and d["cpu_baseline"]["cores"] == 1
+        assert d["value"] == d["cpu_baseline"]["single_thread"]
+    assert "reference_sample_note" in d["config"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and "workload" in d["config"]
 
 
