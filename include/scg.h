@@ -131,6 +131,15 @@ SCG_API int scg_e1d_phase(scg_e1d * s, int phase, int odd_plane, int alpha);
 SCG_API int scg_e1d_march(scg_e1d * s, int alpha, int64_t steps);
 SCG_API int scg_e1d_reduce(scg_e1d * s, double * cfl_min, double * cfl_max, double * mass);
 
+/* ---- synthetic stepped-channel lattice (solvcon_b200/meshgen.py: mixed_3d), connectivity only, on all host threads.
+ * No counterpart in the reference (its only mesher is the Python obsrefl one, _driver.py:57-258); used by bench.py's
+ * mesh generator.  See csrc/scg_meshgen.cpp. */
+SCG_API int scg_meshgen_mixed3d_count(int64_t nx, int64_t ny, int64_t nz, int64_t x1, int64_t z1, int64_t i0, int64_t i1,
+                                      int64_t j0, int64_t j1, int64_t k0, int64_t k1, int64_t * nnode_lattice, int64_t * ncell);
+SCG_API int scg_meshgen_mixed3d_cells(int64_t nx, int64_t ny, int64_t nz, int64_t x1, int64_t z1, int64_t i0, int64_t i1,
+                                      int64_t j0, int64_t j1, int64_t k0, int64_t k1, const double * xyz_lattice, int32_t * cltpn,
+                                      int32_t * clnds, uint8_t * used, int64_t * box_or_null, int64_t * nnode_used);
+
 /* ------------------------------------------------------------- host mesh
  * native twin of solvcon::StaticMesh (cpp/solvcon/mesh/StaticMesh.hpp:270-455): the table builder
  * behind the unchanged `StaticMesh(ndim, nnode, nface, ncell)` / build_interior / add_bc /

@@ -75,6 +75,8 @@ _SIGNATURES = {
     "scg_e1d_march": (C.c_int, [C.c_void_p, C.c_int, C.c_int64]),
     "scg_e1d_reduce": (C.c_int, [C.c_void_p, DP, DP, DP]),
     # host mesh
+    "scg_meshgen_mixed3d_count": (C.c_int, [C.c_int64] * 11 + [I64P, I64P]),
+    "scg_meshgen_mixed3d_cells": (C.c_int, [C.c_int64] * 11 + [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, I64P]),
     "scg_hmesh_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int64, C.c_int64, C.c_int64]),
     "scg_hmesh_destroy": (C.c_int, [C.c_void_p]),
     "scg_hmesh_count": (C.c_int, [C.c_void_p, C.c_int, I64P]),

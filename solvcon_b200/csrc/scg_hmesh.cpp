@@ -41,10 +41,80 @@ namespace
 
 constexpr int FCMND = 4, CLMND = 8, CLMFC = 6, FCREL = 4, BFREL = 3;
 
+void parallel_for(int64_t n, std::function<void(int64_t, int64_t)> const & fn)
+{
+    unsigned nt = std::thread::hardware_concurrency();
+    if (nt > 32) { nt = 32; }
+    if (nt < 2 || n < 200000)
+    {
+        fn(0, n);
+        return;
+    }
+    std::vector<std::thread> th;
+    int64_t const chunk = (n + nt - 1) / nt;
+    for (unsigned t = 0; t < nt; ++t)
+    {
+        int64_t const b = t * chunk, e = std::min<int64_t>(n, b + chunk);
+        if (b >= e) { break; }
+        th.emplace_back([=, &fn]() { fn(b, e); });
+    }
+    for (auto & t : th) { t.join(); }
+}
+
+// Table storage: allocated uninitialised and filled / copied on all host threads (a std::vector would value-initialise
+// on ONE thread: at 5e7 cells that is 14 GB of serial first-touch page faults).
+template <typename T>
+struct PBuf
+{
+    T * p = nullptr;
+    size_t n = 0;
+    PBuf() = default;
+    PBuf(PBuf const &) = delete;
+    PBuf & operator=(PBuf const &) = delete;
+    PBuf(PBuf && o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    PBuf & operator=(PBuf && o) noexcept
+    {
+        if (this != &o)
+        {
+            std::free(p);
+            p = o.p;
+            n = o.n;
+            o.p = nullptr;
+            o.n = 0;
+        }
+        return *this;
+    }
+    ~PBuf() { std::free(p); }
+    void alloc(size_t count)
+    {
+        std::free(p);
+        p = count ? static_cast<T *>(std::malloc(count * sizeof(T))) : nullptr;
+        n = count;
+    }
+    void assign(size_t count, T init)
+    {
+        alloc(count);
+        fill(0, count, init);
+    }
+    void fill(size_t b, size_t e, T init)
+    {
+        T * const q = p;
+        parallel_for(static_cast<int64_t>(e - b), [=](int64_t lo, int64_t hi) { std::fill(q + b + lo, q + b + hi, init); });
+    }
+    T * data() { return p; }
+    T const * data() const { return p; }
+    T * begin() { return p; }
+    T * end() { return p + n; }
+    size_t size() const { return n; }
+    bool empty() const { return 0 == n; }
+    T & operator[](size_t k) { return p[k]; }
+    T const & operator[](size_t k) const { return p[k]; }
+};
+
 template <typename T>
 struct Tab
 {
-    std::vector<T> v;
+    PBuf<T> v;
     int64_t rows = 0, cols = 1, ngh = 0;
     bool one_d = false;
     // A caller may hold zero-copy views of `v` (scg_hmesh_table).  In the reference an ndarray view keeps the old
@@ -52,11 +122,11 @@ struct Tab
     // out is RETIRED instead of freed when the table is re-made, so stale views stay readable (they show the old
     // generation, like the reference's) and writes through them cannot corrupt the heap.
     bool exported = false;
-    std::vector<std::vector<T>> retired;
+    std::vector<PBuf<T>> retired;
     void retire()
     {
         if (exported && !v.empty()) { retired.emplace_back(std::move(v)); }
-        v = std::vector<T>();
+        v = PBuf<T>();
         exported = false;
     }
     void make(int64_t r, int64_t c, T init, bool is1d = false)
@@ -71,8 +141,14 @@ struct Tab
     // prepend `ng` ghost rows filled with `init` (StaticMesh_boundary.cpp:219-234)
     void grow_front(int64_t ng, T init)
     {
-        std::vector<T> nv(static_cast<size_t>((rows + ng) * cols), init);
-        std::copy(v.begin(), v.end(), nv.begin() + ng * cols);
+        PBuf<T> nv;
+        nv.alloc(static_cast<size_t>((rows + ng) * cols));
+        nv.fill(0, static_cast<size_t>(ng * cols), init);
+        {
+            T const * const src = v.data();
+            T * const dst = nv.data() + ng * cols;
+            parallel_for(static_cast<int64_t>(v.size()), [=](int64_t lo, int64_t hi) { std::copy(src + lo, src + hi, dst + lo); });
+        }
         retire();
         v = std::move(nv);
         rows += ng;
@@ -118,26 +194,6 @@ inline int face_type_of(int ndim, int nnd)
     return 2 == ndim ? 2 /*LINE*/ : (3 == nnd ? 4 /*TRIANGLE*/ : 3 /*QUADRILATERAL*/);
 }
 inline int cell_nface(int t) { return (t >= 0 && t <= 8) ? FACEDEF[t].nface : 0; }
-
-void parallel_for(int64_t n, std::function<void(int64_t, int64_t)> const & fn)
-{
-    unsigned nt = std::thread::hardware_concurrency();
-    if (nt > 32) { nt = 32; }
-    if (nt < 2 || n < 200000)
-    {
-        fn(0, n);
-        return;
-    }
-    std::vector<std::thread> th;
-    int64_t const chunk = (n + nt - 1) / nt;
-    for (unsigned t = 0; t < nt; ++t)
-    {
-        int64_t const b = t * chunk, e = std::min<int64_t>(n, b + chunk);
-        if (b >= e) { break; }
-        th.emplace_back([=, &fn]() { fn(b, e); });
-    }
-    for (auto & t : th) { t.join(); }
-}
 
 // SCG_HMESH_TIMING=1: wall time of the builder's stages on stderr
 struct StageTimer
@@ -185,14 +241,17 @@ struct scg_hmesh
 void scg_hmesh::build_faces_from_cells()
 {
     StageTimer tm;
-    int64_t mface = 0;
-    for (int64_t icl = 0; icl < ncell; ++icl) { mface += cell_nface(cltpn(icl)); }
-    std::vector<int32_t> tnds(static_cast<size_t>(mface) * (FCMND + 1), -1);
-    std::vector<int32_t> ttpn(static_cast<size_t>(mface), -1);
-    std::vector<int64_t> first(static_cast<size_t>(ncell) + 1, 0);
+    PBuf<int64_t> first;
+    first.alloc(static_cast<size_t>(ncell) + 1);
+    first[0] = 0;
     for (int64_t icl = 0; icl < ncell; ++icl) { first[icl + 1] = first[icl] + cell_nface(cltpn(icl)); }
+    int64_t const mface = first[ncell];
+    PBuf<int32_t> tnds, ttpn, key;
+    tnds.alloc(static_cast<size_t>(mface) * (FCMND + 1));
+    ttpn.alloc(static_cast<size_t>(mface));
+    key.alloc(static_cast<size_t>(mface) * 4);
     clfcs.make(ncell, CLMFC + 1, -1);
-    // populate every candidate face in cell order
+    // populate every candidate face in cell order, with its sorted node tuple
     parallel_for(ncell, [&](int64_t b, int64_t e)
                  {
                      for (int64_t icl = b; icl < e; ++icl)
@@ -206,35 +265,34 @@ void scg_hmesh::build_faces_from_cells()
                              clfcs(icl, f + 1) = static_cast<int32_t>(ifc);
                              ttpn[ifc] = face_type_of(ndim, fd.fnnd[f]);
                              tnds[ifc * 5] = fd.fnnd[f];
-                             for (int q = 0; q < fd.fnnd[f]; ++q) { tnds[ifc * 5 + 1 + q] = clnds(icl, fd.nd[f][q]); }
+                             int32_t k[4] = {INT32_MAX, INT32_MAX, INT32_MAX, INT32_MAX};
+                             for (int q = 0; q < FCMND; ++q)
+                             {
+                                 int32_t const nd = (q < fd.fnnd[f]) ? clnds(icl, fd.nd[f][q]) : -1;
+                                 tnds[ifc * 5 + 1 + q] = nd;
+                                 if (q < fd.fnnd[f]) { k[q] = nd; }
+                             }
+                             std::sort(k, k + 4);
+                             std::memcpy(&key[ifc * 4], k, sizeof(k));
                          }
                      }
                  });
-    tm.lap("faces: populate");
-    // sorted node tuple of every candidate
-    std::vector<int32_t> key(static_cast<size_t>(mface) * 4);
-    parallel_for(mface, [&](int64_t b, int64_t e)
-                 {
-                     for (int64_t f = b; f < e; ++f)
-                     {
-                         int32_t k[4] = {INT32_MAX, INT32_MAX, INT32_MAX, INT32_MAX};
-                         int const nnd = tnds[f * 5];
-                         for (int q = 0; q < nnd; ++q) { k[q] = tnds[f * 5 + 1 + q]; }
-                         std::sort(k, k + 4);
-                         std::memcpy(&key[f * 4], k, sizeof(k));
-                     }
-                 });
-    tm.lap("faces: keys");
+    tm.lap("faces: populate + keys");
     // counting sort of the candidates by smallest node id (stable: original order inside a bucket)
-    std::vector<int64_t> bstart(static_cast<size_t>(nnode) + 2, 0);
+    PBuf<int64_t> bstart;
+    bstart.assign(static_cast<size_t>(nnode) + 2, 0);
     for (int64_t f = 0; f < mface; ++f) { bstart[key[f * 4] + 2] += 1; }
     for (int64_t n = 0; n < nnode; ++n) { bstart[n + 2] += bstart[n + 1]; }
-    std::vector<int32_t> sorted(static_cast<size_t>(mface));
+    PBuf<int32_t> sorted, root, map2;
+    sorted.alloc(static_cast<size_t>(mface));
     for (int64_t f = 0; f < mface; ++f) { sorted[bstart[key[f * 4] + 1]++] = static_cast<int32_t>(f); }
     tm.lap("faces: counting sort");
     // bstart[n] is now the start of bucket n, bstart[n+1] its end
-    std::vector<int32_t> root(static_cast<size_t>(mface));
-    for (int64_t f = 0; f < mface; ++f) { root[f] = static_cast<int32_t>(f); }
+    root.alloc(static_cast<size_t>(mface));
+    parallel_for(mface, [&](int64_t b, int64_t e)
+                 {
+                     for (int64_t f = b; f < e; ++f) { root[f] = static_cast<int32_t>(f); }
+                 });
     parallel_for(nnode, [&](int64_t nb, int64_t ne)
                  {
                      for (int64_t n = nb; n < ne; ++n)
@@ -256,35 +314,82 @@ void scg_hmesh::build_faces_from_cells()
                      }
                  });
     tm.lap("faces: match duplicates");
-    // compact numbering of the roots in order of first appearance
-    std::vector<int32_t> map2(static_cast<size_t>(mface));
-    int64_t nf = 0;
-    for (int64_t f = 0; f < mface; ++f)
+    // compact numbering of the roots in order of first appearance: a chunked prefix sum over the root flags, then the
+    // duplicates take their root's number (a root always precedes its duplicates)
+    map2.alloc(static_cast<size_t>(mface));
     {
-        if (root[f] == f) { map2[f] = static_cast<int32_t>(nf++); }
-        else { map2[f] = map2[root[f]]; }
+        int64_t const nchunk = 256;
+        int64_t const clen = (mface + nchunk - 1) / nchunk;
+        std::vector<int64_t> cnt(static_cast<size_t>(nchunk) + 1, 0);
+        parallel_for(nchunk, [&](int64_t cb, int64_t ce)
+                     {
+                         for (int64_t c = cb; c < ce; ++c)
+                         {
+                             int64_t n = 0;
+                             for (int64_t f = c * clen; f < std::min(mface, (c + 1) * clen); ++f) { n += (root[f] == f) ? 1 : 0; }
+                             cnt[c + 1] = n;
+                         }
+                     });
+        for (int64_t c = 0; c < nchunk; ++c) { cnt[c + 1] += cnt[c]; }
+        nface = cnt[nchunk];
+        parallel_for(nchunk, [&](int64_t cb, int64_t ce)
+                     {
+                         for (int64_t c = cb; c < ce; ++c)
+                         {
+                             int64_t n = cnt[c];
+                             for (int64_t f = c * clen; f < std::min(mface, (c + 1) * clen); ++f)
+                             {
+                                 if (root[f] == f) { map2[f] = static_cast<int32_t>(n++); }
+                             }
+                         }
+                     });
+        parallel_for(mface, [&](int64_t b, int64_t e)
+                     {
+                         for (int64_t f = b; f < e; ++f)
+                         {
+                             if (root[f] != f) { map2[f] = map2[root[f]]; }
+                         }
+                     });
     }
-    nface = nf;
     fctpn.make(nface, 1, 0, true);
     fcnds.make(nface, FCMND + 1, -1);
     fccls.make(nface, FCREL, -1);
-    for (int64_t f = 0; f < mface; ++f)
-    {
-        if (root[f] != f) { continue; }
-        int64_t const j = map2[f];
-        fctpn(j) = ttpn[f];
-        for (int q = 0; q <= FCMND; ++q) { fcnds(j, q) = tnds[f * 5 + q]; }
-    }
-    for (int64_t icl = 0; icl < ncell; ++icl)
-    {
-        for (int ifl = 1; ifl <= clfcs(icl, 0); ++ifl)
-        {
-            int32_t const jfc = map2[clfcs(icl, ifl)];
-            clfcs(icl, ifl) = jfc;
-            if (-1 == fccls(jfc, 0)) { fccls(jfc, 0) = static_cast<int32_t>(icl); }
-            else if (-1 == fccls(jfc, 1)) { fccls(jfc, 1) = static_cast<int32_t>(icl); }
-        }
-    }
+    parallel_for(mface, [&](int64_t b, int64_t e)
+                 {
+                     for (int64_t f = b; f < e; ++f)
+                     {
+                         if (root[f] != f) { continue; }
+                         int64_t const j = map2[f];
+                         fctpn(j) = ttpn[f];
+                         for (int q = 0; q <= FCMND; ++q) { fcnds(j, q) = tnds[f * 5 + q]; }
+                     }
+                 });
+    // clfcs takes the compact numbers; fccls[:,0] is the first cell that sees the face (the root candidate's: cells
+    // are visited in ascending order and a root precedes its duplicates), fccls[:,1] the second one
+    parallel_for(ncell, [&](int64_t b, int64_t e)
+                 {
+                     for (int64_t icl = b; icl < e; ++icl)
+                     {
+                         for (int ifl = 1; ifl <= clfcs(icl, 0); ++ifl)
+                         {
+                             int64_t const cand = clfcs(icl, ifl);
+                             int32_t const jfc = map2[cand];
+                             clfcs(icl, ifl) = jfc;
+                             if (root[cand] == cand) { fccls(jfc, 0) = static_cast<int32_t>(icl); }
+                             else
+                             {
+                                 // the lowest second cell wins, as in the sequential visit (more than two cells on a face
+                                 // only happens in an invalid mesh)
+                                 int32_t * const slot = &fccls(jfc, 1);
+                                 int32_t cur = __atomic_load_n(slot, __ATOMIC_RELAXED);
+                                 while ((-1 == cur || static_cast<int32_t>(icl) < cur)
+                                        && !__atomic_compare_exchange_n(slot, &cur, static_cast<int32_t>(icl), true, __ATOMIC_RELAXED, __ATOMIC_RELAXED))
+                                 {
+                                 }
+                             }
+                         }
+                     }
+                 });
     fccnd.make(nface, ndim, 0.0);
     fcnml.make(nface, ndim, 0.0);
     fcara.make(nface, 1, 0.0, true);
@@ -431,38 +536,56 @@ void scg_hmesh::calc_metric()
                      });
     }
     tm.lap("metric: face + cell centroids");
-    // cell volumes and face orientation (sequential: a face may be re-oriented by the first cell that
-    // sees it, StaticMesh_interior.cpp:930-976)
-    for (int64_t icl = 0; icl < ncell; ++icl)
-    {
-        clvol(icl) = 0.0;
-        int const nfc = clfcs(icl, 0);
-        for (int it = 1; it <= nfc; ++it)
-        {
-            int64_t const ifc = clfcs(icl, it);
-            double vol = 0.0;
-            for (int d = 0; d < ndim; ++d) { vol += (fccnd(ifc, d) - clcnd(icl, d)) * fcnml(ifc, d); }
-            vol *= fcara(ifc);
-            bool const mine = (fccls(ifc, 0) == icl);
-            bool flip = false;
-            if (vol < 0.0)
-            {
-                flip = mine;
-                vol = -vol;
-            }
-            else { flip = !mine; }
-            if (flip)
-            {
-                int const nnd = fcnds(ifc, 0);
-                int32_t tmp[FCMND];
-                for (int jt = 0; jt < nnd; ++jt) { tmp[jt] = fcnds(ifc, nnd - jt); }
-                for (int jt = 0; jt < nnd; ++jt) { fcnds(ifc, jt + 1) = tmp[jt]; }
-                for (int d = 0; d < ndim; ++d) { fcnml(ifc, d) = -fcnml(ifc, d); }
-            }
-            clvol(icl) += vol;
-        }
-        clvol(icl) /= ndim;
-    }
+    // Cell volumes and face orientation (StaticMesh_interior.cpp:930-976).  The reference walks the cells in order and
+    // lets every cell re-orient a face it sees; per face that is: the owner (first cell) visits, then the neighbour.
+    // Re-orienting negates the normal, which negates the face's volume term EXACTLY (every product and the ordered sum
+    // change sign, rounding is symmetric), and the term enters the volume by its magnitude -- so the volumes do not
+    // depend on the visiting order and the final orientation of a face depends on its own two visits only.
+    parallel_for(ncell, [&](int64_t b, int64_t e)
+                 {
+                     for (int64_t icl = b; icl < e; ++icl)
+                     {
+                         double acc = 0.0;
+                         int const nfc = clfcs(icl, 0);
+                         for (int it = 1; it <= nfc; ++it)
+                         {
+                             int64_t const ifc = clfcs(icl, it);
+                             double vol = 0.0;
+                             for (int d = 0; d < ndim; ++d) { vol += (fccnd(ifc, d) - clcnd(icl, d)) * fcnml(ifc, d); }
+                             vol *= fcara(ifc);
+                             if (vol < 0.0) { vol = -vol; }
+                             acc += vol;
+                         }
+                         clvol(icl) = acc / ndim;
+                     }
+                 });
+    parallel_for(nface, [&](int64_t b, int64_t e)
+                 {
+                     for (int64_t ifc = b; ifc < e; ++ifc)
+                     {
+                         bool flipped = false;
+                         for (int side = 0; side < 2; ++side)
+                         {
+                             int64_t const icl = fccls(ifc, side);
+                             if (icl < 0) { continue; }
+                             double vol = 0.0;
+                             for (int d = 0; d < ndim; ++d) { vol += (fccnd(ifc, d) - clcnd(icl, d)) * fcnml(ifc, d); }
+                             vol *= fcara(ifc);
+                             if (flipped) { vol = -vol; }          // what the visit computes with the current normal
+                             bool const mine = (0 == side);
+                             bool const flip = (vol < 0.0) ? mine : !mine;
+                             if (flip) { flipped = !flipped; }
+                         }
+                         if (flipped)
+                         {
+                             int const nnd = fcnds(ifc, 0);
+                             int32_t tmp[FCMND];
+                             for (int jt = 0; jt < nnd; ++jt) { tmp[jt] = fcnds(ifc, nnd - jt); }
+                             for (int jt = 0; jt < nnd; ++jt) { fcnds(ifc, jt + 1) = tmp[jt]; }
+                             for (int d = 0; d < ndim; ++d) { fcnml(ifc, d) = -fcnml(ifc, d); }
+                         }
+                     }
+                 });
     tm.lap("metric: volumes + orientation");
 }
 

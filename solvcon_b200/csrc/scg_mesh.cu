@@ -7,8 +7,10 @@
 // fcrcl = fccls[ifc,0] + fccls[ifc,1] - icl (StaticMesh.hpp:355-358), is resolved here once into
 // nbr[f][cell] in device numbering.
 #include "scg_md.cuh"
+#include "scg_par.hpp"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <numeric>
@@ -58,13 +60,16 @@ void morton_keys(int ndim, int64_t ncell, double const * clcnd_body, std::vector
     double sc[3];
     for (int d = 0; d < ndim; ++d) { sc[d] = (hi[d] > lo[d]) ? bits / (hi[d] - lo[d]) : 0.0; }
     key.resize(static_cast<size_t>(ncell));
-    for (int64_t i = 0; i < ncell; ++i)
-    {
-        uint64_t q[3] = {0, 0, 0};
-        for (int d = 0; d < ndim; ++d) { q[d] = static_cast<uint64_t>((clcnd_body[i * ndim + d] - lo[d]) * sc[d]); }
-        key[i] = (3 == ndim) ? (spread3(q[0]) | (spread3(q[1]) << 1) | (spread3(q[2]) << 2))
-                             : (spread2(q[0]) | (spread2(q[1]) << 1));
-    }
+    host_parallel_for(ncell, [&](int64_t b, int64_t e)
+                      {
+                          for (int64_t i = b; i < e; ++i)
+                          {
+                              uint64_t q[3] = {0, 0, 0};
+                              for (int d = 0; d < ndim; ++d) { q[d] = static_cast<uint64_t>((clcnd_body[i * ndim + d] - lo[d]) * sc[d]); }
+                              key[i] = (3 == ndim) ? (spread3(q[0]) | (spread3(q[1]) << 1) | (spread3(q[2]) << 2))
+                                                   : (spread2(q[0]) | (spread2(q[1]) << 1));
+                          }
+                      });
 }
 
 // reverse Cuthill-McKee rank of every body cell over the cell-face-cell graph
@@ -76,19 +81,26 @@ void rcm_rank(int64_t ncell, int32_t const * clfcs_body, int32_t const * fccls_b
         return fccls_body[ifc * 4 + 0] + fccls_body[ifc * 4 + 1] - static_cast<int32_t>(icl);
     };
     std::vector<int32_t> degree(static_cast<size_t>(ncell));
-    for (int64_t i = 0; i < ncell; ++i)
-    {
-        int deg = 0;
-        for (int f = 0; f < clfcs_body[i * 7]; ++f) { deg += neighbour(i, f) >= 0 ? 1 : 0; }
-        degree[i] = deg;
-    }
+    host_parallel_for(ncell, [&](int64_t b, int64_t e)
+                      {
+                          for (int64_t i = b; i < e; ++i)
+                          {
+                              int deg = 0;
+                              for (int f = 0; f < clfcs_body[i * 7]; ++f) { deg += neighbour(i, f) >= 0 ? 1 : 0; }
+                              degree[i] = deg;
+                          }
+                      });
     std::vector<int32_t> order;
     order.reserve(static_cast<size_t>(ncell));
     std::vector<char> seen(static_cast<size_t>(ncell), 0);
-    // seeds in ascending (degree, id) so every component starts from a low-degree cell
+    // seeds in ascending (degree, id) so every component starts from a low-degree cell: a counting sort (degree <= 6)
     std::vector<int32_t> seeds(static_cast<size_t>(ncell));
-    std::iota(seeds.begin(), seeds.end(), 0);
-    std::stable_sort(seeds.begin(), seeds.end(), [&](int32_t a, int32_t b) { return degree[a] < degree[b]; });
+    {
+        int64_t cnt[CLMFC + 2] = {0};
+        for (int64_t i = 0; i < ncell; ++i) { cnt[degree[i] + 1] += 1; }
+        for (int d = 0; d <= CLMFC; ++d) { cnt[d + 1] += cnt[d]; }
+        for (int64_t i = 0; i < ncell; ++i) { seeds[cnt[degree[i]]++] = static_cast<int32_t>(i); }
+    }
     for (int32_t const seed : seeds)
     {
         if (seen[seed]) { continue; }
@@ -178,27 +190,72 @@ int scg_mesh_create_part(scg_mesh ** out, int ndim, int64_t nnode, int64_t nface
     if (SCG_ORDER_MORTON == order) { morton_keys(ndim, ncell, clcnd_b, key); }
     else if (SCG_ORDER_RCM == order) { rcm_rank(ncell, clfcs_b, fccls_b, key); }
     m->perm.resize(static_cast<size_t>(ncell));
-    std::iota(m->perm.begin(), m->perm.end(), 0);
     // primary key: cell type; then owned interface cells (owned == 2: their state is sent to another partition, so
     // they are marched first and their halo message travels while the interior cells are marched), owned
-    // interior cells, halo copies; then the locality key
+    // interior cells, halo copies; then the locality key.  (type, class) has at most 27 values: a stable counting
+    // sort, fed in the order of the locality key.
     auto halo = [&](int32_t c) -> int { return !owned ? 1 : (2 == owned[c] ? 0 : (owned[c] ? 1 : 2)); };
-    if (key.empty())
     {
-        std::stable_sort(m->perm.begin(), m->perm.end(), [&](int32_t a, int32_t b)
-                         { return cltpn_b[a] != cltpn_b[b] ? cltpn_b[a] < cltpn_b[b] : halo(a) < halo(b); });
-    }
-    else
-    {
-        std::stable_sort(m->perm.begin(), m->perm.end(), [&](int32_t a, int32_t b)
-                         {
-                             if (cltpn_b[a] != cltpn_b[b]) { return cltpn_b[a] < cltpn_b[b]; }
-                             if (halo(a) != halo(b)) { return halo(a) < halo(b); }
-                             return key[a] < key[b];
-                         });
+        std::vector<int32_t> by_key; // cells in ascending locality key (ties in ascending id); empty = identity
+        if (SCG_ORDER_RCM == order)
+        {
+            // the keys are a permutation of 0 .. ncell-1
+            by_key.resize(static_cast<size_t>(ncell));
+            host_parallel_for(ncell, [&](int64_t b, int64_t e)
+                              {
+                                  for (int64_t i = b; i < e; ++i) { by_key[key[i]] = static_cast<int32_t>(i); }
+                              });
+        }
+        else if (!key.empty())
+        {
+            // Morton: sort (key, id) pairs in one chunk per thread, then merge the chunks pairwise
+            std::vector<std::pair<uint64_t, int32_t>> kv(static_cast<size_t>(ncell));
+            host_parallel_for(ncell, [&](int64_t b, int64_t e)
+                              {
+                                  for (int64_t i = b; i < e; ++i) { kv[i] = {key[i], static_cast<int32_t>(i)}; }
+                              });
+            int64_t const nchunk = (ncell < 200000) ? 1 : host_threads();
+            int64_t const clen = (ncell + nchunk - 1) / nchunk;
+            host_parallel_for(nchunk, [&](int64_t cb, int64_t ce)
+                              {
+                                  for (int64_t c = cb; c < ce; ++c)
+                                  {
+                                      std::sort(kv.begin() + std::min(ncell, c * clen), kv.begin() + std::min(ncell, (c + 1) * clen));
+                                  }
+                              }, 2);
+            for (int64_t w = 1; w < nchunk; w *= 2)
+            {
+                int64_t const npair = (nchunk + 2 * w - 1) / (2 * w);
+                host_parallel_for(npair, [&](int64_t pb, int64_t pe)
+                                  {
+                                      for (int64_t p = pb; p < pe; ++p)
+                                      {
+                                          int64_t const lo = std::min(ncell, 2 * p * w * clen), mid = std::min(ncell, (2 * p + 1) * w * clen),
+                                                        hi = std::min(ncell, (2 * p + 2) * w * clen);
+                                          std::inplace_merge(kv.begin() + lo, kv.begin() + mid, kv.begin() + hi);
+                                      }
+                                  }, 2);
+            }
+            by_key.resize(static_cast<size_t>(ncell));
+            host_parallel_for(ncell, [&](int64_t b, int64_t e)
+                              {
+                                  for (int64_t i = b; i < e; ++i) { by_key[i] = kv[i].second; }
+                              });
+        }
+        int64_t cnt[9 * 3 + 1] = {0};
+        for (int64_t i = 0; i < ncell; ++i) { cnt[cltpn_b[i] * 3 + halo(static_cast<int32_t>(i)) + 1] += 1; }
+        for (int b = 0; b < 27; ++b) { cnt[b + 1] += cnt[b]; }
+        for (int64_t r = 0; r < ncell; ++r)
+        {
+            int32_t const c = by_key.empty() ? static_cast<int32_t>(r) : by_key[r];
+            m->perm[cnt[cltpn_b[c] * 3 + halo(c)]++] = c;
+        }
     }
     m->iperm.resize(static_cast<size_t>(ncell));
-    for (int64_t k = 0; k < ncell; ++k) { m->iperm[m->perm[k]] = static_cast<int32_t>(k); }
+    host_parallel_for(ncell, [&](int64_t b, int64_t e)
+                      {
+                          for (int64_t k = b; k < e; ++k) { m->iperm[m->perm[k]] = static_cast<int32_t>(k); }
+                      });
 
     // ---- groups
     {
@@ -238,44 +295,66 @@ int scg_mesh_create_part(scg_mesh ** out, int ndim, int64_t nnode, int64_t nface
 
     // ---- neighbour table in device numbering
     std::vector<int32_t> nbr(static_cast<size_t>(m->nbr_total));
-    for (auto const & g : m->groups)
     {
-        int const nfc = ct_nfc(g.type);
-        for (int32_t i = 0; i < g.n; ++i)
+        std::atomic<int64_t> bad_cell{-1};
+        std::atomic<int> bad_kind{0};
+        for (auto const & g : m->groups)
         {
-            int64_t const icl = m->perm[g.beg + i];
-            for (int f = 0; f < nfc; ++f)
-            {
-                int32_t const ifc = clfcs_b[icl * 7 + 1 + f];
-                if (ifc < 0 || ifc >= nface)
-                {
-                    delete m;
-                    return fail("scg_mesh_create: clfcs[%lld][%d] = %d out of range", static_cast<long long>(icl), f + 1, ifc);
-                }
-                int32_t const jcl = fccls_b[int64_t(ifc) * 4] + fccls_b[int64_t(ifc) * 4 + 1] - static_cast<int32_t>(icl);
-                if (jcl >= ncell || jcl < -ngstcell)
-                {
-                    delete m;
-                    return fail("scg_mesh_create: neighbour %d of cell %lld out of range (build_ghost() not run?)", jcl,
-                                static_cast<long long>(icl));
-                }
-                nbr[g.off_nbr + int64_t(f) * g.n + i] = (jcl >= 0) ? m->iperm[jcl] : static_cast<int32_t>(ncell + (-jcl - 1));
-            }
+            int const nfc = ct_nfc(g.type);
+            host_parallel_for(g.n, [&](int64_t ib, int64_t ie)
+                              {
+                                  for (int64_t i = ib; i < ie; ++i)
+                                  {
+                                      int64_t const icl = m->perm[g.beg + i];
+                                      for (int f = 0; f < nfc; ++f)
+                                      {
+                                          int32_t const ifc = clfcs_b[icl * 7 + 1 + f];
+                                          if (ifc < 0 || ifc >= nface)
+                                          {
+                                              bad_cell = icl;
+                                              bad_kind = 1;
+                                              return;
+                                          }
+                                          int32_t const jcl = fccls_b[int64_t(ifc) * 4] + fccls_b[int64_t(ifc) * 4 + 1] - static_cast<int32_t>(icl);
+                                          if (jcl >= ncell || jcl < -ngstcell)
+                                          {
+                                              bad_cell = icl;
+                                              bad_kind = 2;
+                                              return;
+                                          }
+                                          nbr[g.off_nbr + int64_t(f) * g.n + i] = (jcl >= 0) ? m->iperm[jcl] : static_cast<int32_t>(ncell + (-jcl - 1));
+                                      }
+                                  }
+                              });
+        }
+        if (bad_cell >= 0)
+        {
+            long long const icl = bad_cell;
+            int const kind = bad_kind;
+            delete m;
+            return (1 == kind) ? fail("scg_mesh_create: a face index in clfcs[%lld] is out of range", icl)
+                               : fail("scg_mesh_create: a neighbour of cell %lld is out of range (build_ghost() not run?)", icl);
         }
     }
 
     // ---- stored-row -> device-index map (ghost rows first on the host side)
     std::vector<int32_t> rowmap(static_cast<size_t>(m->T));
     for (int64_t s = 0; s < ngstcell; ++s) { rowmap[s] = static_cast<int32_t>(ncell + (ngstcell - 1 - s)); }
-    for (int64_t i = 0; i < ncell; ++i) { rowmap[ngstcell + i] = m->iperm[i]; }
+    host_parallel_for(ncell, [&](int64_t b, int64_t e)
+                      {
+                          for (int64_t i = b; i < e; ++i) { rowmap[ngstcell + i] = m->iperm[i]; }
+                      });
 
     // ---- host copies for the boundary-condition setup
     m->h_fccls.resize(static_cast<size_t>(nface) * 2);
-    for (int64_t f = 0; f < nface; ++f)
-    {
-        m->h_fccls[2 * f] = fccls_b[4 * f];
-        m->h_fccls[2 * f + 1] = fccls_b[4 * f + 1];
-    }
+    host_parallel_for(nface, [&](int64_t b, int64_t e)
+                      {
+                          for (int64_t f = b; f < e; ++f)
+                          {
+                              m->h_fccls[2 * f] = fccls_b[4 * f];
+                              m->h_fccls[2 * f + 1] = fccls_b[4 * f + 1];
+                          }
+                      });
     m->h_fcnml.assign(fcnml + ngstface * ndim, fcnml + (ngstface + nface) * ndim);
 
     // ---- device uploads

@@ -99,8 +99,34 @@ for perm in ((0, 1, 2), (0, 2, 1), (1, 0, 2), (1, 2, 0), (2, 0, 1), (2, 1, 0)):
     _KUHN.append(path)
 
 
+def _mixed_3d_native(dims, xyz, return_box_j, return_box):
+    """The connectivity half of ``mixed_3d`` in native code on all host threads (csrc/scg_meshgen.cpp); the numpy code
+    below stays the definition (tests/test_meshgen_native.py holds the two equal, array for array)."""
+    import ctypes as C
+    from . import _lib
+    lib = _lib.load()
+    nlat, ncell = C.c_int64(), C.c_int64()
+    _lib.check(lib.scg_meshgen_mixed3d_count(*dims, C.byref(nlat), C.byref(ncell)))
+    xyz = np.ascontiguousarray(xyz)
+    assert len(xyz) == nlat.value
+    cltpn = np.empty(ncell.value, dtype=np.int32)
+    clnds = np.empty((ncell.value, CLMND + 1), dtype=np.int32)
+    used = np.empty(nlat.value, dtype=np.uint8)
+    want_box = return_box or return_box_j
+    box = np.empty((4, ncell.value), dtype=np.int64) if want_box else None
+    nn = C.c_int64()
+    _lib.check(lib.scg_meshgen_mixed3d_cells(*dims, _lib.ptr(xyz), _lib.ptr(cltpn), _lib.ptr(clnds), used.ctypes.data,
+                                             box.ctypes.data if want_box else None, C.byref(nn)))
+    out = (np.ascontiguousarray(xyz[used.view(bool)]), cltpn, clnds)
+    if return_box_j:
+        out += (box[1].copy(),)
+    if return_box:
+        out += ((box[0], box[1], box[2], box[3]),)
+    return out
+
+
 def mixed_3d(nx, ny, nz, lx=None, ly=None, lz=None, x1=None, z1=None, kinds="hpt", jitter=0.0, j_range=None,
-             return_box_j=False, box_range=None, return_box=False):
+             return_box_j=False, box_range=None, return_box=False, native=True):
     """Stepped channel of ``nx`` x ``ny`` x ``nz`` boxes: block A hexahedra
     (``i < x1, k < z1``), block B z-axis prisms (``i >= x1, k < z1``; each box split on its vertical
     ll-ur diagonal plane), block C tetrahedra (``i >= x1, k >= z1``; Kuhn split, 6 per box); the
@@ -143,6 +169,9 @@ def mixed_3d(nx, ny, nz, lx=None, ly=None, lz=None, x1=None, z1=None, kinds="hpt
         y = y + np.where(inner, jitter * np.cos(26.651 * ii + 41.347 * jj + 11.135 * kk), 0.0) * (ly / ny)
         z = z + np.where(inner, jitter * np.sin(63.7264 * ii + 10.873 * jj + 53.127 * kk), 0.0) * (lz / nz)
     nxl, nyl, nzl = i1 - i0, j1 - j0, k1 - k0
+    if native and (nxl + 1) * (nyl + 1) * (nzl + 1) < 2 ** 31:
+        return _mixed_3d_native((nx, ny, nz, x1, z1, i0, i1, j0, j1, k0, k1), np.stack([x.ravel(), y.ravel(), z.ravel()], axis=1),
+                                return_box_j, return_box)
     # local lattice id, same relative order as the global one
     nid = (((ii - i0) * (nyl + 1) + (jj - j0)) * (nzl + 1) + (kk - k0)).astype(np.int64)
     li, lj, lk = [a.ravel() for a in np.meshgrid(np.arange(nxl), np.arange(nyl), np.arange(nzl), indexing="ij")]
