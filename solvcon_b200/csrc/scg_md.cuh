@@ -13,6 +13,7 @@
 #pragma once
 
 #include "scg_common.cuh"
+#include "scg_par.hpp"
 
 #include <vector>
 
@@ -102,8 +103,8 @@ struct scg_mesh
     int64_t stride = 0; // T padded to a multiple of 32
     std::vector<int32_t> perm;  // device slot -> reference cell
     std::vector<int32_t> iperm; // reference cell -> device slot
-    std::vector<int32_t> h_fccls; // [nface][2] body faces: owner, neighbour (reference ids)
-    std::vector<double> h_fcnml;  // [nface][ndim] body faces
+    scg::HostBuf<int32_t> h_fccls; // [nface][2] body faces: owner, neighbour (reference ids)
+    scg::HostBuf<double> h_fcnml;  // [nface][ndim] body faces
     std::vector<scg::MeshGroup> groups;
     int64_t geo_total = 0;
     int64_t nbr_total = 0;

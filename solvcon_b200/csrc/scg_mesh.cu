@@ -185,10 +185,12 @@ int scg_mesh_create_part(scg_mesh ** out, int ndim, int64_t nnode, int64_t nface
         }
     }
 
+    HostStageTimer tm("dmesh");
     // ---- cell ordering: type groups (ascending type id), inside a group by key
     std::vector<uint64_t> key;
     if (SCG_ORDER_MORTON == order) { morton_keys(ndim, ncell, clcnd_b, key); }
     else if (SCG_ORDER_RCM == order) { rcm_rank(ncell, clfcs_b, fccls_b, key); }
+    tm.lap("ordering keys");
     m->perm.resize(static_cast<size_t>(ncell));
     // primary key: cell type; then owned interface cells (owned == 2: their state is sent to another partition, so
     // they are marched first and their halo message travels while the interior cells are marched), owned
@@ -257,6 +259,7 @@ int scg_mesh_create_part(scg_mesh ** out, int ndim, int64_t nnode, int64_t nface
                           for (int64_t k = b; k < e; ++k) { m->iperm[m->perm[k]] = static_cast<int32_t>(k); }
                       });
 
+    tm.lap("sort into groups");
     // ---- groups
     {
         int64_t k = 0;
@@ -294,7 +297,8 @@ int scg_mesh_create_part(scg_mesh ** out, int ndim, int64_t nnode, int64_t nface
     }
 
     // ---- neighbour table in device numbering
-    std::vector<int32_t> nbr(static_cast<size_t>(m->nbr_total));
+    HostBuf<int32_t> nbr;
+    nbr.alloc(static_cast<size_t>(m->nbr_total));
     {
         std::atomic<int64_t> bad_cell{-1};
         std::atomic<int> bad_kind{0};
@@ -337,8 +341,10 @@ int scg_mesh_create_part(scg_mesh ** out, int ndim, int64_t nnode, int64_t nface
         }
     }
 
+    tm.lap("groups + neighbour table");
     // ---- stored-row -> device-index map (ghost rows first on the host side)
-    std::vector<int32_t> rowmap(static_cast<size_t>(m->T));
+    HostBuf<int32_t> rowmap;
+    rowmap.alloc(static_cast<size_t>(m->T));
     for (int64_t s = 0; s < ngstcell; ++s) { rowmap[s] = static_cast<int32_t>(ncell + (ngstcell - 1 - s)); }
     host_parallel_for(ncell, [&](int64_t b, int64_t e)
                       {
@@ -346,7 +352,7 @@ int scg_mesh_create_part(scg_mesh ** out, int ndim, int64_t nnode, int64_t nface
                       });
 
     // ---- host copies for the boundary-condition setup
-    m->h_fccls.resize(static_cast<size_t>(nface) * 2);
+    m->h_fccls.alloc(static_cast<size_t>(nface) * 2);
     host_parallel_for(nface, [&](int64_t b, int64_t e)
                       {
                           for (int64_t f = b; f < e; ++f)
@@ -355,8 +361,9 @@ int scg_mesh_create_part(scg_mesh ** out, int ndim, int64_t nnode, int64_t nface
                               m->h_fccls[2 * f + 1] = fccls_b[4 * f + 1];
                           }
                       });
-    m->h_fcnml.assign(fcnml + ngstface * ndim, fcnml + (ngstface + nface) * ndim);
+    m->h_fcnml.copy_from(fcnml + ngstface * ndim, static_cast<size_t>(nface) * ndim);
 
+    tm.lap("rowmap + host copies");
     // ---- device uploads
     bool ok = true;
     auto up_i = [&](DevBuf<int32_t> & b, int32_t const * h, int64_t n)
@@ -379,6 +386,7 @@ int scg_mesh_create_part(scg_mesh ** out, int ndim, int64_t nnode, int64_t nface
     up_d(m->d_fccnd, fccnd, (ngstface + nface) * ndim);
     up_d(m->d_clcnd, clcnd, m->T * ndim);
     ok = ok && cudaSuccess == cudaStreamSynchronize(stream());
+    tm.lap("uploads");
     if (!ok)
     {
         cudaError_t const e = cudaGetLastError();
