@@ -495,6 +495,40 @@ __global__ void __launch_bounds__(EqoCfg<TYPE>::TB, EqoCfg<TYPE>::MB) md_dsoln_e
     cell_dsoln_eqo<TYPE, EqoCfg<TYPE>::TB, EqoCfg<TYPE>::PF>(F, G, i, eqo_smem + threadIdx.x);
 }
 
+// second generation of the same phase for the 3D cell types (cell_dsoln_eqo2): every global load before the equation loop
+#ifndef SCG_EQO2_MASK
+#define SCG_EQO2_MASK 0 // cell types marched by md_dsoln_eqo2_kernel: 1 hex, 2 tet, 4 prism, 8 pyramid
+#endif
+#ifndef SCG_EQO2_TB
+#define SCG_EQO2_TB 64
+#endif
+#ifndef SCG_EQO2_MB_HEX
+#define SCG_EQO2_MB_HEX 6
+#endif
+#ifndef SCG_EQO2_MB_PRISM
+#define SCG_EQO2_MB_PRISM 6
+#endif
+#ifndef SCG_EQO2_MB_TET
+#define SCG_EQO2_MB_TET 8
+#endif
+template <int TYPE>
+struct Eqo2Cfg
+{
+    static constexpr bool ON = (3 == ct_ndim(TYPE)) && (0 != (SCG_EQO2_MASK & (1 << (TYPE - CT_HEX))));
+    static constexpr int TYPE3 = (3 == ct_ndim(TYPE)) ? TYPE : CT_TET; // the 2D types never instantiate the 3D body
+    static constexpr int TB = SCG_EQO2_TB;
+    static constexpr int MB = (TYPE == CT_HEX) ? SCG_EQO2_MB_HEX : (TYPE == CT_TET) ? SCG_EQO2_MB_TET : SCG_EQO2_MB_PRISM;
+};
+
+template <int TYPE>
+__global__ void __launch_bounds__(Eqo2Cfg<TYPE>::TB, Eqo2Cfg<TYPE>::MB) md_dsoln_eqo2_kernel(MdField const F, MdGeo const G)
+{
+    extern __shared__ double eqo_smem[];
+    int32_t const i = G.ibeg + blockIdx.x * Eqo2Cfg<TYPE>::TB + threadIdx.x;
+    if (i >= G.iend) { return; }
+    cell_dsoln_eqo2<TYPE, Eqo2Cfg<TYPE>::TB>(F, G, i, eqo_smem + threadIdx.x);
+}
+
 // GradientElementTypeGroup tables for run-time lane -> face lookups (0-based local faces)
 __constant__ int8_t c_fge[9][8][3] = {
     {{0}}, {{0}}, {{0}},
@@ -1391,6 +1425,19 @@ void launch_cell_phase_t(scg_md * s, MeshGroup const & g, CellPhase ph, int part
     }
     case CP_DSOLN_EQO:
     {
+        if constexpr (Eqo2Cfg<TYPE>::ON)
+        {
+            constexpr int TB2 = Eqo2Cfg<TYPE>::TB;
+            constexpr int BYTES2 = DsolnEqo2<TYPE, TB2>::BYTES;
+            static bool attr2_set = false;
+            if (!attr2_set)
+            {
+                cudaFuncSetAttribute(md_dsoln_eqo2_kernel<TYPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, BYTES2);
+                attr2_set = true;
+            }
+            md_dsoln_eqo2_kernel<TYPE><<<static_cast<unsigned>(ceil_div(ncl, TB2)), TB2, BYTES2, stream()>>>(F, G);
+            break;
+        }
         constexpr int TB = EqoCfg<TYPE>::TB;
         constexpr int BYTES = DsolnEqo<TYPE, TB>::BYTES;
         static bool attr_set = false;

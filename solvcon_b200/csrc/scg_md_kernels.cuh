@@ -18,6 +18,7 @@
 #include "scg_md.cuh"
 
 #include <cfloat>
+#include <type_traits>
 
 namespace scg
 {
@@ -1543,6 +1544,450 @@ __device__ __forceinline__ void cell_dsoln_eqo(MdField const & F, MdGeo const & 
         }
         Jaco<ND> J;
         jaco_update<ND>(J, F.gamma[k], u);
+        solt_row<ND>(J, g, t);
+#pragma unroll
+        for (int e = 0; e < NEQ; ++e) { F.so0t_next[e * S + k] = t[e]; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// calc_dsoln, equation-outer, second generation (3D): every global load happens before the equation loop.
+//
+// Three facts about cell_dsoln_eqo's profile drive this version (profiles/r01f_*, r02d_fp64_pipe_ubench.txt):
+// a dependent fp64 instruction waits ~20 cycles, so a scheduler needs >= 10 independent ones in flight and two
+// warps of 255 registers do not supply them; the gather at the top of every equation is an exposed memory round
+// trip (5 per cell); and the register prefetch that hides it for hexahedra costs 62 registers.  Here
+//   * the Taylor differences udf[f][e] of ALL equations (euler_gradient.cpp:60-72) are formed in the prologue, two
+//     faces per batch of loads, and parked in shared memory, so the equation loop touches no global memory and
+//     keeps neither neighbour indices nor displacements alive;
+//   * adj(D) is stored once per PAIR of faces: its columns are the cross products idis[p] x idis[q] of the element's
+//     face displacements (GradientElement.cpp:215-249 written out), a pair of faces is shared by two gradient
+//     elements, and x*y - z*w == -(z*w - x*y) bit for bit, so hexahedra keep 12 x 3 rows instead of 8 x 9 (a zero
+//     entry may change sign, which cannot reach the sum it enters: that sum starts from +0);
+//   * the rows of an equation that is finished are reused for its new gradient and so0n, which the fused calc_solt
+//     reads back from shared memory.
+// Same operations on the same operands in the same order as cell_dsoln.
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int fge_pair_first(int type, int u) // local face pair of use u = ifge*3 + column: (p, q) with column = p x q
+{
+    return fge_face(type, u / 3, (u % 3 + 1) % 3);
+}
+__host__ __device__ constexpr int fge_pair_second(int type, int u) { return fge_face(type, u / 3, (u % 3 + 2) % 3); }
+__host__ __device__ constexpr int fge_pair_key(int type, int u)
+{
+    int const p = fge_pair_first(type, u), q = fge_pair_second(type, u);
+    return p < q ? p * 8 + q : q * 8 + p;
+}
+__host__ __device__ constexpr bool fge_pair_neg(int type, int u) { return fge_pair_first(type, u) > fge_pair_second(type, u); }
+__host__ __device__ constexpr int fge_pair_firstuse(int type, int u)
+{
+    for (int v = 0; v < u; ++v)
+    {
+        if (fge_pair_key(type, v) == fge_pair_key(type, u)) { return v; }
+    }
+    return u;
+}
+__host__ __device__ constexpr int fge_pair_id(int type, int u) // dense index of the pair among the distinct ones
+{
+    int const v = fge_pair_firstuse(type, u);
+    int id = 0;
+    for (int w = 0; w < v; ++w) { id += (fge_pair_firstuse(type, w) == w) ? 1 : 0; }
+    return id;
+}
+__host__ __device__ constexpr int fge_npair(int type)
+{
+    int n = 0;
+    for (int w = 0; w < 3 * ct_nfge(type); ++w) { n += (fge_pair_firstuse(type, w) == w) ? 1 : 0; }
+    return n;
+}
+static_assert(12 == fge_npair(CT_HEX) && 6 == fge_npair(CT_TET) && 9 == fge_npair(CT_PRISM), "face pairs of the gradient elements");
+
+// compile-time loop: f(std::integral_constant<int, I>) for I in [B, E) -- the index is a constant expression inside f,
+// which forces the constexpr table functions above to be evaluated by the compiler and not by the device
+template <int B, int E, typename Fn>
+__device__ __forceinline__ void static_for(Fn && f)
+{
+    if constexpr (B < E)
+    {
+        f(std::integral_constant<int, B>{});
+        static_for<B + 1, E>(f);
+    }
+}
+
+#ifndef SCG_EQO2_YROWS
+#define SCG_EQO2_YROWS 0 // 1: the refined reciprocal of det(D) is parked next to det(D) instead of being refined again by every equation
+#endif
+
+template <int TYPE, int TB>
+struct DsolnEqo2
+{
+    static constexpr int ND = 3;
+    static constexpr int NEQ = 5;
+    static constexpr int NFC = ct_nfc(TYPE);
+    static constexpr int NFGE = ct_nfge(TYPE);
+    static constexpr int NP = fge_npair(TYPE);
+    static constexpr int R_U = 0;                  // Taylor differences [NFC][NEQ]; equation e, once finished: rows
+                                                   // [0..2][e] = its new gradient, [3][e] = so0n of the cell
+    static constexpr int R_X = R_U + NFC * NEQ;    // cross products [NP][3]
+    static constexpr int R_DET = R_X + NP * 3;     // det(D) [NFGE]
+    static constexpr int R_END = R_DET + NFGE;
+    // Prologue staging: the neighbour rows of a face (so0c[5], so0t[5], so1c[15]) travel global -> shared by cp.async,
+    // two faces in flight, into two buffers at the END of the column; they overlay the cross products and det(D),
+    // which are written after the last face has been consumed.
+    static constexpr int FROWS = 5 * NEQ;          // 25 rows per face
+    static constexpr int ROWS = (TYPE == CT_HEX) ? 74 : (TYPE == CT_TET) ? 55 : 65;
+    static constexpr int R_A = ROWS - 2 * FROWS;
+    static constexpr int R_B = ROWS - FROWS;
+    static_assert(ROWS >= R_END, "the staging column holds the final layout");
+    static constexpr int BYTES = ROWS * TB * int(sizeof(double));
+    __host__ __device__ static constexpr int buf(int f) { return (f & 1) ? R_B : R_A; }
+    // May udf[f] be stored right after face f has been consumed?  Its rows must not lie in a buffer that still
+    // holds (or is about to receive) an unconsumed face: face f+1's buffer, and face f's own if it is refilled with f+2.
+    __host__ __device__ static constexpr bool store_now(int f)
+    {
+        int const lo = R_U + f * NEQ, hi = lo + NEQ;
+        bool ok = true;
+        if (f + 1 < NFC) { ok = ok && (hi <= buf(f + 1) || lo >= buf(f + 1) + FROWS); }
+        if (f + 2 < NFC) { ok = ok && (hi <= buf(f) || lo >= buf(f) + FROWS); }
+        return ok;
+    }
+};
+
+template <int TYPE, int TB>
+__device__ __forceinline__ void eqo2_stage_face(MdField const & F, int64_t j, double * st)
+{
+    int64_t const S = F.S;
+#pragma unroll
+    for (int e = 0; e < 5; ++e)
+    {
+        cp_async8(st + e * TB, &F.so0c[e * S + j]);
+        cp_async8(st + (5 + e) * TB, &F.so0t[e * S + j]);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { cp_async8(st + (10 + e * 3 + d) * TB, &F.so1c[(e * 3 + d) * S + j]); }
+    }
+    cp_async_commit();
+}
+
+template <int TYPE, int TB, bool FAST>
+__device__ __forceinline__ bool eqo2_solve(double const * sm, int e, double ofg1, double sgm0,
+                                           double (&grad)[ct_nfge(TYPE)][3], double (&w)[ct_nfge(TYPE)], double & sigma_max)
+{
+    using L = DsolnEqo2<TYPE, TB>;
+    constexpr int ND = 3;
+    constexpr int NFC = L::NFC;
+    constexpr int NFGE = L::NFGE;
+    bool ok = true;
+    double udf[NFC];
+#pragma unroll
+    for (int f = 0; f < NFC; ++f) { udf[f] = sm[(L::R_U + f * L::NEQ + e) * TB]; }
+    static_for<0, NFGE>([&](auto IFGE) {
+        constexpr int ifge = decltype(IFGE)::value;
+#pragma unroll
+        for (int a = 0; a < ND; ++a)
+        {
+            double r = 0.0;
+            static_for<0, ND>([&](auto B) {
+                constexpr int b = decltype(B)::value;
+                constexpr int u = ifge * 3 + b;
+                constexpr int row = L::R_X + fge_pair_id(TYPE, u) * 3;
+                constexpr int fl = fge_face(TYPE, ifge, b);
+                constexpr bool neg = fge_pair_neg(TYPE, u);
+                double const p = sm[(row + a) * TB] * udf[fl];
+                r = neg ? r - p : r + p;
+            });
+            grad[ifge][a] = r;
+        }
+    });
+#pragma unroll
+    for (int ifge = 0; ifge < NFGE; ++ifge)
+    {
+        DivBy<FAST> by_det(sm[(L::R_DET + ifge) * TB]);
+#pragma unroll
+        for (int a = 0; a < ND; ++a) { grad[ifge][a] = by_det.template quot<SCG_EQO_ZERO>(grad[ifge][a]); }
+        ok = ok && by_det.ok;
+    }
+#pragma unroll
+    for (int ifge = 0; ifge < NFGE; ++ifge)
+    {
+        double sq = 0.0;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) { sq += grad[ifge][d] * grad[ifge][d]; }
+        w[ifge] = sq + MD_ALMOST_ZERO;
+    }
+#pragma unroll
+    for (int ifge = 0; ifge < NFGE; ++ifge) { w[ifge] = FAST ? sqrt_fast(w[ifge], ok) : sqrt(w[ifge]); }
+#pragma unroll
+    for (int ifge = 0; ifge < NFGE; ++ifge) { w[ifge] = FAST ? rcp_fast(w[ifge], ok) : 1.0 / w[ifge]; }
+    double wacc = 0.0;
+#pragma unroll
+    for (int ifge = 0; ifge < NFGE; ++ifge) { wacc += w[ifge]; }
+    {
+        DivBy<FAST> by_wacc(wacc);
+#pragma unroll
+        for (int ifge = 0; ifge < NFGE; ++ifge) { w[ifge] = by_wacc.template quot<0>(w[ifge]) - ofg1; }
+        ok = ok && by_wacc.ok;
+    }
+    double wmax = 0.0, wmin = 0.0;
+#pragma unroll
+    for (int ifge = 0; ifge < NFGE; ++ifge)
+    {
+        wmax = fmax(wmax, w[ifge]);
+        wmin = fmin(wmin, w[ifge]);
+    }
+    DivBy<FAST> by_hi(wmax + MD_ALMOST_ZERO);
+    DivBy<FAST> by_lo(wmin - MD_ALMOST_ZERO);
+    double const sm_ = fmin(by_hi.template quot<0>(1.0 - ofg1), by_lo.template quot<0>(-ofg1));
+    ok = ok && by_hi.ok && by_lo.ok;
+    sigma_max = fmin(sm_, sgm0);
+    return ok;
+}
+
+template <int TYPE, int TB>
+__device__ __forceinline__ void cell_dsoln_eqo2(MdField const & F, MdGeo const & G, int32_t i, double * sm)
+{
+    using L = DsolnEqo2<TYPE, TB>;
+    constexpr int ND = 3;
+    constexpr int NEQ = 5;
+    constexpr int NFC = L::NFC;
+    constexpr int NFGE = L::NFGE;
+    int64_t const n = G.n;
+    int64_t const S = F.S;
+    int64_t const k = G.beg + i;
+    double const hdt = F.dt * 0.5;
+    double const ofg1 = 1.0 / NFGE;
+    double sgm0;
+    double ga_own;
+    {
+        int32_t rcl[NFC];
+        double jdis[NFC][ND];
+#pragma unroll
+        for (int f = 0; f < NFC; ++f) { rcl[f] = G.nbr[f * n + i]; }
+        // the neighbour rows of the first two faces travel while the geometry is worked out
+        eqo2_stage_face<TYPE, TB>(F, rcl[0], sm + L::R_A * TB);
+        eqo2_stage_face<TYPE, TB>(F, rcl[1], sm + L::R_B * TB);
+        double const cflc_in = F.cflc[k];
+        ga_own = F.gamma[k]; // for the fused calc_solt at the end: requested now, used last
+        double un[NEQ];
+#pragma unroll
+        for (int e = 0; e < NEQ; ++e) { un[e] = F.so0n[e * S + k]; }
+        double gp[NFC][ND];
+        {
+            // ---- gradient element geometry (GradientElement.cpp:137-213, :81-133)
+            double icecnd[ND];
+#pragma unroll
+            for (int d = 0; d < ND; ++d) { icecnd[d] = F.solpt[d * S + k]; }
+            double mid[NFC][ND], jce[NFC][ND];
+#pragma unroll
+            for (int f = 0; f < NFC; ++f)
+            {
+                int64_t const j = rcl[f];
+#pragma unroll
+                for (int d = 0; d < ND; ++d)
+                {
+                    mid[f][d] = G.cecnd[(f * ND + d) * n + i];
+                    jce[f][d] = F.solpt[d * S + j];
+                }
+            }
+            double const acfl = fabs(cflc_in);
+            sgm0 = F.sigma0 / acfl;
+            double const tau = F.taumin + acfl * F.tauscale;
+#pragma unroll
+            for (int f = 0; f < NFC; ++f)
+            {
+#pragma unroll
+                for (int d = 0; d < ND; ++d)
+                {
+                    gp[f][d] = mid[f][d] + tau * (jce[f][d] - mid[f][d]);
+                    jdis[f][d] = gp[f][d] - jce[f][d]; // completed below: + icecnd - cnd
+                }
+            }
+            double avg[ND];
+#pragma unroll
+            for (int d = 0; d < ND; ++d) { avg[d] = 0.0; }
+#pragma unroll
+            for (int f = 0; f < NFC; ++f)
+            {
+#pragma unroll
+                for (int d = 0; d < ND; ++d) { avg[d] += gp[f][d]; }
+            }
+            {
+                double a2[ND];
+                DivBy<true> by_nfc(static_cast<double>(NFC));
+#pragma unroll
+                for (int d = 0; d < ND; ++d) { a2[d] = by_nfc.template quot<0>(avg[d]); }
+                if (!by_nfc.ok)
+                {
+#pragma unroll
+                    for (int d = 0; d < ND; ++d) { a2[d] = avg[d] / static_cast<double>(NFC); }
+                }
+#pragma unroll
+                for (int d = 0; d < ND; ++d) { avg[d] = a2[d]; }
+            }
+            double cnd[ND];
+#pragma unroll
+            for (int d = 0; d < ND; ++d) { cnd[d] = 0.0; }
+            double voc = 0.0;
+#pragma unroll
+            for (int isub = 0; isub < NFGE; ++isub)
+            {
+                double subcnd[ND];
+                double dst[ND][ND];
+#pragma unroll
+                for (int d = 0; d < ND; ++d) { subcnd[d] = avg[d]; }
+#pragma unroll
+                for (int ivx = 0; ivx < ND; ++ivx)
+                {
+                    int const fl = fge_face(TYPE, isub, ivx);
+#pragma unroll
+                    for (int d = 0; d < ND; ++d)
+                    {
+                        subcnd[d] += gp[fl][d];
+                        dst[ivx][d] = gp[fl][d] - avg[d];
+                    }
+                }
+#pragma unroll
+                for (int d = 0; d < ND; ++d) { subcnd[d] /= static_cast<double>(ND + 1); }
+                double const vob = det_n<ND>(dst);
+                voc += vob;
+#pragma unroll
+                for (int d = 0; d < ND; ++d) { cnd[d] += subcnd[d] * vob; }
+            }
+            {
+                double c2[ND];
+                DivBy<true> by_voc(voc);
+#pragma unroll
+                for (int d = 0; d < ND; ++d) { c2[d] = by_voc.template quot<0>(cnd[d]); }
+                if (!by_voc.ok)
+                {
+#pragma unroll
+                    for (int d = 0; d < ND; ++d) { c2[d] = cnd[d] / voc; }
+                }
+#pragma unroll
+                for (int d = 0; d < ND; ++d) { cnd[d] = c2[d]; }
+            }
+            // ---- displacements (GradientElement.cpp:196-211); idis replaces gp
+#pragma unroll
+            for (int f = 0; f < NFC; ++f)
+            {
+#pragma unroll
+                for (int d = 0; d < ND; ++d)
+                {
+                    jdis[f][d] = jdis[f][d] + icecnd[d] - cnd[d];
+                    gp[f][d] = gp[f][d] - cnd[d];
+                }
+            }
+        }
+        // ---- Taylor differences of every equation (euler_gradient.cpp:60-72) -> shared memory.  Face f is consumed from
+        //      its staging buffer, the buffer is refilled with face f+2, and udf[f] is stored at once when its rows are
+        //      clear of the buffers still in use (DsolnEqo2::store_now), else after the last face.
+        double uv[NFC][NEQ];
+        static_for<0, NFC>([&](auto FC) {
+            constexpr int f = decltype(FC)::value;
+            if constexpr (f + 1 < NFC) { cp_async_wait<1>(); }
+            else { cp_async_wait<0>(); }
+            double const * st = sm + L::buf(f) * TB;
+#pragma unroll
+            for (int e = 0; e < NEQ; ++e)
+            {
+                double val = st[e * TB] + hdt * st[(5 + e) * TB] - un[e];
+#pragma unroll
+                for (int d = 0; d < ND; ++d) { val += jdis[f][d] * st[(10 + e * ND + d) * TB]; }
+                uv[f][e] = val;
+            }
+            if constexpr (f + 2 < NFC)
+            {
+                asm volatile("" ::: "memory"); // the buffer is refilled only after its last read
+                eqo2_stage_face<TYPE, TB>(F, rcl[f + 2], sm + L::buf(f) * TB);
+            }
+            if constexpr (L::store_now(f))
+            {
+#pragma unroll
+                for (int e = 0; e < NEQ; ++e) { sm[(L::R_U + f * NEQ + e) * TB] = uv[f][e]; }
+            }
+        });
+        static_for<0, NFC>([&](auto FC) {
+            constexpr int f = decltype(FC)::value;
+            if constexpr (!L::store_now(f))
+            {
+#pragma unroll
+                for (int e = 0; e < NEQ; ++e) { sm[(L::R_U + f * NEQ + e) * TB] = uv[f][e]; }
+            }
+        });
+        // ---- adj(D) as cross products of face pairs, det(D) of every gradient element -> shared memory (over the
+        //      staging buffers, which are idle now)
+        static_for<0, 3 * NFGE>([&](auto U) {
+            constexpr int u = decltype(U)::value;
+            if constexpr (fge_pair_firstuse(TYPE, u) == u)
+            {
+                constexpr int key = fge_pair_key(TYPE, u);
+                constexpr int p = key / 8, q = key % 8; // p < q
+                constexpr int row = L::R_X + fge_pair_id(TYPE, u) * 3;
+                sm[(row + 0) * TB] = gp[p][1] * gp[q][2] - gp[p][2] * gp[q][1];
+                sm[(row + 1) * TB] = gp[p][2] * gp[q][0] - gp[p][0] * gp[q][2];
+                sm[(row + 2) * TB] = gp[p][0] * gp[q][1] - gp[p][1] * gp[q][0];
+            }
+        });
+        static_for<0, NFGE>([&](auto IFGE) {
+            constexpr int ifge = decltype(IFGE)::value;
+            constexpr int f0 = fge_face(TYPE, ifge, 0), f1 = fge_face(TYPE, ifge, 1), f2 = fge_face(TYPE, ifge, 2);
+            double dst[ND][ND];
+#pragma unroll
+            for (int d = 0; d < ND; ++d)
+            {
+                dst[0][d] = gp[f0][d];
+                dst[1][d] = gp[f1][d];
+                dst[2][d] = gp[f2][d];
+            }
+            sm[(L::R_DET + ifge) * TB] = det_n<ND>(dst);
+        });
+    }
+    {
+        // ---- one equation at a time; no global loads but the cell's own so0n, which is parked for the fused calc_solt
+        //      where equation e's fourth Taylor difference was
+#pragma unroll 1
+        for (int e = 0; e < NEQ; ++e)
+        {
+            asm volatile("" ::: "memory"); // keep the loop-invariant shared-memory reads inside the loop
+            double const un_e = F.so0n[e * S + k]; // cached by the prologue's read; wanted at the end of the iteration only
+            double grad[NFGE][ND], w[NFGE];
+            double sigma_max;
+            if (!eqo2_solve<TYPE, TB, true>(sm, e, ofg1, sgm0, grad, w, sigma_max))
+            {
+                eqo2_solve<TYPE, TB, false>(sm, e, ofg1, sgm0, grad, w, sigma_max);
+            }
+            double o[ND];
+#pragma unroll
+            for (int d = 0; d < ND; ++d) { o[d] = 0.0; }
+#pragma unroll
+            for (int isub = 0; isub < NFGE; ++isub)
+            {
+                double const wgt = ofg1 + sigma_max * w[isub];
+#pragma unroll
+                for (int d = 0; d < ND; ++d) { o[d] += wgt * grad[isub][d]; }
+            }
+#pragma unroll
+            for (int d = 0; d < ND; ++d)
+            {
+                F.so1n[(e * ND + d) * S + k] = o[d];
+                sm[(L::R_U + d * NEQ + e) * TB] = o[d];
+            }
+            sm[(L::R_U + 3 * NEQ + e) * TB] = un_e;
+        }
+    }
+    // ---- fused calc_solt of the NEXT substep (euler_march.cpp:161-191)
+    if (F.fuse_solt)
+    {
+        asm volatile("" ::: "memory");
+        double u[NEQ], g[NEQ][ND], t[NEQ];
+#pragma unroll
+        for (int e = 0; e < NEQ; ++e)
+        {
+            u[e] = sm[(L::R_U + 3 * NEQ + e) * TB];
+#pragma unroll
+            for (int d = 0; d < ND; ++d) { g[e][d] = sm[(L::R_U + d * NEQ + e) * TB]; }
+        }
+        Jaco<ND> J;
+        jaco_update<ND>(J, ga_own, u);
         solt_row<ND>(J, g, t);
 #pragma unroll
         for (int e = 0; e < NEQ; ++e) { F.so0t_next[e * S + k] = t[e]; }
