@@ -551,14 +551,16 @@ def run_subs(args, rank, world, local, dist):
     import gc
     out = []
 
-    def one(workload, steps, chunk, size=0, e2e=False, extra=None):
+    def one(workload, steps, chunk, size=0, e2e=False, extra=None, order=None, tag=None):
         a = copy.copy(args)
         a.workload, a.size, a.chunk = workload, size, chunk
+        if order is not None:
+            a.order = order
         t0 = time.perf_counter()
         try:
             wl = make_workload(a)
             wl.rank, wl.world, wl.dist, wl.local = rank, world, dist, local
-            par = wl.parity() if (rank == 0 and world == 1 and hasattr(wl, "parity") and not args.no_parity) else None
+            par = wl.parity() if (rank == 0 and world == 1 and hasattr(wl, "parity") and not args.no_parity and not tag) else None
             r = measure(wl, steps, 3, a, rank, world, local, dist, e2e=e2e, cpu=False)
             entry = {"workload": wl.name, "value": r["value"], "unit": UNIT, "ms_per_step": r["ms_per_step"],
                      "steps": steps, "warmup": 3, "scaling": r["scaling"], "n_gpus": world,
@@ -573,6 +575,8 @@ def run_subs(args, rank, world, local, dist):
                 entry["parity"] = par
             if extra:
                 entry.update(extra(wl))
+            if tag:
+                entry["workload"] = tag
             del wl
         except Exception as exc:   # a sub-result that cannot run says so; the headline line is still printed
             entry = {"workload": workload, "error": f"{type(exc).__name__}: {exc}"}
@@ -586,6 +590,10 @@ def run_subs(args, rank, world, local, dist):
         one("e1d", 4, 5)
         one("sod", 3, 1000)
         one("md2d", 6, 5)
+        # BASELINE configs[4]'s ordering pair: the same 3D mesh under both cell orderings (L2 hit rate and DRAM bytes
+        # per update of the pair come from ncu: profiles/r02e_ordering_ncu.txt)
+        for o in ("morton", "rcm"):
+            one("md3d", 4, 5, size=8_000_000, order=o, tag=f"md3d_8M_{o}")
     else:
         one("md3d_strong", max(4, min(args.steps, 10)), args.chunk)
     return out

@@ -1614,6 +1614,9 @@ __device__ __forceinline__ void static_for(Fn && f)
     }
 }
 
+#ifndef SCG_EQO2_UNROLL
+#define SCG_EQO2_UNROLL 1 // equations per trip of the equation loop (2: the serial tail of one overlaps the wide head of the next)
+#endif
 #ifndef SCG_EQO2_YROWS
 #define SCG_EQO2_YROWS 0 // 1: the refined reciprocal of det(D) is parked next to det(D) instead of being refined again by every equation
 #endif
@@ -1944,7 +1947,8 @@ __device__ __forceinline__ void cell_dsoln_eqo2(MdField const & F, MdGeo const &
     {
         // ---- one equation at a time; no global loads but the cell's own so0n, which is parked for the fused calc_solt
         //      where equation e's fourth Taylor difference was
-#pragma unroll 1
+        constexpr int UNR = SCG_EQO2_UNROLL;
+#pragma unroll UNR
         for (int e = 0; e < NEQ; ++e)
         {
             asm volatile("" ::: "memory"); // keep the loop-invariant shared-memory reads inside the loop
