@@ -1534,17 +1534,26 @@ int rebuild_bc(scg_md * s)
             emitted[f] = 1;
             faces.push_back(f);
             reg_of.push_back(static_cast<int32_t>(r));
-            icl.push_back(m->iperm[m->h_fccls[2 * static_cast<size_t>(f)]]);
-            jcl.push_back(static_cast<int32_t>(m->ncell + (-m->h_fccls[2 * static_cast<size_t>(f) + 1] - 1)));
             kind.push_back(s->regs[r].kind);
         }
     }
     int64_t const n = static_cast<int64_t>(faces.size());
+    // owner / ghost cell and unit normal of the registered faces, from the device copies of fccls / fcnml
+    std::vector<int32_t> fc2(static_cast<size_t>(n) * 2);
+    std::vector<double> fnml(static_cast<size_t>(n) * nd);
+    if (int rc = mesh_fetch_faces(m, faces.data(), n, fc2.data(), fnml.data())) { return rc; }
+    icl.resize(static_cast<size_t>(n));
+    jcl.resize(static_cast<size_t>(n));
+    for (int64_t b = 0; b < n; ++b)
+    {
+        icl[b] = m->iperm[fc2[2 * b]];
+        jcl[b] = static_cast<int32_t>(m->ncell + (-fc2[2 * b + 1] - 1));
+    }
     std::vector<double> mat(static_cast<size_t>(n) * nd * nd, 0.0), val(static_cast<size_t>(n) * neq, 0.0);
     for (int64_t b = 0; b < n; ++b)
     {
         double mm[9];
-        normal_matrix_host(nd, &m->h_fcnml[static_cast<size_t>(faces[b]) * nd], mm);
+        normal_matrix_host(nd, &fnml[static_cast<size_t>(b) * nd], mm);
         for (int c = 0; c < nd * nd; ++c) { mat[c * n + b] = mm[c]; }
         BcReg const & reg = s->regs[reg_of[b]];
         if (SCG_BC_INLET == reg.kind)
@@ -1925,7 +1934,14 @@ int scg_md_add_bc(scg_md * s, int kind, const int32_t * faces, int64_t nface, co
         int32_t const ifc = faces[q];
         SCG_REQUIRE(ifc >= 0 && ifc < m->nface, "EulerCore::add_bc: face %d out of range [0, %lld)", ifc,
                     static_cast<long long>(m->nface));
-        SCG_REQUIRE(m->h_fccls[2 * static_cast<size_t>(ifc) + 1] < 0, "EulerCore::add_bc: face %d is not a boundary face", ifc);
+    }
+    {
+        std::vector<int32_t> fc2(static_cast<size_t>(nface) * 2);
+        if (int rc = mesh_fetch_faces(m, faces, nface, fc2.data(), nullptr)) { return rc; }
+        for (int64_t q = 0; q < nface; ++q)
+        {
+            SCG_REQUIRE(fc2[2 * static_cast<size_t>(q) + 1] < 0, "EulerCore::add_bc: face %d is not a boundary face", faces[q]);
+        }
     }
     if (SCG_BC_INLET == kind)
     {
@@ -2108,7 +2124,9 @@ int scg_md_normal_matrix(scg_md * s, int32_t ifc, double * out)
 {
     SCG_REQUIRE(s && out, "scg_md_normal_matrix: null argument");
     SCG_REQUIRE(ifc >= 0 && ifc < s->mesh->nface, "get_normal_matrix: face %d out of range", ifc);
-    normal_matrix_host(s->ndim, &s->mesh->h_fcnml[static_cast<size_t>(ifc) * s->ndim], out);
+    double nml[3] = {0.0, 0.0, 0.0};
+    if (int rc = mesh_fetch_faces(s->mesh, &ifc, 1, nullptr, nml)) { return rc; }
+    normal_matrix_host(s->ndim, nml, out);
     return 0;
 }
 

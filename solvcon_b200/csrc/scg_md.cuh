@@ -94,6 +94,10 @@ struct GroupTable // passed by value to the layout-conversion kernels
 
 } // namespace scg
 
+struct scg_mesh;
+// fccls[f][0..1] and fcnml[f][:] of the listed body faces, from the device copies (scg_mesh.cu)
+int mesh_fetch_faces(scg_mesh * m, int32_t const * faces, int64_t n, int32_t * fccls2, double * fcnml);
+
 struct scg_mesh
 {
     int ndim = 0;
@@ -103,8 +107,6 @@ struct scg_mesh
     int64_t stride = 0; // T padded to a multiple of 32
     std::vector<int32_t> perm;  // device slot -> reference cell
     std::vector<int32_t> iperm; // reference cell -> device slot
-    scg::HostBuf<int32_t> h_fccls; // [nface][2] body faces: owner, neighbour (reference ids)
-    scg::HostBuf<double> h_fcnml;  // [nface][ndim] body faces
     std::vector<scg::MeshGroup> groups;
     int64_t geo_total = 0;
     int64_t nbr_total = 0;
@@ -115,5 +117,6 @@ struct scg_mesh
     // raw reference tables kept for prepare_ce (full stored arrays, ghost rows first)
     scg::DevBuf<int32_t> d_clfcs, d_fccls, d_fcnds;
     scg::DevBuf<double> d_ndcrd, d_fccnd, d_clcnd;
+    scg::DevBuf<double> d_fcnml; // [nface][ndim] body faces (boundary-condition setup, normal matrices)
     int refcount = 0; // scg_md objects using this mesh
 };

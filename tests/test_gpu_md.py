@@ -573,3 +573,27 @@ def test_channel_march_stays_uniform(gpu, dims):
         assert ec.so0n[icl, 0] > 0.0 and abs(ec.so0n[icl, 0] - RHO) < 1e-6
     for ifc in left:
         assert abs(ec.so0n[int(mh.fccls[ifc, 1]), 0] - RHO) < 1e-7
+
+
+@pytest.mark.parametrize("name", ["mixed2d", "step2d", "mixed3d", "pyramid3d"])
+@pytest.mark.parametrize("order", ["none", "morton", "rcm"])
+def test_device_layout_equals_host_layout(gpu, bridge, monkeypatch, name, order):
+    """The layout stage (ordering keys incl. the level-by-level reverse Cuthill-McKee, the sort into type / class
+    groups, perm) runs on the device by default; the host implementation is its checker: same permutation, with and
+    without an ownership array (partitions: interface cells first, halo copies last inside a type group)."""
+    from solvcon_b200.mesh import TableMesh
+    from solvcon_b200.multidim import DeviceMesh
+    if not bridge.have_ref():
+        pytest.skip("needs oracle/_ref (mesh tables come from the reference's StaticMesh)")
+    ndim, ndcrd, cltpn, clnds = md_mesh_case(name)
+    mesh = TableMesh(ndim, bridge.make_ref_mesh(ndim, ndcrd, cltpn, clnds).tables())
+    rng = np.random.default_rng(5)
+    owned = rng.integers(0, 3, size=len(cltpn)).astype(np.int8)
+    for own in (None, owned):
+        monkeypatch.delenv("SCG_MESH_HOST_LAYOUT", raising=False)
+        dev = DeviceMesh(mesh, order=order, owned=own).perm
+        monkeypatch.setenv("SCG_MESH_HOST_LAYOUT", "1")
+        host = DeviceMesh(mesh, order=order, owned=own).perm
+        monkeypatch.delenv("SCG_MESH_HOST_LAYOUT", raising=False)
+        assert np.array_equal(np.sort(dev), np.arange(len(cltpn)))
+        assert np.array_equal(dev, host), f"{name} {order}: device and host layouts order the cells differently"
