@@ -167,6 +167,17 @@ SCG_API int scg_hmesh_bc_rename(scg_hmesh * m, int64_t ibc, const char * name); 
 SCG_API int scg_hmesh_drop_retired(scg_hmesh * m);
 SCG_API int scg_hmesh_build_boundary(scg_hmesh * m); /* StaticMesh_boundary.cpp:103-182 */
 SCG_API int scg_hmesh_build_ghost(scg_hmesh * m);    /* StaticMesh_boundary.cpp:185-627 */
+/* Where build_interior / build_boundary / build_ghost run: 1 = GPU kernels (csrc/scg_hmesh_dev.cu: faces-from-cells
+ * dedup, metrics, ghost mirroring; tables stay on the device and are downloaded table by table when scg_hmesh_table
+ * asks for one), 0 = host threads, -1 = automatic (device when one is present and the mesh has >= 2e5 cells; the
+ * environment variable SCG_HMESH_DEVICE=0|1 overrides).  Same tables either way, bit for bit.
+ * scg_hmesh_on_device: 0 = host tables, 1 = interior tables on the device, 2 = + ghost entities. */
+SCG_API int scg_hmesh_set_device(scg_hmesh * m, int mode);
+/* rows idx[0..n) (entity indices: >= 0 body, < 0 ghost) of the named table -> out[n][cols] (double or int32 like the
+ * table), gathered on the device when the table lives there: a caller that needs the boundary faces' centroids of a
+ * 1e8-face mesh does not bring the whole table to the host. */
+SCG_API int scg_hmesh_gather(scg_hmesh * m, const char * name, const int32_t * idx, int64_t n, void * out);
+SCG_API int scg_hmesh_on_device(scg_hmesh * m, int * out);
 
 /* ---------------------------------------------------------- multidim Euler
  * replaces EulerCore over StaticMesh (cpp/solvcon/multidim/euler.hpp:56-211,
@@ -203,6 +214,12 @@ SCG_API int scg_mesh_create_part(scg_mesh ** out, int ndim,
                                  const int32_t * cltpn, const int32_t * clfcs, const int32_t * fccls,
                                  const int32_t * fcnds, const double * ndcrd, const double * fccnd,
                                  const double * fcnml, const double * clcnd, int order, const int8_t * owned);
+
+/* The device mesh of a StaticMesh object (scg_hmesh, above) whose tables were built ON THE DEVICE
+ * (scg_hmesh_set_device): the tables go from the builder's kernels to the layout stage without crossing the bus.
+ * Same result as scg_mesh_create_part over the downloaded tables. */
+struct scg_hmesh;
+SCG_API int scg_mesh_create_from_hmesh(scg_mesh ** out, struct scg_hmesh * hmesh, int order, const int8_t * owned);
 SCG_API int scg_mesh_destroy(scg_mesh * m);
 /* device order <-> reference order permutation: perm[k] = reference cell id stored at device slot k */
 SCG_API int scg_mesh_perm(scg_mesh * m, int32_t * perm /* ncell */);

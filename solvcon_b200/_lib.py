@@ -98,6 +98,10 @@ _SIGNATURES = {
     "scg_hmesh_drop_retired": (C.c_int, [C.c_void_p]),
     "scg_hmesh_build_boundary": (C.c_int, [C.c_void_p]),
     "scg_hmesh_build_ghost": (C.c_int, [C.c_void_p]),
+    "scg_hmesh_set_device": (C.c_int, [C.c_void_p, C.c_int]),
+    "scg_hmesh_gather": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "scg_hmesh_on_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "scg_mesh_create_from_hmesh": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_void_p]),
     # multidim
     "scg_mesh_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                    C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -68,7 +68,7 @@ def build_case_3d(ncell_target, order="morton", kinds="hpt", log=None):
     mesh = make_mesh(3, ndcrd, cltpn, clnds)
     t2 = time.perf_counter()
     lo, hi = ndcrd.min(axis=0), ndcrd.max(axis=0)
-    inlet, outlet, wall = meshgen.boundary_groups(3, mesh.fccnd.body, mesh.fccls.body, mesh.nface, lo, hi)
+    inlet, outlet, wall = meshgen.boundary_groups_of(mesh, lo, hi)
     dt = 0.05 * h
     svr = EulerCore(mesh, dt, order=order)
     import os

@@ -14,7 +14,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
-SOURCES = ["scg_core.cu", "scg_comm.cu", "scg_st.cu", "scg_e1d.cu", "scg_md.cu", "scg_mesh.cu", "scg_hmesh.cpp", "scg_meshgen.cpp"]
+SOURCES = ["scg_core.cu", "scg_comm.cu", "scg_st.cu", "scg_e1d.cu", "scg_md.cu", "scg_mesh.cu", "scg_hmesh.cpp", "scg_hmesh_dev.cu", "scg_meshgen.cpp"]
 
 # host code keeps the reference's x86-64 floating-point contract too: no FMA contraction
 HOSTFLAGS = "-fPIC,-fvisibility=hidden,-O2,-ffp-contract=off,-pthread"

@@ -31,6 +31,8 @@
 
 #include "../../include/scg.h"
 
+#include "scg_hmesh_dev.cuh"
+
 namespace scg
 {
 int fail(char const * fmt, ...);
@@ -122,7 +124,17 @@ struct Tab
     // out is RETIRED instead of freed when the table is re-made, so stale views stay readable (they show the old
     // generation, like the reference's) and writes through them cannot corrupt the heap.
     bool exported = false;
+    // the table lives on the device (built by scg_hmesh_dev.cu) and has not been brought to the host yet: rows / cols /
+    // ngh are set, `v` is empty until somebody asks for the table
+    bool stale = false;
     std::vector<PBuf<T>> retired;
+    void on_device(int64_t r, int64_t ng)
+    {
+        retire();
+        rows = r;
+        ngh = ng;
+        stale = true;
+    }
     void retire()
     {
         if (exported && !v.empty()) { retired.emplace_back(std::move(v)); }
@@ -226,6 +238,12 @@ struct scg_hmesh
     Tab<int32_t> fctpn, cltpn, clgrp, fcnds, fccls, clnds, clfcs, ednds, bndfcs;
     std::vector<std::unique_ptr<Bc>> bcs;
     bool use_incenter = false;
+    // device builder (scg_hmesh_dev.cu): -1 = automatic (a CUDA device is present and the mesh is large), 0 = host, 1 = device
+    int dev_mode = -1;
+    std::unique_ptr<scg::hdev::Tables> dev;
+    bool device_wanted() const;
+    int fetch(char const * name); // bring one table to the host if it only lives on the device
+    int fetch_all();
 
     void build_faces_from_cells();
     void calc_metric();
@@ -693,6 +711,67 @@ void scg_hmesh::fill_ghost()
     }
 }
 
+bool scg_hmesh::device_wanted() const
+{
+    if (ndim < 2) { return false; }
+    int mode = dev_mode;
+    if (mode < 0)
+    {
+        char const * const env = std::getenv("SCG_HMESH_DEVICE");
+        if (env && ('0' == env[0] || '1' == env[0])) { mode = env[0] - '0'; }
+    }
+    if (0 == mode) { return false; }
+    int ndev = 0;
+    if (cudaSuccess != cudaGetDeviceCount(&ndev) || ndev < 1)
+    {
+        cudaGetLastError();
+        return false;
+    }
+    return 1 == mode || ncell >= 200000;
+}
+
+namespace
+{
+template <typename T>
+int fetch_tab(Tab<T> & t, scg::DevBuf<T> const & d)
+{
+    if (!t.stale) { return 0; }
+    size_t const n = static_cast<size_t>(t.rows * t.cols);
+    t.v.alloc(n);
+    if (n > 0)
+    {
+        if (static_cast<int64_t>(n) != d.n) { return scg::fail("StaticMesh: device table size mismatch (%lld != %lld)", static_cast<long long>(n), static_cast<long long>(d.n)); }
+        cudaError_t const e = cudaMemcpy(t.v.data(), d.p, n * sizeof(T), cudaMemcpyDeviceToHost);
+        if (cudaSuccess != e) { return scg::fail("StaticMesh: download of a device-built table failed: %s", cudaGetErrorString(e)); }
+    }
+    t.stale = false;
+    return 0;
+}
+} // namespace
+
+int scg_hmesh::fetch(char const * name)
+{
+    if (!dev) { return 0; }
+    std::string const n(name);
+#define HM_FETCH(N)                        \
+    if (n == #N) { return fetch_tab(N, dev->N); }
+    HM_FETCH(ndcrd) HM_FETCH(fccnd) HM_FETCH(fcnml) HM_FETCH(fcara) HM_FETCH(clcnd) HM_FETCH(clvol)
+    HM_FETCH(fctpn) HM_FETCH(cltpn) HM_FETCH(clgrp) HM_FETCH(fcnds) HM_FETCH(fccls) HM_FETCH(clnds) HM_FETCH(clfcs)
+#undef HM_FETCH
+    return 0;
+}
+
+int scg_hmesh::fetch_all()
+{
+    for (char const * n : {"ndcrd", "fccnd", "fcnml", "fcara", "clcnd", "clvol", "fctpn", "cltpn", "clgrp", "fcnds", "fccls", "clnds", "clfcs"})
+    {
+        if (int rc = fetch(n)) { return rc; }
+    }
+    return 0;
+}
+
+scg::hdev::Tables * scg::hdev::tables_of(scg_hmesh * m) { return m ? m->dev.get() : nullptr; }
+
 using scg::fail;
 
 #define HM_REQUIRE(cond, ...)          \
@@ -763,6 +842,7 @@ int scg_hmesh_table(scg_hmesh * m, const char * name, void ** ptr, int64_t * row
                     int * one_d)
 {
     HM_REQUIRE(m && name && ptr && rows && cols && nghost && is_real && one_d, "scg_hmesh_table: null argument");
+    if (int rc = m->fetch(name)) { return rc; }
     std::string const n(name);
 #define HM_TAB(N, REAL)                                \
     if (n == #N)                                       \
@@ -783,9 +863,85 @@ int scg_hmesh_table(scg_hmesh * m, const char * name, void ** ptr, int64_t * row
     return fail("StaticMesh: unknown table %s", name);
 }
 
+int scg_hmesh_set_device(scg_hmesh * m, int mode)
+{
+    HM_REQUIRE(m, "scg_hmesh_set_device: null mesh");
+    HM_REQUIRE(mode >= -1 && mode <= 1, "scg_hmesh_set_device: mode must be -1 (automatic), 0 (host) or 1 (device)");
+    m->dev_mode = mode;
+    return 0;
+}
+
+int scg_hmesh_on_device(scg_hmesh * m, int * out)
+{
+    HM_REQUIRE(m && out, "scg_hmesh_on_device: null argument");
+    *out = (m->dev && m->dev->interior) ? (m->dev->ghost ? 2 : 1) : 0;
+    return 0;
+}
+
+// rows idx[0..n) (entity indices: >= 0 body, < 0 ghost) of one table -> out[n][cols], without bringing a device-built
+// table to the host
+int scg_hmesh_gather(scg_hmesh * m, const char * name, const int32_t * idx, int64_t n, void * out)
+{
+    HM_REQUIRE(m && name && out && (idx || 0 == n), "scg_hmesh_gather: null argument");
+    std::string const nm(name);
+#define HM_GATHER(N, T)                                                                                          \
+    if (nm == #N)                                                                                                \
+    {                                                                                                            \
+        for (int64_t q = 0; q < n; ++q)                                                                          \
+        {                                                                                                        \
+            HM_REQUIRE(idx[q] >= -m->N.ngh && idx[q] < m->N.nbody(), "StaticMesh: index %d of table %s is out of range", idx[q], name); \
+        }                                                                                                        \
+        if (m->N.stale && m->dev) { return scg::hdev::gather_rows(m->dev->N.p, m->N.ngh, static_cast<int>(m->N.cols), idx, n, static_cast<T *>(out)); } \
+        T * const o = static_cast<T *>(out);                                                                     \
+        for (int64_t q = 0; q < n; ++q)                                                                          \
+        {                                                                                                        \
+            for (int64_t c = 0; c < m->N.cols; ++c) { o[q * m->N.cols + c] = m->N(idx[q], c); }                   \
+        }                                                                                                        \
+        return 0;                                                                                                \
+    }
+    HM_GATHER(ndcrd, double) HM_GATHER(fccnd, double) HM_GATHER(fcnml, double) HM_GATHER(fcara, double) HM_GATHER(clcnd, double)
+    HM_GATHER(clvol, double) HM_GATHER(fctpn, int32_t) HM_GATHER(cltpn, int32_t) HM_GATHER(clgrp, int32_t) HM_GATHER(fcnds, int32_t)
+    HM_GATHER(fccls, int32_t) HM_GATHER(clnds, int32_t) HM_GATHER(clfcs, int32_t)
+#undef HM_GATHER
+    return fail("StaticMesh: unknown table %s", name);
+}
+
 int scg_hmesh_build_interior(scg_hmesh * m, int do_metric, int do_edge)
 {
     HM_REQUIRE(m, "scg_hmesh_build_interior: null mesh");
+    if (m->device_wanted())
+    {
+        if (int rc = m->fetch_all()) { return rc; } // a rebuild starts from the host copies of nodes and cells
+        m->dev.reset(new scg::hdev::Tables);
+        StageTimer tm;
+        int const rc = scg::hdev::build_interior(*m->dev, m->ndim, m->nnode, m->ncell, m->ndcrd.body(), m->cltpn.body(), m->clgrp.body(),
+                                                 m->clnds.body(), 0 != do_metric);
+        if (0 == rc)
+        {
+            tm.lap("device: interior tables");
+            m->nface = m->dev->nface;
+            m->fctpn.on_device(m->nface, 0);
+            m->fcnds.on_device(m->nface, 0);
+            m->fccls.on_device(m->nface, 0);
+            m->clfcs.on_device(m->ncell, 0);
+            m->fccnd.on_device(m->nface, 0);
+            m->fcnml.on_device(m->nface, 0);
+            m->fcara.on_device(m->nface, 0);
+            m->clcnd.on_device(m->ncell, 0);
+            m->clvol.on_device(m->ncell, 0);
+            if (do_edge)
+            {
+                if (int rc2 = m->fetch("fcnds")) { return rc2; }
+                m->build_edge();
+            }
+            return 0;
+        }
+        // an out-of-range node: fall through to the host loop below for the reference's message
+        m->dev.reset();
+        std::string const msg = scg_last_error();
+        if (msg.find("out of range") == std::string::npos) { return rc; }
+    }
+    m->dev.reset();
     for (int64_t icl = 0; icl < m->ncell; ++icl)
     {
         int const t = m->cltpn(icl);
@@ -806,6 +962,7 @@ int scg_hmesh_build_interior(scg_hmesh * m, int do_metric, int do_edge)
 int scg_hmesh_build_edge(scg_hmesh * m)
 {
     HM_REQUIRE(m, "scg_hmesh_build_edge: null mesh");
+    if (int rc = m->fetch("fcnds")) { return rc; }
     m->build_edge();
     return 0;
 }
@@ -816,6 +973,7 @@ int scg_hmesh_add_bc(scg_hmesh * m, const char * name, const int32_t * faces, in
     HM_REQUIRE(m && name, "scg_hmesh_add_bc: null argument");
     HM_REQUIRE(0 == m->nbound, "StaticMesh::add_bc: boundary is already built");
     HM_REQUIRE(name[0] != '\0', "StaticMesh::add_bc: empty name");
+    if (int rc = m->fetch("fccls")) { return rc; }
     for (auto const & b : m->bcs)
     {
         HM_REQUIRE(b->name != name, "StaticMesh::add_bc: duplicated name \"%s\"", name);
@@ -881,21 +1039,28 @@ int scg_hmesh_build_boundary(scg_hmesh * m)
 {
     HM_REQUIRE(m, "scg_hmesh_build_boundary: null mesh");
     HM_REQUIRE(0 == m->nbound, "StaticMesh::build_boundary: boundary is already built");
-    int64_t nb = 0;
-    for (int64_t f = 0; f < m->fccls.rows; ++f) { nb += m->fccls.v[f * FCREL + 1] < 0 ? 1 : 0; }
-    m->nbound = nb;
-    m->bndfcs.make(nb, BFREL, -1);
+    // all boundary faces (no second cell) in ascending id: from the device tables when the interior was built there
     std::vector<int32_t> allfacn;
-    allfacn.reserve(static_cast<size_t>(nb));
-    std::vector<int32_t> where(static_cast<size_t>(m->nface), -1);
-    for (int64_t f = 0; f < m->nface; ++f)
+    if (m->dev && m->dev->interior && !m->fccls.exported)
     {
-        if (m->fccls(f, 1) < 0)
+        if (int rc = scg::hdev::boundary_faces(*m->dev, allfacn)) { return rc; }
+    }
+    else
+    {
+        if (int rc = m->fetch("fccls")) { return rc; }
+        for (int64_t f = 0; f < m->nface; ++f)
         {
-            where[f] = static_cast<int32_t>(allfacn.size());
-            allfacn.push_back(static_cast<int32_t>(f));
+            if (m->fccls(f, 1) < 0) { allfacn.push_back(static_cast<int32_t>(f)); }
         }
     }
+    int64_t const nb = static_cast<int64_t>(allfacn.size());
+    m->nbound = nb;
+    m->bndfcs.make(nb, BFREL, -1);
+    auto where = [&](int32_t f) -> int64_t
+    {
+        auto const it = std::lower_bound(allfacn.begin(), allfacn.end(), f);
+        return (it != allfacn.end() && *it == f) ? (it - allfacn.begin()) : -1;
+    };
     std::vector<char> specified(static_cast<size_t>(nb), 0);
     int64_t ibfc = 0, nleft = nb;
     for (size_t ibnd = 0; ibnd < m->bcs.size(); ++ibnd)
@@ -906,7 +1071,7 @@ int scg_hmesh_build_boundary(scg_hmesh * m)
             m->bndfcs(ibfc, 0) = facn(q, 0);
             m->bndfcs(ibfc, 1) = static_cast<int32_t>(ibnd);
             facn(q, 1) = static_cast<int32_t>(ibfc);
-            int32_t const pos = where[facn(q, 0)];
+            int64_t const pos = where(facn(q, 0));
             if (pos >= 0)
             {
                 specified[pos] = 1;
@@ -944,6 +1109,39 @@ int scg_hmesh_build_ghost(scg_hmesh * m)
 {
     HM_REQUIRE(m, "scg_hmesh_build_ghost: null mesh");
     HM_REQUIRE(0 == m->ngstcell, "StaticMesh::build_ghost: ghost entities are already built");
+    // a view of a device-built table that was handed out may have been written through: then the host copies rule
+    bool const handed_out = m->fctpn.exported || m->fcnds.exported || m->fccls.exported || m->clfcs.exported || m->fccnd.exported
+                            || m->fcnml.exported || m->fcara.exported || m->clcnd.exported || m->clvol.exported;
+    if (m->dev && m->dev->interior && !m->dev->ghost && !handed_out)
+    {
+        // the device copies of the interior tables are current: ghost entities are built there too
+        StageTimer tmd;
+        std::vector<int32_t> bnd(static_cast<size_t>(m->nbound));
+        for (int64_t ib = 0; ib < m->nbound; ++ib) { bnd[static_cast<size_t>(ib)] = m->bndfcs(ib, 0); }
+        if (int rc = scg::hdev::build_ghost(*m->dev, bnd.data(), m->nbound)) { return rc; }
+        tmd.lap("device: ghost entities");
+        scg::hdev::Tables const & t = *m->dev;
+        m->ngstnode = t.ngstnode;
+        m->ngstface = t.ngstface;
+        m->ngstcell = t.ngstcell;
+        m->ndcrd.on_device(t.nnode + t.ngstnode, t.ngstnode);
+        m->fccnd.on_device(t.nface + t.ngstface, t.ngstface);
+        m->fcnml.on_device(t.nface + t.ngstface, t.ngstface);
+        m->fcara.on_device(t.nface + t.ngstface, t.ngstface);
+        m->clcnd.on_device(t.ncell + t.ngstcell, t.ngstcell);
+        m->clvol.on_device(t.ncell + t.ngstcell, t.ngstcell);
+        m->fctpn.on_device(t.nface + t.ngstface, t.ngstface);
+        m->cltpn.on_device(t.ncell + t.ngstcell, t.ngstcell);
+        m->clgrp.on_device(t.ncell + t.ngstcell, t.ngstcell);
+        m->fcnds.on_device(t.nface + t.ngstface, t.ngstface);
+        m->fccls.on_device(t.nface + t.ngstface, t.ngstface);
+        m->clnds.on_device(t.ncell + t.ngstcell, t.ngstcell);
+        m->clfcs.on_device(t.ncell + t.ngstcell, t.ngstcell);
+        return 0;
+    }
+    // host path: every table on the host; device copies (if any) are out of date from here on
+    if (int rc = m->fetch_all()) { return rc; }
+    m->dev.reset();
     int64_t gn = 0, gf = 0;
     for (int64_t ib = 0; ib < m->nbound; ++ib)
     {

@@ -6,6 +6,7 @@
 // never touch clfcs/fccls/fcnds: the neighbour of cell icl across local face f,
 // fcrcl = fccls[ifc,0] + fccls[ifc,1] - icl (StaticMesh.hpp:355-358), is resolved here once into
 // nbr[f][cell] in device numbering.
+#include "scg_hmesh_dev.cuh"
 #include "scg_md.cuh"
 #include "scg_par.hpp"
 
@@ -505,24 +506,28 @@ int device_rcm(int64_t ncell, int32_t const * clfcs_b, int32_t const * fccls_b, 
 
 
 // Upload the raw tables, then build ordering, groups, perm / iperm, neighbour table and row map on the device.
+// `on_device`: the eight table pointers are device pointers (tables built by scg_hmesh_dev.cu); they are copied device
+// to device, because the mesh object owns its tables.  `owned` is always a host pointer.
 int layout_on_device(scg_mesh * m, int32_t const * cltpn, int32_t const * clfcs, int32_t const * fccls, int32_t const * fcnds,
-                     double const * ndcrd, double const * fccnd, double const * fcnml, double const * clcnd, int8_t const * owned)
+                     double const * ndcrd, double const * fccnd, double const * fcnml, double const * clcnd, int8_t const * owned,
+                     bool on_device = false)
 {
     HostStageTimer tm("dmesh");
     int const ndim = m->ndim;
     int64_t const ncell = m->ncell, nface = m->nface, nnode = m->nnode;
     int64_t const ngstcell = m->ngstcell, ngstface = m->ngstface, ngstnode = m->ngstnode;
     cudaStream_t const st = stream();
+    cudaMemcpyKind const kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     auto up_i = [&](DevBuf<int32_t> & b, int32_t const * h, int64_t n) -> int
     {
         SCG_CUDA(b.alloc(n));
-        SCG_CUDA(cudaMemcpyAsync(b.p, h, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+        SCG_CUDA(cudaMemcpyAsync(b.p, h, sizeof(int32_t) * n, kind, st));
         return 0;
     };
     auto up_d = [&](DevBuf<double> & b, double const * h, int64_t n) -> int
     {
         SCG_CUDA(b.alloc(n));
-        SCG_CUDA(cudaMemcpyAsync(b.p, h, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+        SCG_CUDA(cudaMemcpyAsync(b.p, h, sizeof(double) * n, kind, st));
         return 0;
     };
     DevBuf<int32_t> d_cltpn;
@@ -552,8 +557,10 @@ int layout_on_device(scg_mesh * m, int32_t const * cltpn, int32_t const * clfcs,
     if (h_err[0] != INT_MAX)
     {
         int64_t const i = h_err[0];
-        return fail("scg_mesh_create: cell %lld has type %d / %d faces, not supported in %dD", static_cast<long long>(i),
-                    cltpn[ngstcell + i], clfcs[(ngstcell + i) * 7], ndim);
+        int32_t ht = 0, hn = 0;
+        SCG_CUDA(cudaMemcpy(&ht, d_cltpn.p + ngstcell + i, sizeof(int32_t), cudaMemcpyDeviceToHost));
+        SCG_CUDA(cudaMemcpy(&hn, m->d_clfcs.p + (ngstcell + i) * 7, sizeof(int32_t), cudaMemcpyDeviceToHost));
+        return fail("scg_mesh_create: cell %lld has type %d / %d faces, not supported in %dD", static_cast<long long>(i), ht, hn, ndim);
     }
     tm.lap("upload connectivity");
 
@@ -966,6 +973,37 @@ int scg_mesh_create_part(scg_mesh ** out, int ndim, int64_t nnode, int64_t nface
         cudaError_t const e = cudaGetLastError();
         delete m;
         return fail("scg_mesh_create: device allocation/upload failed: %s", cudaGetErrorString(e));
+    }
+    *out = m;
+    return 0;
+}
+
+// The device mesh of a StaticMesh whose tables were built on the device (scg_hmesh_dev.cu): no table crosses the bus.
+int scg_mesh_create_from_hmesh(scg_mesh ** out, scg_hmesh * hm, int order, const int8_t * owned)
+{
+    if (int rc = ensure_init()) { return rc; }
+    SCG_REQUIRE(out && hm, "scg_mesh_create_from_hmesh: null argument");
+    scg::hdev::Tables * const t = scg::hdev::tables_of(hm);
+    SCG_REQUIRE(t && t->interior && t->ghost, "scg_mesh_create_from_hmesh: the mesh has no complete device tables (build_ghost() on the device first)");
+    SCG_REQUIRE(2 == t->ndim || 3 == t->ndim, "scg_mesh_create: ndim must be 2 or 3");
+    SCG_REQUIRE(t->ncell > 0 && t->nface > 0 && t->nnode > 0, "scg_mesh_create: empty mesh");
+    SCG_REQUIRE(t->ncell + t->ngstcell < (int64_t(1) << 31) - 64, "scg_mesh_create: too many cells for int32 indices");
+    SCG_REQUIRE(order >= SCG_ORDER_NONE && order <= SCG_ORDER_RCM, "scg_mesh_create: unknown ordering %d", order);
+    auto * m = new scg_mesh;
+    m->ndim = t->ndim;
+    m->order = order;
+    m->nnode = t->nnode;
+    m->nface = t->nface;
+    m->ncell = t->ncell;
+    m->ngstnode = t->ngstnode;
+    m->ngstface = t->ngstface;
+    m->ngstcell = t->ngstcell;
+    m->T = m->ncell + m->ngstcell;
+    m->stride = (m->T + 31) / 32 * 32;
+    if (int rc = layout_on_device(m, t->cltpn.p, t->clfcs.p, t->fccls.p, t->fcnds.p, t->ndcrd.p, t->fccnd.p, t->fcnml.p, t->clcnd.p, owned, true))
+    {
+        delete m;
+        return rc;
     }
     *out = m;
     return 0;

@@ -153,6 +153,34 @@ class StaticMesh:
             raise exc(msg)
         self._cache = {}  # the native arrays may have been re-allocated
 
+    def set_device(self, mode):
+        """Additive API: where the build_* calls run -- ``True`` GPU kernels (``csrc/scg_hmesh_dev.cu``; tables stay on
+        the device and come to the host one by one when they are accessed), ``False`` host threads, ``None`` automatic
+        (device when one is present and the mesh has >= 2e5 cells).  Same tables either way."""
+        _libmod.check(self._lib.scg_hmesh_set_device(self._h, -1 if mode is None else int(bool(mode))))
+        return self
+
+    _REAL = ("ndcrd", "fccnd", "fcnml", "fcara", "clcnd", "clvol")
+    _COLS = {"fcara": 1, "clvol": 1, "fctpn": 1, "cltpn": 1, "clgrp": 1, "fcnds": 5, "fccls": 4, "clnds": 9, "clfcs": 7}
+
+    def gather(self, name, idx):
+        """Additive API: rows ``idx`` (entity indices, negative = ghost) of table ``name`` as an array ``[len(idx), cols]``
+        -- gathered on the device when the table was built there, so a few boundary rows of a 1e8-face table do not
+        bring the whole table to the host."""
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        cols = self._COLS.get(name, self.ndim)
+        out = np.empty((len(idx), cols), dtype=np.float64 if name in self._REAL else np.int32)
+        if self._lib.scg_hmesh_gather(self._h, name.encode(), _libmod.ptr(idx) if len(idx) else None, len(idx), _libmod.ptr(out)):
+            raise IndexError(self._lib.scg_last_error().decode())
+        return out
+
+    @property
+    def on_device(self):
+        """0 = host tables, 1 = interior tables live on the device, 2 = + ghost entities (a complete device mesh)."""
+        v = _C.c_int()
+        _libmod.check(self._lib.scg_hmesh_on_device(self._h, _C.byref(v)))
+        return int(v.value)
+
     def build_interior(self, do_metric=True, build_edge=True, _do_metric=None):
         self._check(self._lib.scg_hmesh_build_interior(self._h, int(bool(do_metric)), int(bool(build_edge))))
 
@@ -204,10 +232,11 @@ class StaticMesh:
         return {n: (self._table(n).ndarray.copy(), self._table(n).nghost) for n in TABLES}
 
 
-def make_mesh(ndim, ndcrd, cltpn, clnds, bcs=(), build_edge=False):
-    """Nodes + cells -> a fully built StaticMesh (interior, boundary, ghost)."""
+def make_mesh(ndim, ndcrd, cltpn, clnds, bcs=(), build_edge=False, device=None):
+    """Nodes + cells -> a fully built StaticMesh (interior, boundary, ghost).  ``device``: see ``StaticMesh.set_device``."""
     ndcrd = np.asarray(ndcrd, dtype=np.float64)
     m = StaticMesh(ndim, len(ndcrd), 0, len(cltpn))
+    m.set_device(device)
     m.ndcrd.ndarray[...] = ndcrd
     m.cltpn.ndarray[...] = cltpn
     m.clnds.ndarray[...] = clnds

@@ -247,6 +247,19 @@ def boundary_groups(ndim, fccnd, fccls, nface, lo, hi, tol=1e-9):
     return inlet, outlet, wall
 
 
+def boundary_groups_of(mesh, lo, hi, tol=1e-9):
+    """``boundary_groups`` of a built StaticMesh, reading only the boundary faces' rows (``StaticMesh.gather``): the same
+    three face lists, in ascending face id."""
+    if not hasattr(mesh, "gather") or getattr(mesh, "on_device", 0) == 0:
+        return boundary_groups(mesh.ndim, mesh.fccnd.body, mesh.fccls.body, mesh.nface, lo, hi, tol)
+    bnd = np.sort(mesh.bndfcs.ndarray[:, 0]).astype(np.int32)
+    xc = mesh.gather("fccnd", bnd)[:, 0]
+    inlet = bnd[np.abs(xc - lo[0]) < tol]
+    outlet = bnd[np.abs(xc - hi[0]) < tol]
+    wall = bnd[(np.abs(xc - lo[0]) >= tol) & (np.abs(xc - hi[0]) >= tol)]
+    return inlet, outlet, wall
+
+
 def pyramid_3d(nx, ny, nz, lx=None, ly=None, lz=None, jitter=0.0):
     """``nx`` x ``ny`` x ``nz`` boxes, each cut into six pyramids whose apex is the box centre and whose bases are
     the six box faces (the only conforming all-pyramid lattice; quadrilateral faces are shared between boxes,

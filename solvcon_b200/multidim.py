@@ -76,6 +76,11 @@ class DeviceMesh:
         self.ngstcell, self.ngstface, self.ngstnode = int(mesh.ngstcell), int(mesh.ngstface), int(mesh.ngstnode)
         if self.ngstcell == 0 and getattr(mesh, "nbound", 1) != 0:
             raise ValueError("EulerCore: the mesh has no ghost cells; call build_boundary() and build_ghost() first")
+        if getattr(mesh, "on_device", 0) == 2:
+            # the tables were built by the device builder (csrc/scg_hmesh_dev.cu) and are still there: no upload
+            if self._lib.scg_mesh_create_from_hmesh(C.byref(self._h), mesh._h, self.order, _lib.ptr(own)):
+                _raise(ValueError)
+            return
         t = {n: _table(mesh, n) for n in ("cltpn", "clfcs", "fccls", "fcnds", "ndcrd", "fccnd", "fcnml", "clcnd")}
         for n in ("cltpn", "clfcs", "fccls", "fcnds"):
             if t[n].dtype != np.int32:
