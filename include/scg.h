@@ -171,7 +171,8 @@ SCG_API int scg_hmesh_build_ghost(scg_hmesh * m);    /* StaticMesh_boundary.cpp:
  * dedup, metrics, ghost mirroring; tables stay on the device and are downloaded table by table when scg_hmesh_table
  * asks for one), 0 = host threads, -1 = automatic (device when one is present and the mesh has >= 2e5 cells; the
  * environment variable SCG_HMESH_DEVICE=0|1 overrides).  Same tables either way, bit for bit.
- * scg_hmesh_on_device: 0 = host tables, 1 = interior tables on the device, 2 = + ghost entities. */
+ * scg_hmesh_on_device: 0 = host tables, 1 = interior tables on the device, 2 = + ghost entities and no table has been
+ * handed out to the host since (a view is writable: from then on the host copies are the mesh). */
 SCG_API int scg_hmesh_set_device(scg_hmesh * m, int mode);
 /* rows idx[0..n) (entity indices: >= 0 body, < 0 ghost) of the named table -> out[n][cols] (double or int32 like the
  * table), gathered on the device when the table lives there: a caller that needs the boundary faces' centroids of a

@@ -874,7 +874,12 @@ int scg_hmesh_set_device(scg_hmesh * m, int mode)
 int scg_hmesh_on_device(scg_hmesh * m, int * out)
 {
     HM_REQUIRE(m && out, "scg_hmesh_on_device: null argument");
-    *out = (m->dev && m->dev->interior) ? (m->dev->ghost ? 2 : 1) : 0;
+    // a table that was handed out as a (writable) view may have been changed on the host: from then on the host copies
+    // are the mesh and the device copies are no longer offered
+    bool const handed_out = m->ndcrd.exported || m->cltpn.exported || m->clgrp.exported || m->clnds.exported || m->fctpn.exported
+                            || m->fcnds.exported || m->fccls.exported || m->clfcs.exported || m->fccnd.exported || m->fcnml.exported
+                            || m->fcara.exported || m->clcnd.exported || m->clvol.exported;
+    *out = (m->dev && m->dev->interior && !(m->dev->ghost && handed_out)) ? (m->dev->ghost ? 2 : 1) : 0;
     return 0;
 }
 

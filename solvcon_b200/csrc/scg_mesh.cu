@@ -984,7 +984,10 @@ int scg_mesh_create_from_hmesh(scg_mesh ** out, scg_hmesh * hm, int order, const
     if (int rc = ensure_init()) { return rc; }
     SCG_REQUIRE(out && hm, "scg_mesh_create_from_hmesh: null argument");
     scg::hdev::Tables * const t = scg::hdev::tables_of(hm);
-    SCG_REQUIRE(t && t->interior && t->ghost, "scg_mesh_create_from_hmesh: the mesh has no complete device tables (build_ghost() on the device first)");
+    int where = 0;
+    if (int rc = scg_hmesh_on_device(hm, &where)) { return rc; }
+    SCG_REQUIRE(t && 2 == where, "scg_mesh_create_from_hmesh: the mesh has no current device tables (not built on the device, or a table "
+                                 "was handed out to the host since: use scg_mesh_create over the host tables)");
     SCG_REQUIRE(2 == t->ndim || 3 == t->ndim, "scg_mesh_create: ndim must be 2 or 3");
     SCG_REQUIRE(t->ncell > 0 && t->nface > 0 && t->nnode > 0, "scg_mesh_create: empty mesh");
     SCG_REQUIRE(t->ncell + t->ngstcell < (int64_t(1) << 31) - 64, "scg_mesh_create: too many cells for int32 indices");

@@ -176,7 +176,8 @@ class StaticMesh:
 
     @property
     def on_device(self):
-        """0 = host tables, 1 = interior tables live on the device, 2 = + ghost entities (a complete device mesh)."""
+        """0 = host tables, 1 = interior tables live on the device, 2 = + ghost entities and no table has been handed out
+        as a (writable) host view since: a complete, current device mesh."""
         v = _C.c_int()
         _libmod.check(self._lib.scg_hmesh_on_device(self._h, _C.byref(v)))
         return int(v.value)

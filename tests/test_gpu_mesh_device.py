@@ -51,6 +51,7 @@ def test_device_built_tables_equal_host_built(gpu, name):
     dev = make_mesh(ndim, ndcrd, cltpn, clnds, device=True)
     assert host.on_device == 0 and dev.on_device == 2
     _same(dev, host, name)
+    assert dev.on_device == 0, "tables were handed out as host views: the host copies are the mesh now"
 
 
 @pytest.mark.parametrize("name", ["mixed2d", "mixed3d"])
