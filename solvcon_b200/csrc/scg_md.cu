@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(128) md_prepare_ce_kernel(RawMesh const M, MdG
     constexpr int ND = ct_ndim(TYPE);
     constexpr int NFC = ct_nfc(TYPE);
     int32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= G.n) { return; }
+    if (i >= G.cnt) { return; }
     int64_t const n = G.n;
     int64_t const k = G.beg + i;
     int64_t const icl = M.perm[k];
@@ -398,15 +398,41 @@ __global__ void __launch_bounds__(StagedCfg<TYPE>::TB, StagedCfg<TYPE>::MB) md_s
     constexpr int ND = ct_ndim(TYPE);
     constexpr int NEQ = ND + 2;
     constexpr int NFC = ct_nfc(TYPE);
+    constexpr int TB = StagedCfg<TYPE>::TB;
     extern __shared__ double stage_smem[];
-    int32_t const i = G.ibeg + blockIdx.x * StagedCfg<TYPE>::TB + threadIdx.x;
+#if SCG_SOLN_BULK
+    // Warps start on multiples of 32 cells so that the bulk copies of the geometry rows are aligned; lanes outside
+    // [ibeg, iend) evaluate a clamped cell (they take part in the warp's barriers) and store nothing.
+    int const lane = threadIdx.x & 31;
+    int32_t const i_raw = (G.ibeg & ~31) + blockIdx.x * TB + threadIdx.x;
+    int32_t const iw0 = i_raw - lane;
+    if (iw0 >= G.iend) { return; } // the whole warp is past the range
+    bool const active = i_raw >= G.ibeg && i_raw < G.iend;
+    int32_t const i = i_raw < G.ibeg ? G.ibeg : (i_raw >= G.iend ? G.iend - 1 : i_raw);
+    uint64_t * const bars = reinterpret_cast<uint64_t *>(stage_smem + SolnStage<TYPE, TB>::ROWS * TB) + 2 * (threadIdx.x >> 5);
+    if (0 == lane)
+    {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+#else
+    int32_t const i = G.ibeg + blockIdx.x * TB + threadIdx.x;
     if (i >= G.iend) { return; }
+    constexpr bool active = true;
+#endif
     int64_t const k = G.beg + i;
     double un[NEQ];
     double dist;
     bool dist_ok;
     int32_t jmax;
-    cell_soln_staged<TYPE, StagedCfg<TYPE>::TB>(F, G, i, stage_smem + threadIdx.x, un, dist, dist_ok, jmax);
+#if SCG_SOLN_BULK
+    cell_soln_staged_bulk<TYPE, TB>(F, G, i, iw0, lane, stage_smem + threadIdx.x, bars, un, dist, dist_ok, jmax);
+    if (!active) { return; }
+#else
+    cell_soln_staged<TYPE, TB>(F, G, i, stage_smem + threadIdx.x, un, dist, dist_ok, jmax);
+#endif
     if (!dist_ok)
     {
         // a square root of calc_cfl's distance left the fast range: redo the distance with the plain operator
@@ -438,6 +464,7 @@ __global__ void __launch_bounds__(StagedCfg<TYPE>::TB, StagedCfg<TYPE>::MB) md_s
     F.cflc[k] = cflc;
 #pragma unroll
     for (int e = 0; e < NEQ; ++e) { F.so0n[e * F.S + k] = un[e]; }
+    (void)active;
 }
 
 // Split substep, kernel 2, equation-outer variant (march mode 3): one thread per cell, adj(D)/det(D) of the
@@ -1067,7 +1094,7 @@ __global__ void md_geo_rows_kernel(int which, double * stage, int64_t row0, int6
         int32_t const k = rowmap[stored];
         MeshGroup const & g = GT.g[find_group(GT, k)];
         int64_t const i = k - g.beg;
-        int64_t const n = g.n;
+        int64_t const n = g.ld;
         int const nfc = ct_nfc(g.type);
         if (SCG_A_CEVOL == which)
         {
@@ -1345,7 +1372,8 @@ MdGeo geo_of(scg_md * s, MeshGroup const & g)
     G.sfcnd = s->geo.p + g.geo_sfcnd();
     G.sfnml = s->geo.p + g.geo_sfnml();
     G.beg = g.beg;
-    G.n = g.n;
+    G.n = g.ld;
+    G.cnt = g.n;
     G.nact = g.nact;
     G.ibeg = 0;
     G.iend = g.nact;
@@ -1413,14 +1441,20 @@ void launch_cell_phase_t(scg_md * s, MeshGroup const & g, CellPhase ph, int part
     case CP_SOLNCFL_STAGED:
     {
         constexpr int TBS = StagedCfg<TYPE>::TB;
+#if SCG_SOLN_BULK
+        constexpr int BYTES = SolnStage<TYPE, TBS>::BYTES + 2 * (TBS / 32) * int(sizeof(uint64_t)); // + one mbarrier per warp and buffer
+        int64_t const span = G.iend - (G.ibeg & ~31); // warps start on multiples of 32 cells
+#else
         constexpr int BYTES = SolnStage<TYPE, TBS>::BYTES;
+        int64_t const span = ncl;
+#endif
         static bool attr_set = false;
         if (!attr_set)
         {
             cudaFuncSetAttribute(md_solncfl_staged_kernel<TYPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, BYTES);
             attr_set = true;
         }
-        md_solncfl_staged_kernel<TYPE><<<static_cast<unsigned>(ceil_div(ncl, TBS)), TBS, BYTES, stream()>>>(F, G, s->eraw.p);
+        md_solncfl_staged_kernel<TYPE><<<static_cast<unsigned>(ceil_div(span, TBS)), TBS, BYTES, stream()>>>(F, G, s->eraw.p);
         break;
     }
     case CP_DSOLN_EQO:

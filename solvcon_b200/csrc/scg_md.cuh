@@ -73,15 +73,16 @@ struct MeshGroup
     int type = 0;
     int32_t beg = 0; // first device cell
     int32_t n = 0;   // cells in the group
+    int32_t ld = 0;  // leading dimension of the group's arrays: n padded to a multiple of 32 (every row starts 256-byte aligned)
     int32_t nact = 0; // owned cells (stored first); the rest are halo copies owned by another partition
     int32_t nif = 0;  // owned interface cells (stored first among the owned ones)
     int64_t off_nbr = 0;  // into scg_mesh::d_nbr   (ints)
     int64_t off_geo = 0;  // into scg_md::geo        (doubles): cevol, cecnd, sfcnd, sfnml in this order
     __host__ __device__ int64_t geo_cevol() const { return off_geo; }
-    __host__ __device__ int64_t geo_cecnd() const { return off_geo + int64_t(ct_nfc(type) + 1) * n; }
-    __host__ __device__ int64_t geo_sfcnd() const { return geo_cecnd() + int64_t(ct_nfc(type)) * ct_ndim(type) * n; }
-    __host__ __device__ int64_t geo_sfnml() const { return geo_sfcnd() + int64_t(ct_nsf(type)) * ct_ndim(type) * n; }
-    __host__ __device__ int64_t geo_size() const { return geo_sfnml() + int64_t(ct_nsf(type)) * ct_ndim(type) * n - off_geo; }
+    __host__ __device__ int64_t geo_cecnd() const { return off_geo + int64_t(ct_nfc(type) + 1) * ld; }
+    __host__ __device__ int64_t geo_sfcnd() const { return geo_cecnd() + int64_t(ct_nfc(type)) * ct_ndim(type) * ld; }
+    __host__ __device__ int64_t geo_sfnml() const { return geo_sfcnd() + int64_t(ct_nsf(type)) * ct_ndim(type) * ld; }
+    __host__ __device__ int64_t geo_size() const { return geo_sfnml() + int64_t(ct_nsf(type)) * ct_ndim(type) * ld - off_geo; }
 };
 
 constexpr int MAX_GROUPS = 8;

@@ -53,7 +53,8 @@ struct MdGeo // one cell-type group
     double * sfcnd;      // [nsf*ndim][n]
     double * sfnml;      // [nsf*ndim][n]
     int32_t beg;
-    int32_t n;    // cells in the group (array stride)
+    int32_t n;    // array stride of the group (its cell count padded to a multiple of 32)
+    int32_t cnt;  // cells in the group
     int32_t nact; // owned cells, stored first: the march kernels stop here
     int32_t ibeg, iend; // cell range of this launch (mode-3 kernels): [0, nact) or the interface / interior part of it
 };
@@ -654,6 +655,47 @@ __device__ __forceinline__ void l2_prefetch(void const * p) { asm volatile("pref
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// ------------------------------------------------------------------------------------------------
+// Bulk asynchronous copies (cp.async.bulk, the TMA's 1D mode) completing on an mbarrier.  The geometry rows of a
+// cell group are contiguous over its cells, so the 32 doubles a warp needs of one row are ONE 256-byte copy issued by
+// one lane instead of 32 8-byte LDGSTS: no per-lane address arithmetic, nothing through the LSU / L1 (which the
+// neighbour gathers keep for themselves).  One mbarrier per warp and buffer; a wait flips with the buffer's use count.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t * bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(bar))), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t * bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(bar))), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(double * smem_dst, double const * gsrc, unsigned bytes, uint64_t * bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     static_cast<unsigned>(__cvta_generic_to_shared(smem_dst))),
+                 "l"(gsrc), "r"(bytes), "r"(static_cast<unsigned>(__cvta_generic_to_shared(bar)))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t * bar, unsigned parity)
+{
+    asm volatile("{\n"
+                 ".reg .pred P1;\n"
+                 "SCG_MBAR_WAIT:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+                 "@P1 bra SCG_MBAR_DONE;\n"
+                 "bra SCG_MBAR_WAIT;\n"
+                 "SCG_MBAR_DONE:\n"
+                 "}" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(bar))),
+                 "r"(parity)
+                 : "memory");
+}
+
+#ifndef SCG_SOLN_BULK
+#define SCG_SOLN_BULK 0 // 1: md_solncfl_staged stages the geometry rows with cp.async.bulk + mbarrier (one lane per warp)
+#endif
+
 // Jacobian in scalar form: the quantities every entry of EulerJacobian<ND>::update is built from
 // (euler_march.cpp:35-81, 94-157), and row<E>() which forms fcn[E][:] and jac[E][:][:] from them with the
 // very expressions of jaco_update_2d/3d.  Evaluating a row right where it is consumed keeps one row in
@@ -1026,6 +1068,211 @@ __device__ __forceinline__ void cell_soln_staged(MdField const & F, MdGeo const 
 #pragma unroll
     for (int e = 0; e < NEQ; ++e) { out[e] = acc[e] / cvol; }
 }
+
+
+// The neighbour gather alone (the N rows of SolnStage): every thread copies its own column
+template <int TYPE, int TB>
+__device__ __forceinline__ void soln_stage_issue_n(MdField const & F, int64_t j, double * st)
+{
+    using L = SolnStage<TYPE, TB>;
+    constexpr int ND = L::ND, NEQ = L::NEQ;
+    int64_t const S = F.S;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) { cp_async8(st + (L::R_JC + d) * TB, &F.solpt[d * S + j]); }
+#pragma unroll
+    for (int e = 0; e < NEQ; ++e)
+    {
+        cp_async8(st + (L::R_JU + e) * TB, &F.so0c[e * S + j]);
+        cp_async8(st + (L::R_JT + e) * TB, &F.so0t[e * S + j]);
+#pragma unroll
+        for (int d = 0; d < ND; ++d) { cp_async8(st + (L::R_JG + e * ND + d) * TB, &F.so1c[(e * ND + d) * S + j]); }
+    }
+    cp_async8(st + L::R_GA * TB, &F.gamma[j]);
+    cp_async_commit();
+}
+
+// The geometry rows of face f for the 32 cells [iw0, iw0 + 32) of a warp: one 256-byte bulk copy per row, issued by
+// one lane, completing on the warp's mbarrier.  Group strides are multiples of 32 and iw0 is one too, so every source
+// segment is 256-byte aligned and inside its row.
+template <int TYPE, int TB>
+__device__ __forceinline__ void soln_bulk_issue_a(MdGeo const & G, int64_t iw0, int f, double * wst, uint64_t * bar)
+{
+    using L = SolnStage<TYPE, TB>;
+    constexpr int ND = L::ND;
+    constexpr unsigned ROWB = 32 * sizeof(double);
+    int64_t const n = G.n;
+    int const nsf = ct_fnnd(TYPE, f);
+    int const q0 = ct_sfoff(TYPE, f);
+    mbar_expect_tx(bar, (ND + 1 + L::MSF * ND) * ROWB);
+#pragma unroll
+    for (int d = 0; d < ND; ++d) { bulk_g2s(wst + (L::R_BC + d) * TB, &G.cecnd[(f * ND + d) * n + iw0], ROWB, bar); }
+    bulk_g2s(wst + L::R_VOL * TB, &G.cevol[(f + 1) * n + iw0], ROWB, bar);
+#pragma unroll
+    for (int s = 0; s < L::MSF; ++s)
+    {
+        int64_t const q = q0 + (s < nsf ? s : nsf - 1); // a triangle face of a prism/pyramid re-reads its last sub-face
+#pragma unroll
+        for (int d = 0; d < ND; ++d) { bulk_g2s(wst + (L::R_SC + s * ND + d) * TB, &G.sfcnd[(q * ND + d) * n + iw0], ROWB, bar); }
+    }
+}
+
+template <int TYPE, int TB>
+__device__ __forceinline__ void soln_bulk_issue_b(MdGeo const & G, int64_t iw0, int f, double * wst, uint64_t * bar)
+{
+    using L = SolnStage<TYPE, TB>;
+    constexpr int ND = L::ND;
+    constexpr unsigned ROWB = 32 * sizeof(double);
+    int64_t const n = G.n;
+    int const nsf = ct_fnnd(TYPE, f);
+    int const q0 = ct_sfoff(TYPE, f);
+    mbar_expect_tx(bar, L::MSF * ND * ROWB);
+#pragma unroll
+    for (int s = 0; s < L::MSF; ++s)
+    {
+        int64_t const q = q0 + (s < nsf ? s : nsf - 1);
+#pragma unroll
+        for (int d = 0; d < ND; ++d) { bulk_g2s(wst + (L::R_SN + s * ND + d) * TB, &G.sfnml[(q * ND + d) * n + iw0], ROWB, bar); }
+    }
+}
+
+// cell_soln_staged with the geometry rows staged by bulk copies (SCG_SOLN_BULK): same terms, same order.  `i` is the
+// cell this lane evaluates (clamped into the launch range for the lanes that have none: they keep the warp's
+// barriers and __syncwarp()s company and their results are dropped by the caller), `iw0` the first cell of the warp.
+template <int TYPE, int TB>
+__device__ __forceinline__ void cell_soln_staged_bulk(MdField const & F, MdGeo const & G, int32_t i, int32_t iw0, int lane, double * st,
+                                                      uint64_t * bars, double (&out)[ct_ndim(TYPE) + 2], double & dist, bool & dist_ok,
+                                                      int32_t & jmax)
+{
+    using L = SolnStage<TYPE, TB>;
+    constexpr int ND = ct_ndim(TYPE);
+    constexpr int NEQ = ND + 2;
+    constexpr int NFC = ct_nfc(TYPE);
+    constexpr int MSF = L::MSF;
+    int64_t const n = G.n;
+    double const qdt = F.dt * 0.25;
+    double const hdt = F.dt * 0.5;
+    double acc[NEQ];
+#pragma unroll
+    for (int e = 0; e < NEQ; ++e) { acc[e] = 0.0; }
+
+    double * const wst = st - lane; // the warp's 32 columns of the staging buffer
+    int32_t jn = G.nbr[i];
+    jmax = jn; // the largest neighbour index tells whether the cell touches a ghost
+    soln_stage_issue_n<TYPE, TB>(F, jn, st);
+    if (0 == lane)
+    {
+        soln_bulk_issue_a<TYPE, TB>(G, iw0, 0, wst, &bars[0]);
+        soln_bulk_issue_b<TYPE, TB>(G, iw0, 0, wst, &bars[1]);
+    }
+    jn = G.nbr[n + i]; // NFC >= 3
+    double cc[ND];
+#pragma unroll
+    for (int d = 0; d < ND; ++d) { cc[d] = F.solpt[d * F.S + G.beg + i]; }
+    dist = DBL_MAX;
+    dist_ok = true;
+
+#pragma unroll 1
+    for (int f = 0; f < NFC; ++f)
+    {
+        int const nsf = ct_fnnd(TYPE, f);
+        double usfc[MSF][NEQ];
+        JacoS<ND> JS;
+        cp_async_wait<0>();          // the neighbour gather of this face (this thread's own copies)
+        mbar_wait(&bars[0], f & 1);  // cecnd / cevol / sfcnd rows of this face (the warp's bulk copies)
+        {
+            double jc[ND], ju[NEQ], jt[NEQ], jg[NEQ][ND];
+#pragma unroll
+            for (int d = 0; d < ND; ++d) { jc[d] = st[(L::R_JC + d) * TB]; }
+#pragma unroll
+            for (int e = 0; e < NEQ; ++e)
+            {
+                ju[e] = st[(L::R_JU + e) * TB];
+                jt[e] = st[(L::R_JT + e) * TB];
+#pragma unroll
+                for (int d = 0; d < ND; ++d) { jg[e][d] = st[(L::R_JG + e * ND + d) * TB]; }
+            }
+            double const ga = st[L::R_GA * TB];
+            // ---- spatial part over the basic CE (euler_march.cpp:236-249) and calc_cfl's distance
+            {
+                double bc[ND];
+#pragma unroll
+                for (int d = 0; d < ND; ++d) { bc[d] = st[(L::R_BC + d) * TB]; }
+                double const bvol = st[L::R_VOL * TB];
+#pragma unroll
+                for (int e = 0; e < NEQ; ++e)
+                {
+                    double fusp = ju[e];
+#pragma unroll
+                    for (int d = 0; d < ND; ++d) { fusp += (bc[d] - jc[d]) * jg[e][d]; }
+                    acc[e] += fusp * bvol;
+                }
+                double d2 = 0.0;
+#pragma unroll
+                for (int d = 0; d < ND; ++d)
+                {
+                    double const diff = bc[d] - cc[d];
+                    d2 += diff * diff;
+                }
+                double const r = sqrt_fast(d2, dist_ok); // range test deferred: no branch inside the face loop
+                dist = (r < dist) ? r : dist; // std::min(dist, r), euler_solution.cpp:129
+            }
+            // ---- Taylor state on every sub-face (euler_march.cpp:268-280)
+#pragma unroll
+            for (int s = 0; s < MSF; ++s)
+            {
+                double sc[ND];
+#pragma unroll
+                for (int d = 0; d < ND; ++d) { sc[d] = st[(L::R_SC + s * ND + d) * TB] - jc[d]; }
+#pragma unroll
+                for (int e = 0; e < NEQ; ++e)
+                {
+                    usfc[s][e] = qdt * jt[e];
+#pragma unroll
+                    for (int d = 0; d < ND; ++d) { usfc[s][e] += sc[d] * jg[e][d]; }
+                }
+            }
+            JS.set(ga, ju);
+        }
+        // ---- N and A are free (every lane of the warp has read its column): start the copies of the next face
+        if (f + 1 < NFC)
+        {
+            soln_stage_issue_n<TYPE, TB>(F, jn, st);
+            __syncwarp();
+            if (0 == lane) { soln_bulk_issue_a<TYPE, TB>(G, iw0, f + 1, wst, &bars[0]); }
+            jmax = jn > jmax ? jn : jmax;
+            if (f + 2 < NFC) { jn = G.nbr[(f + 2) * n + i]; }
+        }
+        mbar_wait(&bars[1], f & 1); // sfnml rows of this face
+        double sn[MSF][ND];
+#pragma unroll
+        for (int s = 0; s < MSF; ++s)
+        {
+#pragma unroll
+            for (int d = 0; d < ND; ++d) { sn[s][d] = st[(L::R_SN + s * ND + d) * TB]; }
+        }
+        if (f + 1 < NFC)
+        {
+            __syncwarp();
+            if (0 == lane) { soln_bulk_issue_b<TYPE, TB>(G, iw0, f + 1, wst, &bars[1]); }
+        }
+        // ---- temporal part, one equation (Jacobian row) at a time (euler_march.cpp:281-294)
+        flux_row<ND, 0, MSF>(JS, usfc, sn, hdt, nsf, acc[0]);
+        flux_row<ND, 1, MSF>(JS, usfc, sn, hdt, nsf, acc[1]);
+        flux_row<ND, 2, MSF>(JS, usfc, sn, hdt, nsf, acc[2]);
+        flux_row<ND, 3, MSF>(JS, usfc, sn, hdt, nsf, acc[3]);
+        if (NEQ > 4) { flux_row<ND, (NEQ > 4 ? 4 : 0), MSF>(JS, usfc, sn, hdt, nsf, acc[NEQ - 1]); }
+    }
+    double const cvol = G.cevol[i];
+#if SCG_SHARED_RCP
+    DivBy<true> by_cvol(cvol);
+#pragma unroll
+    for (int e = 0; e < NEQ; ++e) { out[e] = by_cvol(acc[e]); }
+    if (by_cvol.ok) { return; }
+#endif
+#pragma unroll
+    for (int e = 0; e < NEQ; ++e) { out[e] = acc[e] / cvol; }
+}
+
 
 
 // EulerCore::calc_dsoln for one cell, euler_gradient.cpp:23-130, with the GradientElement constructor

@@ -409,7 +409,7 @@ __global__ void mesh_nbr_kernel(MeshGroup g, int64_t ncell, int64_t nface, int64
             atomicMin(&err[2], static_cast<int>(icl));
             return;
         }
-        nbr[g.off_nbr + int64_t(f) * g.n + i] = (jcl >= 0) ? iperm[jcl] : static_cast<int32_t>(ncell + (-jcl - 1));
+        nbr[g.off_nbr + int64_t(f) * g.ld + i] = (jcl >= 0) ? iperm[jcl] : static_cast<int32_t>(ncell + (-jcl - 1));
     }
 }
 
@@ -633,11 +633,12 @@ int layout_on_device(scg_mesh * m, int32_t const * cltpn, int32_t const * clfcs,
             g.type = t;
             g.beg = static_cast<int32_t>(k);
             g.n = static_cast<int32_t>(n_t);
+            g.ld = (g.n + 31) / 32 * 32;
             g.nif = static_cast<int32_t>(h_hist[t * 3]);
             g.nact = static_cast<int32_t>(h_hist[t * 3] + h_hist[t * 3 + 1]);
             g.off_nbr = off_nbr;
             g.off_geo = off_geo;
-            off_nbr += int64_t(ct_nfc(t)) * g.n;
+            off_nbr += int64_t(ct_nfc(t)) * g.ld;
             off_geo += g.geo_size();
             m->groups.push_back(g);
             k += n_t;
@@ -865,6 +866,7 @@ int scg_mesh_create_part(scg_mesh ** out, int ndim, int64_t nnode, int64_t nface
             g.type = t;
             g.beg = static_cast<int32_t>(k);
             g.n = static_cast<int32_t>(e - k);
+            g.ld = (g.n + 31) / 32 * 32;
             g.nact = 0;
             g.nif = 0;
             for (int64_t q = k; q < e; ++q)
@@ -874,7 +876,7 @@ int scg_mesh_create_part(scg_mesh ** out, int ndim, int64_t nnode, int64_t nface
             }
             g.off_nbr = off_nbr;
             g.off_geo = off_geo;
-            off_nbr += int64_t(ct_nfc(t)) * g.n;
+            off_nbr += int64_t(ct_nfc(t)) * g.ld;
             off_geo += g.geo_size();
             m->groups.push_back(g);
             k = e;
@@ -918,7 +920,7 @@ int scg_mesh_create_part(scg_mesh ** out, int ndim, int64_t nnode, int64_t nface
                                               bad_kind = 2;
                                               return;
                                           }
-                                          nbr[g.off_nbr + int64_t(f) * g.n + i] = (jcl >= 0) ? m->iperm[jcl] : static_cast<int32_t>(ncell + (-jcl - 1));
+                                          nbr[g.off_nbr + int64_t(f) * g.ld + i] = (jcl >= 0) ? m->iperm[jcl] : static_cast<int32_t>(ncell + (-jcl - 1));
                                       }
                                   }
                               });
