@@ -400,39 +400,43 @@ __global__ void __launch_bounds__(StagedCfg<TYPE>::TB, StagedCfg<TYPE>::MB) md_s
     constexpr int NFC = ct_nfc(TYPE);
     constexpr int TB = StagedCfg<TYPE>::TB;
     extern __shared__ double stage_smem[];
-#if SCG_SOLN_BULK
-    // Warps start on multiples of 32 cells so that the bulk copies of the geometry rows are aligned; lanes outside
-    // [ibeg, iend) evaluate a clamped cell (they take part in the warp's barriers) and store nothing.
-    int const lane = threadIdx.x & 31;
-    int32_t const i_raw = (G.ibeg & ~31) + blockIdx.x * TB + threadIdx.x;
-    int32_t const iw0 = i_raw - lane;
-    if (iw0 >= G.iend) { return; } // the whole warp is past the range
-    bool const active = i_raw >= G.ibeg && i_raw < G.iend;
-    int32_t const i = i_raw < G.ibeg ? G.ibeg : (i_raw >= G.iend ? G.iend - 1 : i_raw);
-    uint64_t * const bars = reinterpret_cast<uint64_t *>(stage_smem + SolnStage<TYPE, TB>::ROWS * TB) + 2 * (threadIdx.x >> 5);
-    if (0 == lane)
-    {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
-        mbar_fence_init();
-    }
-    __syncwarp();
-#else
-    int32_t const i = G.ibeg + blockIdx.x * TB + threadIdx.x;
-    if (i >= G.iend) { return; }
-    constexpr bool active = true;
-#endif
-    int64_t const k = G.beg + i;
+    constexpr int MODE = soln_stage_mode(TYPE);
+    int32_t i;
     double un[NEQ];
     double dist;
     bool dist_ok;
     int32_t jmax;
-#if SCG_SOLN_BULK
-    cell_soln_staged_bulk<TYPE, TB>(F, G, i, iw0, lane, stage_smem + threadIdx.x, bars, un, dist, dist_ok, jmax);
-    if (!active) { return; }
-#else
-    cell_soln_staged<TYPE, TB>(F, G, i, stage_smem + threadIdx.x, un, dist, dist_ok, jmax);
-#endif
+    if constexpr (0 != MODE)
+    {
+        // Warps start on multiples of 32 cells so that the copies of the geometry rows are aligned; lanes outside
+        // [ibeg, iend) evaluate a clamped cell (they take part in the warp's barriers) and store nothing.
+        int const lane = threadIdx.x & 31;
+        int32_t const i_raw = (G.ibeg & ~31) + blockIdx.x * TB + threadIdx.x;
+        int32_t const iw0 = i_raw - lane;
+        if (iw0 >= G.iend) { return; } // the whole warp is past the range
+        bool const active = i_raw >= G.ibeg && i_raw < G.iend;
+        i = i_raw < G.ibeg ? G.ibeg : (i_raw >= G.iend ? G.iend - 1 : i_raw);
+        uint64_t * const bars = reinterpret_cast<uint64_t *>(stage_smem + SolnStage<TYPE, TB>::ROWS * TB) + 2 * (threadIdx.x >> 5);
+        if constexpr (1 == MODE)
+        {
+            if (0 == lane)
+            {
+                mbar_init(&bars[0], 1);
+                mbar_init(&bars[1], 1);
+                mbar_fence_init();
+            }
+            __syncwarp();
+        }
+        cell_soln_staged_bulk<TYPE, TB, MODE>(F, G, i, iw0, lane, stage_smem + threadIdx.x, bars, un, dist, dist_ok, jmax);
+        if (!active) { return; }
+    }
+    else
+    {
+        i = G.ibeg + blockIdx.x * TB + threadIdx.x;
+        if (i >= G.iend) { return; }
+        cell_soln_staged<TYPE, TB>(F, G, i, stage_smem + threadIdx.x, un, dist, dist_ok, jmax);
+    }
+    int64_t const k = G.beg + i;
     if (!dist_ok)
     {
         // a square root of calc_cfl's distance left the fast range: redo the distance with the plain operator
@@ -464,7 +468,6 @@ __global__ void __launch_bounds__(StagedCfg<TYPE>::TB, StagedCfg<TYPE>::MB) md_s
     F.cflc[k] = cflc;
 #pragma unroll
     for (int e = 0; e < NEQ; ++e) { F.so0n[e * F.S + k] = un[e]; }
-    (void)active;
 }
 
 // Split substep, kernel 2, equation-outer variant (march mode 3): one thread per cell, adj(D)/det(D) of the
@@ -1441,13 +1444,10 @@ void launch_cell_phase_t(scg_md * s, MeshGroup const & g, CellPhase ph, int part
     case CP_SOLNCFL_STAGED:
     {
         constexpr int TBS = StagedCfg<TYPE>::TB;
-#if SCG_SOLN_BULK
-        constexpr int BYTES = SolnStage<TYPE, TBS>::BYTES + 2 * (TBS / 32) * int(sizeof(uint64_t)); // + one mbarrier per warp and buffer
-        int64_t const span = G.iend - (G.ibeg & ~31); // warps start on multiples of 32 cells
-#else
-        constexpr int BYTES = SolnStage<TYPE, TBS>::BYTES;
-        int64_t const span = ncl;
-#endif
+        constexpr int MODE = soln_stage_mode(TYPE);
+        // mode 1: + one mbarrier per warp and buffer; modes 1 and 2: warps start on multiples of 32 cells
+        constexpr int BYTES = SolnStage<TYPE, TBS>::BYTES + (1 == MODE ? 2 * (TBS / 32) * int(sizeof(uint64_t)) : 0);
+        int64_t const span = (0 != MODE) ? G.iend - (G.ibeg & ~31) : ncl;
         static bool attr_set = false;
         if (!attr_set)
         {

@@ -638,6 +638,12 @@ __device__ __forceinline__ void cp_async8(double * smem_dst, double const * gsrc
     unsigned const d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
 }
+// 16 bytes, L2 only (.cg): for rows a warp reads once -- they do not displace the neighbour gathers from L1
+__device__ __forceinline__ void cp_async16(double * smem_dst, double const * gsrc)
+{
+    unsigned const d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 // Ask L2 for the line holding *p: no register, no scoreboard.  Used for data THIS thread reads a few microseconds
 // later (later faces / later equations of its own cell), so that the staged copies and gathers meet L2 instead of HBM.
@@ -692,9 +698,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t * bar, unsigned parity)
                  : "memory");
 }
 
-#ifndef SCG_SOLN_BULK
-#define SCG_SOLN_BULK 0 // 1: md_solncfl_staged stages the geometry rows with cp.async.bulk + mbarrier (one lane per warp)
+// How md_solncfl_staged stages the geometry rows, per cell type (one decimal digit each, in the order quad, tri, hex,
+// tet, prism, pyramid from the lowest digit): 0 = 8-byte cp.async.ca per thread, 1 = cp.async.bulk + mbarrier (one lane
+// per warp, 256-byte copies), 2 = 16-byte cp.async.cg (two rows per warp instruction, nothing allocated in L1).
+// Measured (profiles/r02f_*): mode 2 is 1-3 % faster for hexahedra, prisms, quadrilaterals and triangles and 15 % slower
+// for tetrahedra (odd row counts: 13 and 9); mode 1 is slower everywhere.
+#ifndef SCG_SOLN_STAGE_MODES
+#define SCG_SOLN_STAGE_MODES 220222
 #endif
+__host__ __device__ constexpr int soln_stage_mode(int type)
+{
+    int m = SCG_SOLN_STAGE_MODES;
+    for (int t = CT_QUAD; t < type; ++t) { m /= 10; }
+    return m % 10;
+}
 
 // Jacobian in scalar form: the quantities every entry of EulerJacobian<ND>::update is built from
 // (euler_march.cpp:35-81, 94-157), and row<E>() which forms fcn[E][:] and jac[E][:][:] from them with the
@@ -1135,10 +1152,75 @@ __device__ __forceinline__ void soln_bulk_issue_b(MdGeo const & G, int64_t iw0, 
     }
 }
 
-// cell_soln_staged with the geometry rows staged by bulk copies (SCG_SOLN_BULK): same terms, same order.  `i` is the
+// The same rows by 16-byte cp.async.cg (staging mode 2): a warp's 32 doubles of one row are 16 chunks, so one
+// instruction of the warp moves TWO rows (lanes 0-15 the first, lanes 16-31 the second): half the LDGSTS of the 8-byte
+// scheme, 128-bit accesses, and nothing allocated in L1.  Rows are addressed inside the group's geometry block
+// [cevol | cecnd | sfcnd | sfnml], all with stride n.
+template <int TYPE, int TB>
+struct SolnRows
+{
+    using L = SolnStage<TYPE, TB>;
+    static constexpr int ND = L::ND;
+    static constexpr int NFC = ct_nfc(TYPE);
+    static constexpr int NSF = ct_nsf(TYPE);
+    // geometry-block row of staging row r of buffer A (r = 0 .. ND + MSF*ND) for face f
+    __device__ static __forceinline__ int row_a(int r, int f, int q0, int nsf)
+    {
+        if (r < ND) { return (NFC + 1) + f * ND + r; }                // cecnd[f][d]
+        if (r == ND) { return f + 1; }                                // cevol[f + 1]
+        int const s = (r - ND - 1) / ND, d = (r - ND - 1) % ND;
+        int const q = q0 + (s < nsf ? s : nsf - 1);
+        return (NFC + 1) + NFC * ND + q * ND + d;                     // sfcnd[q][d]
+    }
+    __device__ static __forceinline__ int row_b(int r, int q0, int nsf)
+    {
+        int const s = r / ND, d = r % ND;
+        int const q = q0 + (s < nsf ? s : nsf - 1);
+        return (NFC + 1) + NFC * ND + NSF * ND + q * ND + d;          // sfnml[q][d]
+    }
+};
+
+template <int TYPE, int TB>
+__device__ __forceinline__ void soln_vec_issue_a(MdGeo const & G, int64_t iw0, int f, int lane, double * wst)
+{
+    using L = SolnStage<TYPE, TB>;
+    using R = SolnRows<TYPE, TB>;
+    constexpr int NR = L::ND + 1 + L::MSF * L::ND;
+    int64_t const n = G.n;
+    int const nsf = ct_fnnd(TYPE, f);
+    int const q0 = ct_sfoff(TYPE, f);
+    int const hi = lane >> 4, ch = (lane & 15) * 2;
+#pragma unroll
+    for (int p = 0; p < (NR + 1) / 2; ++p)
+    {
+        int const r = 2 * p + hi;
+        if (r < NR) { cp_async16(wst + (L::R_BC + r) * TB + ch, G.cevol + R::row_a(r, f, q0, nsf) * n + iw0 + ch); }
+    }
+}
+
+template <int TYPE, int TB>
+__device__ __forceinline__ void soln_vec_issue_b(MdGeo const & G, int64_t iw0, int f, int lane, double * wst)
+{
+    using L = SolnStage<TYPE, TB>;
+    using R = SolnRows<TYPE, TB>;
+    constexpr int NR = L::MSF * L::ND;
+    int64_t const n = G.n;
+    int const nsf = ct_fnnd(TYPE, f);
+    int const q0 = ct_sfoff(TYPE, f);
+    int const hi = lane >> 4, ch = (lane & 15) * 2;
+#pragma unroll
+    for (int p = 0; p < (NR + 1) / 2; ++p)
+    {
+        int const r = 2 * p + hi;
+        if (r < NR) { cp_async16(wst + (L::R_SN + r) * TB + ch, G.cevol + R::row_b(r, q0, nsf) * n + iw0 + ch); }
+    }
+    cp_async_commit();
+}
+
+// cell_soln_staged with the geometry rows staged by bulk copies (MODE 1) or 16-byte copies (MODE 2): same terms, same order.  `i` is the
 // cell this lane evaluates (clamped into the launch range for the lanes that have none: they keep the warp's
 // barriers and __syncwarp()s company and their results are dropped by the caller), `iw0` the first cell of the warp.
-template <int TYPE, int TB>
+template <int TYPE, int TB, int MODE>
 __device__ __forceinline__ void cell_soln_staged_bulk(MdField const & F, MdGeo const & G, int32_t i, int32_t iw0, int lane, double * st,
                                                       uint64_t * bars, double (&out)[ct_ndim(TYPE) + 2], double & dist, bool & dist_ok,
                                                       int32_t & jmax)
@@ -1158,11 +1240,20 @@ __device__ __forceinline__ void cell_soln_staged_bulk(MdField const & F, MdGeo c
     double * const wst = st - lane; // the warp's 32 columns of the staging buffer
     int32_t jn = G.nbr[i];
     jmax = jn; // the largest neighbour index tells whether the cell touches a ghost
-    soln_stage_issue_n<TYPE, TB>(F, jn, st);
-    if (0 == lane)
+    if constexpr (2 == MODE)
     {
-        soln_bulk_issue_a<TYPE, TB>(G, iw0, 0, wst, &bars[0]);
-        soln_bulk_issue_b<TYPE, TB>(G, iw0, 0, wst, &bars[1]);
+        soln_vec_issue_a<TYPE, TB>(G, iw0, 0, lane, wst);
+        soln_stage_issue_n<TYPE, TB>(F, jn, st); // commits the group: A and N of face 0
+        soln_vec_issue_b<TYPE, TB>(G, iw0, 0, lane, wst);
+    }
+    else
+    {
+        soln_stage_issue_n<TYPE, TB>(F, jn, st);
+        if (0 == lane)
+        {
+            soln_bulk_issue_a<TYPE, TB>(G, iw0, 0, wst, &bars[0]);
+            soln_bulk_issue_b<TYPE, TB>(G, iw0, 0, wst, &bars[1]);
+        }
     }
     jn = G.nbr[n + i]; // NFC >= 3
     double cc[ND];
@@ -1177,8 +1268,16 @@ __device__ __forceinline__ void cell_soln_staged_bulk(MdField const & F, MdGeo c
         int const nsf = ct_fnnd(TYPE, f);
         double usfc[MSF][NEQ];
         JacoS<ND> JS;
-        cp_async_wait<0>();          // the neighbour gather of this face (this thread's own copies)
-        mbar_wait(&bars[0], f & 1);  // cecnd / cevol / sfcnd rows of this face (the warp's bulk copies)
+        if constexpr (2 == MODE)
+        {
+            cp_async_wait<1>(); // this lane's share of A and N of this face has landed (B may still be in flight) ...
+            __syncwarp();       // ... and so has every other lane's
+        }
+        else
+        {
+            cp_async_wait<0>();          // the neighbour gather of this face (this thread's own copies)
+            mbar_wait(&bars[0], f & 1);  // cecnd / cevol / sfcnd rows of this face (the warp's bulk copies)
+        }
         {
             double jc[ND], ju[NEQ], jt[NEQ], jg[NEQ][ND];
 #pragma unroll
@@ -1234,15 +1333,32 @@ __device__ __forceinline__ void cell_soln_staged_bulk(MdField const & F, MdGeo c
             JS.set(ga, ju);
         }
         // ---- N and A are free (every lane of the warp has read its column): start the copies of the next face
-        if (f + 1 < NFC)
+        if constexpr (2 == MODE)
         {
-            soln_stage_issue_n<TYPE, TB>(F, jn, st);
+            if (f + 1 < NFC)
+            {
+                __syncwarp();
+                soln_vec_issue_a<TYPE, TB>(G, iw0, f + 1, lane, wst);
+                soln_stage_issue_n<TYPE, TB>(F, jn, st);
+                jmax = jn > jmax ? jn : jmax;
+                if (f + 2 < NFC) { jn = G.nbr[(f + 2) * n + i]; }
+                cp_async_wait<1>(); // B of this face
+            }
+            else { cp_async_wait<0>(); }
             __syncwarp();
-            if (0 == lane) { soln_bulk_issue_a<TYPE, TB>(G, iw0, f + 1, wst, &bars[0]); }
-            jmax = jn > jmax ? jn : jmax;
-            if (f + 2 < NFC) { jn = G.nbr[(f + 2) * n + i]; }
         }
-        mbar_wait(&bars[1], f & 1); // sfnml rows of this face
+        else
+        {
+            if (f + 1 < NFC)
+            {
+                soln_stage_issue_n<TYPE, TB>(F, jn, st);
+                __syncwarp();
+                if (0 == lane) { soln_bulk_issue_a<TYPE, TB>(G, iw0, f + 1, wst, &bars[0]); }
+                jmax = jn > jmax ? jn : jmax;
+                if (f + 2 < NFC) { jn = G.nbr[(f + 2) * n + i]; }
+            }
+            mbar_wait(&bars[1], f & 1); // sfnml rows of this face
+        }
         double sn[MSF][ND];
 #pragma unroll
         for (int s = 0; s < MSF; ++s)
@@ -1253,7 +1369,8 @@ __device__ __forceinline__ void cell_soln_staged_bulk(MdField const & F, MdGeo c
         if (f + 1 < NFC)
         {
             __syncwarp();
-            if (0 == lane) { soln_bulk_issue_b<TYPE, TB>(G, iw0, f + 1, wst, &bars[1]); }
+            if constexpr (2 == MODE) { soln_vec_issue_b<TYPE, TB>(G, iw0, f + 1, lane, wst); }
+            else if (0 == lane) { soln_bulk_issue_b<TYPE, TB>(G, iw0, f + 1, wst, &bars[1]); }
         }
         // ---- temporal part, one equation (Jacobian row) at a time (euler_march.cpp:281-294)
         flux_row<ND, 0, MSF>(JS, usfc, sn, hdt, nsf, acc[0]);
