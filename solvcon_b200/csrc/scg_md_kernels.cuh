@@ -1578,12 +1578,20 @@ __device__ __forceinline__ void cell_dsoln(MdField const & F, MdGeo const & G, i
 // weighs and limits them (:79-128) and stores its ND gradient components.  The neighbour gather of
 // equation e+1 is issued into a second register set before the arithmetic of equation e starts.  Same
 // operations on the same operands in the same order as cell_dsoln; only the schedule differs.
+// Cell types (bit t - CT_QUAD) for which the refined reciprocal of det(D) is parked in shared memory next to det(D)
+// instead of being refined again by every equation (5 DFMA + 1 MUFU per gradient element and equation).  Measured
+// (profiles/r02f_dsoln_yrow_ab.txt): tetrahedra 6 % faster, hexahedra / quadrilaterals / triangles 1-2 %, prisms 16 %
+// slower (the extra rows cost them L1).
+#ifndef SCG_EQO_YROW_MASK
+#define SCG_EQO_YROW_MASK 0x0f // quad, tri, hex, tet
+#endif
+__host__ __device__ constexpr int eqo_yrow(int type) { return (SCG_EQO_YROW_MASK >> (type - CT_QUAD)) & 1; }
 template <int TYPE, int TB>
 struct DsolnEqo
 {
     static constexpr int ND = ct_ndim(TYPE);
     static constexpr int NFGE = ct_nfge(TYPE);
-    static constexpr int RPF = ND * ND + 1; // rows per gradient element: adj, det
+    static constexpr int RPF = ND * ND + 1 + eqo_yrow(TYPE); // rows per gradient element: adj, det (, refined 1/det)
     // the cell's new gradient so1n[NEQ][ND] for the fused calc_solt: parked in shared memory in 2D (8 rows, 5 % faster
     // than reading it back); in 3D 15 more rows per thread would shrink L1 by as much and the gathers of the
     // equation loop live on L1 (tetrahedra: 318 -> 452 us), so there it is read back from L2
@@ -1602,7 +1610,7 @@ __device__ __forceinline__ bool eqo_solve(double const * sadj, double const (&ud
 {
     constexpr int ND = ct_ndim(TYPE);
     constexpr int NFGE = ct_nfge(TYPE);
-    constexpr int RPF = ND * ND + 1;
+    constexpr int RPF = ND * ND + 1 + eqo_yrow(TYPE);
     bool ok = true;
 #pragma unroll
     for (int ifge = 0; ifge < NFGE; ++ifge)
@@ -1619,7 +1627,8 @@ __device__ __forceinline__ bool eqo_solve(double const * sadj, double const (&ud
 #pragma unroll
     for (int ifge = 0; ifge < NFGE; ++ifge)
     {
-        DivBy<FAST> by_det(sadj[(ifge * RPF + ND * ND) * TB]);
+        DivBy<FAST> by_det = (FAST && eqo_yrow(TYPE)) ? DivBy<FAST>(sadj[(ifge * RPF + ND * ND) * TB], sadj[(ifge * RPF + RPF - 1) * TB])
+                                                      : DivBy<FAST>(sadj[(ifge * RPF + ND * ND) * TB]);
 #pragma unroll
         for (int a = 0; a < ND; ++a) { grad[ifge][a] = by_det.template quot<SCG_EQO_ZERO>(grad[ifge][a]); }
         ok = ok && by_det.ok;
@@ -1692,7 +1701,7 @@ __device__ __forceinline__ void cell_dsoln_eqo(MdField const & F, MdGeo const & 
     constexpr int NEQ = ND + 2;
     constexpr int NFC = ct_nfc(TYPE);
     constexpr int NFGE = ct_nfge(TYPE);
-    constexpr int RPF = ND * ND + 1;
+    constexpr int RPF = ND * ND + 1 + eqo_yrow(TYPE);
     int64_t const n = G.n;
     int64_t const S = F.S;
     int64_t const k = G.beg + i;
@@ -1840,6 +1849,7 @@ __device__ __forceinline__ void cell_dsoln_eqo(MdField const & F, MdGeo const & 
                 for (int b = 0; b < ND; ++b) { sadj[(ifge * RPF + a * ND + b) * TB] = adj[a][b]; }
             }
             sadj[(ifge * RPF + ND * ND) * TB] = det;
+            if (eqo_yrow(TYPE)) { sadj[(ifge * RPF + RPF - 1) * TB] = DivBy<true>(det).y; }
         }
     }
 
