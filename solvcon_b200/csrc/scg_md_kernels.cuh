@@ -69,6 +69,10 @@ __device__ __forceinline__ void prefetch_l2(void const * p) { asm volatile("pref
 #define SCG_EQO_ZERO 2
 #endif
 
+#ifndef SCG_SKIP_ZERO_ADD
+#define SCG_SKIP_ZERO_ADD 1 // drop the leading "0.0 +" of two ordered sums whose zero sign provably cannot reach a result
+#endif
+
 #ifndef SCG_SHARED_RCP
 #define SCG_SHARED_RCP 1
 #endif
@@ -824,6 +828,9 @@ __device__ __forceinline__ void flux_row(JacoS<ND> const & JS, double const (&us
 #pragma unroll
     for (int s = 0; s < MSF; ++s)
     {
+        // dot = 0.0 + t0 + t1 + ..: without the leading "0.0 +" (SCG_SKIP_ZERO_ADD) dot can be -0 where the reference has
+        // +0; hdt * dot is then -0 instead of +0 and acc - (-0) == acc - (+0) for every acc but -0, which acc never is (it
+        // starts from +0 and x - y is -0 only for x == -0)
         double dot = 0.0;
 #pragma unroll
         for (int d2 = 0; d2 < ND; ++d2)
@@ -835,7 +842,8 @@ __device__ __forceinline__ void flux_row(JacoS<ND> const & JS, double const (&us
                 if (2 == jkind<ND>(E, je, d2)) { dfcn += jr[je][d2] * usfc[s][je]; }
                 else if (1 == jkind<ND>(E, je, d2)) { dfcn += usfc[s][je]; }
             }
-            dot += dfcn * sn[s][d2];
+            double const t = dfcn * sn[s][d2];
+            dot = (SCG_SKIP_ZERO_ADD && 0 == d2) ? t : dot + t;
         }
         if (s < nsf) { acc_e -= hdt * dot; }
     }
@@ -1618,9 +1626,15 @@ __device__ __forceinline__ bool eqo_solve(double const * sadj, double const (&ud
 #pragma unroll
         for (int a = 0; a < ND; ++a)
         {
+            // r = 0.0 + p0 + p1 + ..: the leading "0.0 +" is dropped when SCG_SKIP_ZERO_ADD: it can only turn a -0 into a
+            // +0, and the sign of a zero gradient cannot reach so1n (see SCG_EQO_ZERO)
             double r = 0.0;
 #pragma unroll
-            for (int b = 0; b < ND; ++b) { r += sadj[(ifge * RPF + a * ND + b) * TB] * udf[fge_face(TYPE, ifge, b)]; }
+            for (int b = 0; b < ND; ++b)
+            {
+                double const p = sadj[(ifge * RPF + a * ND + b) * TB] * udf[fge_face(TYPE, ifge, b)];
+                r = (SCG_SKIP_ZERO_ADD && 0 == b) ? p : r + p;
+            }
             grad[ifge][a] = r;
         }
     }

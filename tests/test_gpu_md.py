@@ -597,3 +597,25 @@ def test_device_layout_equals_host_layout(gpu, bridge, monkeypatch, name, order)
         monkeypatch.delenv("SCG_MESH_HOST_LAYOUT", raising=False)
         assert np.array_equal(np.sort(dev), np.arange(len(cltpn)))
         assert np.array_equal(dev, host), f"{name} {order}: device and host layouts order the cells differently"
+
+
+@pytest.mark.parametrize("name", ["mixed2d", "mixed3d", "pyramid3d"])
+def test_md_march_same_bit_patterns(gpu, bridge, name):
+    """Stricter than array_equal (which calls -0.0 and +0.0 equal): the arrays a caller can read after march() carry the
+    checker's bit patterns, signs of zeros included.  The default kernels drop two leading `0.0 +` of ordered sums
+    (SCG_SKIP_ZERO_ADD) on the argument that the sign of those zeros cannot reach a result; the bump case keeps whole
+    regions of exactly zero transverse momentum and zero gradients, which is where it would show."""
+    b = bridge
+    if not _strict(gpu):
+        pytest.skip("bit patterns are a property of the strict build")
+    c = Case(b, name, order="rcm")
+    c.chk.phase(b.MD_BC_SOLN)
+    c.chk.phase(b.MD_BC_DSOLN)
+    c.dev.bc_soln()
+    c.dev.bc_dsoln()
+    c.chk.march(12)
+    c.dev.march(12)
+    for n in ("so0n", "so1n", "cflo", "cflc"):
+        a = np.ascontiguousarray(getattr(c.dev, n).ndarray).view(np.int64)
+        w = np.ascontiguousarray(c.chk.arr(n)).view(np.int64)
+        assert np.array_equal(a, w), f"{name}: {n} differs in bit pattern at {np.argwhere(a != w)[:4].tolist()}"
