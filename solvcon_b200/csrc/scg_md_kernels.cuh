@@ -18,6 +18,7 @@
 #include "scg_md.cuh"
 
 #include <cfloat>
+#include <math_constants.h>
 #include <type_traits>
 
 namespace scg
@@ -959,6 +960,7 @@ __device__ __forceinline__ void cell_soln_staged(MdField const & F, MdGeo const 
     for (int d = 0; d < ND; ++d) { cc[d] = F.solpt[d * F.S + G.beg + i]; }
     dist = DBL_MAX;
     dist_ok = true;
+    double d2min = CUDART_INF;
 #if SCG_SOLN_L2PF
     // the staged copies run ONE face ahead; faces >= 2 are requested from HBM now so that their copies meet L2
 #pragma unroll
@@ -1039,8 +1041,9 @@ __device__ __forceinline__ void cell_soln_staged(MdField const & F, MdGeo const 
                     double const diff = bc[d] - cc[d];
                     d2 += diff * diff;
                 }
-                double const r = sqrt_fast(d2, dist_ok); // range test deferred: no branch inside the face loop
-                dist = (r < dist) ? r : dist; // std::min(dist, r), euler_solution.cpp:129
+                // euler_solution.cpp:129 takes std::min over the faces of sqrt(d2); the square root is monotone and
+                // correctly rounded, so the minimum of the roots is the root of the minimum: one square root per cell
+                d2min = (d2 < d2min) ? d2 : d2min;
             }
             // ---- Taylor state on every sub-face (euler_march.cpp:268-280)
 #pragma unroll
@@ -1083,6 +1086,7 @@ __device__ __forceinline__ void cell_soln_staged(MdField const & F, MdGeo const 
         flux_row<ND, 3, MSF>(JS, usfc, sn, hdt, nsf, acc[3]);
         if (NEQ > 4) { flux_row<ND, (NEQ > 4 ? 4 : 0), MSF>(JS, usfc, sn, hdt, nsf, acc[NEQ - 1]); }
     }
+    if (d2min < CUDART_INF) { dist = sqrt_fast(d2min, dist_ok); } // no finite face distance: dist stays DBL_MAX like in the reference
     double const cvol = G.cevol[i];
 #if SCG_SHARED_RCP
     DivBy<true> by_cvol(cvol);
@@ -1269,6 +1273,7 @@ __device__ __forceinline__ void cell_soln_staged_bulk(MdField const & F, MdGeo c
     for (int d = 0; d < ND; ++d) { cc[d] = F.solpt[d * F.S + G.beg + i]; }
     dist = DBL_MAX;
     dist_ok = true;
+    double d2min = CUDART_INF;
 
 #pragma unroll 1
     for (int f = 0; f < NFC; ++f)
@@ -1320,8 +1325,9 @@ __device__ __forceinline__ void cell_soln_staged_bulk(MdField const & F, MdGeo c
                     double const diff = bc[d] - cc[d];
                     d2 += diff * diff;
                 }
-                double const r = sqrt_fast(d2, dist_ok); // range test deferred: no branch inside the face loop
-                dist = (r < dist) ? r : dist; // std::min(dist, r), euler_solution.cpp:129
+                // euler_solution.cpp:129 takes std::min over the faces of sqrt(d2); the square root is monotone and
+                // correctly rounded, so the minimum of the roots is the root of the minimum: one square root per cell
+                d2min = (d2 < d2min) ? d2 : d2min;
             }
             // ---- Taylor state on every sub-face (euler_march.cpp:268-280)
 #pragma unroll
@@ -1387,6 +1393,7 @@ __device__ __forceinline__ void cell_soln_staged_bulk(MdField const & F, MdGeo c
         flux_row<ND, 3, MSF>(JS, usfc, sn, hdt, nsf, acc[3]);
         if (NEQ > 4) { flux_row<ND, (NEQ > 4 ? 4 : 0), MSF>(JS, usfc, sn, hdt, nsf, acc[NEQ - 1]); }
     }
+    if (d2min < CUDART_INF) { dist = sqrt_fast(d2min, dist_ok); } // no finite face distance: dist stays DBL_MAX like in the reference
     double const cvol = G.cevol[i];
 #if SCG_SHARED_RCP
     DivBy<true> by_cvol(cvol);
