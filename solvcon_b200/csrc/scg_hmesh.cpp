@@ -941,10 +941,14 @@ int scg_hmesh_build_interior(scg_hmesh * m, int do_metric, int do_edge)
             }
             return 0;
         }
-        // an out-of-range node: fall through to the host loop below for the reference's message
+        // An out-of-range node: the host loop below gives the reference's message.  Anything else (no memory left on the
+        // device, a mesh too large for the int32 candidate numbering): the host builder makes the same tables.
         m->dev.reset();
-        std::string const msg = scg_last_error();
-        if (msg.find("out of range") == std::string::npos) { return rc; }
+        cudaGetLastError();
+        if (std::getenv("SCG_HMESH_TIMING"))
+        {
+            std::fprintf(stderr, "[hmesh] device builder gave up (%s); building on the host\n", scg_last_error());
+        }
     }
     m->dev.reset();
     for (int64_t icl = 0; icl < m->ncell; ++icl)

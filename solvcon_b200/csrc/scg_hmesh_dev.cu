@@ -599,6 +599,9 @@ int build_interior(Tables & t, int ndim, int64_t nnode, int64_t ncell, double co
                    int32_t const * clnds, bool do_metric)
 {
     if (int rc = ensure_init()) { return rc; }
+    // candidate faces are numbered with int32 (at most 6 per cell)
+    SCG_REQUIRE(ncell < (int64_t(1) << 31) / 6 - 1, "StaticMesh (device builder): %lld cells exceed the int32 numbering of the candidate faces",
+                static_cast<long long>(ncell));
     cudaStream_t const st = stream();
     // `t` is a fresh object (scg_hmesh.cpp makes a new one for every build)
     t.ndim = ndim;

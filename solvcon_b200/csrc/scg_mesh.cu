@@ -439,6 +439,8 @@ __global__ void mesh_fetch_faces_kernel(int64_t n, int ndim, int32_t const * fac
 
 inline unsigned grid_of(int64_t n, int tb = 256) { return static_cast<unsigned>(n > 0 ? (n + tb - 1) / tb : 1); }
 
+constexpr int RCM_TOO_DEEP = 77;
+
 // RCM order of the body cells on the device: d_order[r] = r-th cell of the Cuthill-McKee order (not yet reversed)
 int device_rcm(int64_t ncell, int32_t const * clfcs_b, int32_t const * fccls_b, DevBuf<int32_t> & d_order)
 {
@@ -465,7 +467,7 @@ int device_rcm(int64_t ncell, int32_t const * clfcs_b, int32_t const * fccls_b, 
     if (int rc = size_scan(cap)) { return rc; }
     cudaStream_t const st = stream();
     rcm_degree_kernel<<<grid_of(ncell), 256, 0, st>>>(ncell, clfcs_b, fccls_b, degree.p, pos.p, claim.p);
-    int64_t done = 0;
+    int64_t done = 0, levels = 0;
     while (done < ncell)
     {
         // next component
@@ -497,6 +499,9 @@ int device_rcm(int64_t ncell, int32_t const * clfcs_b, int32_t const * fccls_b, 
             }
             lb = le;
             le += total;
+            // One host round trip per level: a graph that is a long chain (a strip of cells) has as many levels as cells.
+            // Such graphs go back to the sequential host code, which is linear in the cells whatever the depth.
+            if (++levels > 16384 && le < levels * 64) { return RCM_TOO_DEEP; }
         }
         done = le;
     }
@@ -571,9 +576,26 @@ int layout_on_device(scg_mesh * m, int32_t const * cltpn, int32_t const * clfcs,
     if (SCG_ORDER_RCM == m->order)
     {
         DevBuf<int32_t> order;
-        if (int rc = device_rcm(ncell, clfcs_b, fccls_b, order)) { return rc; }
-        mesh_reverse_kernel<<<grid_of(ncell), 256, 0, st>>>(ncell, order.p, by_key.p);
-        SCG_CUDA(cudaStreamSynchronize(st));
+        int const rc = device_rcm(ncell, clfcs_b, fccls_b, order);
+        if (RCM_TOO_DEEP == rc)
+        {
+            // the sequential code on host copies of the two connectivity tables, its rank uploaded as the cell list
+            SCG_CUDA(cudaStreamSynchronize(st));
+            std::vector<int32_t> h_clfcs(static_cast<size_t>(ncell) * 7), h_fccls(static_cast<size_t>(nface) * 4);
+            SCG_CUDA(cudaMemcpy(h_clfcs.data(), clfcs_b, sizeof(int32_t) * h_clfcs.size(), cudaMemcpyDeviceToHost));
+            SCG_CUDA(cudaMemcpy(h_fccls.data(), fccls_b, sizeof(int32_t) * h_fccls.size(), cudaMemcpyDeviceToHost));
+            std::vector<uint64_t> key;
+            rcm_rank(ncell, h_clfcs.data(), h_fccls.data(), key);
+            std::vector<int32_t> h_by_key(static_cast<size_t>(ncell));
+            for (int64_t i = 0; i < ncell; ++i) { h_by_key[key[i]] = static_cast<int32_t>(i); }
+            SCG_CUDA(cudaMemcpy(by_key.p, h_by_key.data(), sizeof(int32_t) * ncell, cudaMemcpyHostToDevice));
+        }
+        else if (rc) { return rc; }
+        else
+        {
+            mesh_reverse_kernel<<<grid_of(ncell), 256, 0, st>>>(ncell, order.p, by_key.p);
+            SCG_CUDA(cudaStreamSynchronize(st));
+        }
     }
     else if (SCG_ORDER_MORTON == m->order)
     {

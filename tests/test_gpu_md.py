@@ -619,3 +619,19 @@ def test_md_march_same_bit_patterns(gpu, bridge, name):
         a = np.ascontiguousarray(getattr(c.dev, n).ndarray).view(np.int64)
         w = np.ascontiguousarray(c.chk.arr(n)).view(np.int64)
         assert np.array_equal(a, w), f"{name}: {n} differs in bit pattern at {np.argwhere(a != w)[:4].tolist()}"
+
+
+def test_device_layout_rcm_on_a_chain_of_cells(gpu, monkeypatch):
+    """A strip of cells is a graph with as many BFS levels as cells; the level-by-level device RCM hands such graphs back
+    to the sequential host code after 16384 levels.  Same permutation as the host layout."""
+    from solvcon_b200 import meshgen
+    from solvcon_b200.mesh import make_mesh
+    from solvcon_b200.multidim import DeviceMesh
+    ndcrd, cltpn, clnds = meshgen.mixed_2d(18000, 1, lx=18000.0, ly=1.0)
+    mesh = make_mesh(2, ndcrd, cltpn, clnds, device=False)
+    monkeypatch.delenv("SCG_MESH_HOST_LAYOUT", raising=False)
+    dev = DeviceMesh(mesh, order="rcm").perm
+    monkeypatch.setenv("SCG_MESH_HOST_LAYOUT", "1")
+    host = DeviceMesh(mesh, order="rcm").perm
+    monkeypatch.delenv("SCG_MESH_HOST_LAYOUT", raising=False)
+    assert len(dev) > 18000 and np.array_equal(dev, host)
