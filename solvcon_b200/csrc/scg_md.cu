@@ -195,6 +195,13 @@ __global__ void __launch_bounds__(256) md_solt_kernel(MdField const F, int32_t r
     solt_row<ND>(J, g, t);
 #pragma unroll
     for (int e = 0; e < ND + 2; ++e) { F.so0t[e * S + k] = t[e]; }
+#if SCG_JS_SHARE
+    {
+        JacoS<ND> Q;
+        Q.set(F.gamma[k], u);
+        Q.pack(F.js, S, k);
+    }
+#endif
 }
 
 // calc_solt for a list of rows (device indices): the rows the fused path does not cover -- ghost rows without a
@@ -219,6 +226,13 @@ __global__ void __launch_bounds__(256) md_solt_rows_kernel(MdField const F, int3
     solt_row<ND>(J, g, t);
 #pragma unroll
     for (int e = 0; e < ND + 2; ++e) { F.so0t[e * S + k] = t[e]; }
+#if SCG_JS_SHARE
+    {
+        JacoS<ND> Q;
+        Q.set(F.gamma[k], u);
+        Q.pack(F.js, S, k);
+    }
+#endif
 }
 
 template <int TYPE>
@@ -1054,6 +1068,13 @@ __global__ void __launch_bounds__(128) md_bc_dsoln_kernel(MdField const F, BcDev
         solt_row<ND>(J, gj, t);
 #pragma unroll
         for (int e = 0; e < NEQ; ++e) { F.so0t_next[e * S + jcl] = t[e]; }
+#if SCG_JS_SHARE
+        {
+            JacoS<ND> Q;
+            Q.set(F.gamma[jcl], u);
+            Q.pack(F.js_next, S, jcl);
+        }
+#endif
     }
 }
 
@@ -1303,7 +1324,7 @@ struct scg_md
     int ndim = 0, neq = 0;
     double dt = 0, sigma0 = 3.0, taumin = 0.0, tauscale = 1.0; // euler.hpp:184-188
     int cur = 0;                                               // so0[cur] is so0c, so0[1-cur] is so0n
-    DevBuf<double> so0[2], so1[2], so0t[2], gamma, cflo, cflc, solpt, geo, eraw, stage, red, clvol;
+    DevBuf<double> so0[2], so1[2], so0t[2], js[2], gamma, cflo, cflc, solpt, geo, eraw, stage, red, clvol;
     // fused calc_solt (march mode 3): so0t[tcur] belongs to the current so0c/so1c; while a substep runs, its gradient
     // kernels fill so0t[1 - tcur] for the next one.  so0t_valid: so0t[1 - tcur] is complete for every covered row
     // (owned body cells and ghost rows with a boundary condition); solt_rows lists the others.
@@ -1351,6 +1372,8 @@ MdField field_of(scg_md * s)
     F.so1n = s->so1[1 - s->cur].p;
     F.so0t = s->so0t[s->tcur].p;
     F.so0t_next = s->so0t[1 - s->tcur].p;
+    F.js = s->js[s->tcur].p; // same life cycle as so0t: same producers, same buffer flip
+    F.js_next = s->js[1 - s->tcur].p;
     F.fuse_solt = s->fuse_now ? 1 : 0;
     F.gamma = s->gamma.p;
     F.cflo = s->cflo.p;
@@ -1867,6 +1890,8 @@ int scg_md_create(scg_md ** out, scg_mesh * mesh, double time_increment)
     }
     z(s->so0t[0], S * neq);
     z(s->so0t[1], S * neq);
+    z(s->js[0], SCG_JS_SHARE ? S * (2 * nd + 3) : 1);
+    z(s->js[1], SCG_JS_SHARE ? S * (2 * nd + 3) : 1);
     z(s->gamma, S);
     z(s->cflo, S);
     z(s->cflc, S);

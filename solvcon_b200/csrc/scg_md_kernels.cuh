@@ -33,6 +33,8 @@ struct MdField // by value to every kernel
     double * so0n;
     double * so0t;
     double * so0t_next; // fused calc_solt: so0t of the NEXT substep, written by the dsoln / bc_dsoln kernels
+    double * js;        // [2*ndim+3][stride] the quotients of EulerJacobian::update of every row's so0c (see JacoS::pack);
+    double * js_next;   // produced wherever so0t / so0t_next is, consumed by md_solncfl_staged instead of redoing them per face
     double * so1c;
     double * so1n;
     double * gamma;
@@ -68,6 +70,12 @@ __device__ __forceinline__ void prefetch_l2(void const * p) { asm volatile("pref
 // (grad*grad is +0 either way; o[d] starts at +0 and +0 + (+-0) is +0, x + (+-0) is x)
 #ifndef SCG_EQO_ZERO
 #define SCG_EQO_ZERO 2
+#endif
+
+#ifndef SCG_JS_SHARE
+#define SCG_JS_SHARE 0 // 1: md_solncfl_staged gathers the Jacobian quotients of the neighbour state (MdField::js) instead of redoing them per
+                       // face.  Bit-equal and 140 instructions per face less, but the 9 extra gathered values cost more: hex soln -2 %,
+                       // tet soln +22 %, dsoln +3-5 % (the producer), 2D soln +17 % (profiles/README.md)
 #endif
 
 #ifndef SCG_SKIP_ZERO_ADD
@@ -772,6 +780,42 @@ struct JacoS
 #endif
         set_impl<false>(ga_in, u);
     }
+    // The members of set() that cost divisions -- v[], vs, getot, pr, e0[] -- as NJS values per row.  A cell's state is
+    // the neighbour state of each of its faces' other cell, so calc_soln evaluates set() of the same state once per
+    // face that sees it (6 times for a hexahedron's); pack() is evaluated once, by the kernel that produces so0t of the
+    // row, and load() rebuilds the object from the stored values: the same numbers, since set() is deterministic.
+    static constexpr int NJS = 2 * ND + 3;
+    __device__ __forceinline__ void pack(double * js, int64_t S, int64_t k) const
+    {
+#pragma unroll
+        for (int d = 0; d < ND; ++d)
+        {
+            js[d * S + k] = v[d];
+            js[(ND + 3 + d) * S + k] = e0[d];
+        }
+        js[ND * S + k] = vs;
+        js[(ND + 1) * S + k] = getot;
+        js[(ND + 2) * S + k] = pr;
+    }
+    __device__ __forceinline__ void load(double ga_in, double const (&u)[NEQ], double const (&q)[NJS])
+    {
+        ga = ga_in;
+        ga1 = ga - 1;
+        ga3 = ga - 3;
+        ga1h = ga1 / 2;
+#pragma unroll
+        for (int d = 0; d < ND; ++d)
+        {
+            m[d] = u[1 + d];
+            v[d] = q[d];
+            vo2[d] = v[d] * v[d];
+            e0[d] = q[ND + 3 + d];
+        }
+        en = u[NEQ - 1];
+        vs = q[ND];
+        getot = q[ND + 1];
+        pr = q[ND + 2];
+    }
     // fcn[E][d] and the general entries of jac[E][j][d] (structural zeros / ones are never read)
     template <int E>
     __device__ __forceinline__ void row(double (&fc)[ND], double (&jr)[NEQ][ND]) const
@@ -873,8 +917,10 @@ struct SolnStage
     static constexpr int R_JT = R_JU + NEQ;          // so0t[NEQ]
     static constexpr int R_JG = R_JT + NEQ;          // so1c[NEQ][ND]
     static constexpr int R_GA = R_JG + NEQ * ND;     // gamma
+    static constexpr int NJS = SCG_JS_SHARE ? 2 * ND + 3 : 0;
+    static constexpr int R_JS = R_GA + 1;            // js[NJS] (SCG_JS_SHARE)
     // A
-    static constexpr int R_BC = R_GA + 1;            // cecnd[f][ND]
+    static constexpr int R_BC = R_JS + NJS;          // cecnd[f][ND]
     static constexpr int R_VOL = R_BC + ND;          // cevol[f+1]
     static constexpr int R_SC = R_VOL + 1;           // sfcnd[s][ND]
     // B
@@ -901,6 +947,8 @@ __device__ __forceinline__ void soln_stage_issue_an(MdField const & F, MdGeo con
         for (int d = 0; d < ND; ++d) { cp_async8(st + (L::R_JG + e * ND + d) * TB, &F.so1c[(e * ND + d) * S + j]); }
     }
     cp_async8(st + L::R_GA * TB, &F.gamma[j]);
+#pragma unroll
+    for (int q = 0; q < L::NJS; ++q) { cp_async8(st + (L::R_JS + q) * TB, &F.js[q * S + j]); }
     int const nsf = ct_fnnd(TYPE, f);
     int const q0 = ct_sfoff(TYPE, f);
 #pragma unroll
@@ -1060,7 +1108,16 @@ __device__ __forceinline__ void cell_soln_staged(MdField const & F, MdGeo const 
                     for (int d = 0; d < ND; ++d) { usfc[s][e] += sc[d] * jg[e][d]; }
                 }
             }
+#if SCG_JS_SHARE
+            {
+                double jq[L::NJS];
+#pragma unroll
+                for (int q = 0; q < L::NJS; ++q) { jq[q] = st[(L::R_JS + q) * TB]; }
+                JS.load(ga, ju, jq);
+            }
+#else
             JS.set(ga, ju);
+#endif
         }
         // ---- N and A are free: start the copies of the next face
         if (f + 1 < NFC)
@@ -1117,6 +1174,8 @@ __device__ __forceinline__ void soln_stage_issue_n(MdField const & F, int64_t j,
         for (int d = 0; d < ND; ++d) { cp_async8(st + (L::R_JG + e * ND + d) * TB, &F.so1c[(e * ND + d) * S + j]); }
     }
     cp_async8(st + L::R_GA * TB, &F.gamma[j]);
+#pragma unroll
+    for (int q = 0; q < L::NJS; ++q) { cp_async8(st + (L::R_JS + q) * TB, &F.js[q * S + j]); }
     cp_async_commit();
 }
 
@@ -1344,7 +1403,16 @@ __device__ __forceinline__ void cell_soln_staged_bulk(MdField const & F, MdGeo c
                     for (int d = 0; d < ND; ++d) { usfc[s][e] += sc[d] * jg[e][d]; }
                 }
             }
+#if SCG_JS_SHARE
+            {
+                double jq[L::NJS];
+#pragma unroll
+                for (int q = 0; q < L::NJS; ++q) { jq[q] = st[(L::R_JS + q) * TB]; }
+                JS.load(ga, ju, jq);
+            }
+#else
             JS.set(ga, ju);
+#endif
         }
         // ---- N and A are free (every lane of the warp has read its column): start the copies of the next face
         if constexpr (2 == MODE)
@@ -1942,6 +2010,13 @@ __device__ __forceinline__ void cell_dsoln_eqo(MdField const & F, MdGeo const & 
         solt_row<ND>(J, g, t);
 #pragma unroll
         for (int e = 0; e < NEQ; ++e) { F.so0t_next[e * S + k] = t[e]; }
+#if SCG_JS_SHARE
+        {
+            JacoS<ND> Q;
+            Q.set(F.gamma[k], u);
+            Q.pack(F.js_next, S, k);
+        }
+#endif
     }
 }
 
@@ -2390,6 +2465,13 @@ __device__ __forceinline__ void cell_dsoln_eqo2(MdField const & F, MdGeo const &
         solt_row<ND>(J, g, t);
 #pragma unroll
         for (int e = 0; e < NEQ; ++e) { F.so0t_next[e * S + k] = t[e]; }
+#if SCG_JS_SHARE
+        {
+            JacoS<ND> Q;
+            Q.set(ga_own, u);
+            Q.pack(F.js_next, S, k);
+        }
+#endif
     }
 }
 
