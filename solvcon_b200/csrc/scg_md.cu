@@ -195,6 +195,10 @@ __global__ void __launch_bounds__(256) md_solt_kernel(MdField const F, int32_t r
     solt_row<ND>(J, g, t);
 #pragma unroll
     for (int e = 0; e < ND + 2; ++e) { F.so0t[e * S + k] = t[e]; }
+#if SCG_SW_SHARE
+#pragma unroll
+    for (int e = 0; e < ND + 2; ++e) { F.sw[e * S + k] = u[e] + (F.dt * 0.5) * t[e]; }
+#endif
 #if SCG_JS_SHARE
     {
         JacoS<ND> Q;
@@ -226,6 +230,10 @@ __global__ void __launch_bounds__(256) md_solt_rows_kernel(MdField const F, int3
     solt_row<ND>(J, g, t);
 #pragma unroll
     for (int e = 0; e < ND + 2; ++e) { F.so0t[e * S + k] = t[e]; }
+#if SCG_SW_SHARE
+#pragma unroll
+    for (int e = 0; e < ND + 2; ++e) { F.sw[e * S + k] = u[e] + (F.dt * 0.5) * t[e]; }
+#endif
 #if SCG_JS_SHARE
     {
         JacoS<ND> Q;
@@ -1068,6 +1076,10 @@ __global__ void __launch_bounds__(128) md_bc_dsoln_kernel(MdField const F, BcDev
         solt_row<ND>(J, gj, t);
 #pragma unroll
         for (int e = 0; e < NEQ; ++e) { F.so0t_next[e * S + jcl] = t[e]; }
+#if SCG_SW_SHARE
+#pragma unroll
+        for (int e = 0; e < NEQ; ++e) { F.sw_next[e * S + jcl] = u[e] + (F.dt * 0.5) * t[e]; }
+#endif
 #if SCG_JS_SHARE
         {
             JacoS<ND> Q;
@@ -1324,7 +1336,7 @@ struct scg_md
     int ndim = 0, neq = 0;
     double dt = 0, sigma0 = 3.0, taumin = 0.0, tauscale = 1.0; // euler.hpp:184-188
     int cur = 0;                                               // so0[cur] is so0c, so0[1-cur] is so0n
-    DevBuf<double> so0[2], so1[2], so0t[2], js[2], gamma, cflo, cflc, solpt, geo, eraw, stage, red, clvol;
+    DevBuf<double> so0[2], so1[2], so0t[2], sw[2], js[2], gamma, cflo, cflc, solpt, geo, eraw, stage, red, clvol;
     // fused calc_solt (march mode 3): so0t[tcur] belongs to the current so0c/so1c; while a substep runs, its gradient
     // kernels fill so0t[1 - tcur] for the next one.  so0t_valid: so0t[1 - tcur] is complete for every covered row
     // (owned body cells and ghost rows with a boundary condition); solt_rows lists the others.
@@ -1372,7 +1384,9 @@ MdField field_of(scg_md * s)
     F.so1n = s->so1[1 - s->cur].p;
     F.so0t = s->so0t[s->tcur].p;
     F.so0t_next = s->so0t[1 - s->tcur].p;
-    F.js = s->js[s->tcur].p; // same life cycle as so0t: same producers, same buffer flip
+    F.sw = s->sw[s->tcur].p; // same life cycle as so0t: same producers, same buffer flip
+    F.sw_next = s->sw[1 - s->tcur].p;
+    F.js = s->js[s->tcur].p;
     F.js_next = s->js[1 - s->tcur].p;
     F.fuse_solt = s->fuse_now ? 1 : 0;
     F.gamma = s->gamma.p;
@@ -1890,6 +1904,8 @@ int scg_md_create(scg_md ** out, scg_mesh * mesh, double time_increment)
     }
     z(s->so0t[0], S * neq);
     z(s->so0t[1], S * neq);
+    z(s->sw[0], SCG_SW_SHARE ? S * neq : 1);
+    z(s->sw[1], SCG_SW_SHARE ? S * neq : 1);
     z(s->js[0], SCG_JS_SHARE ? S * (2 * nd + 3) : 1);
     z(s->js[1], SCG_JS_SHARE ? S * (2 * nd + 3) : 1);
     z(s->gamma, S);
@@ -1945,6 +1961,7 @@ int scg_md_set_params(scg_md * s, double sigma0, double taumin, double tauscale)
 int scg_md_set_time_increment(scg_md * s, double time_increment)
 {
     SCG_REQUIRE(s, "scg_md_set_time_increment: null solver");
+    if (time_increment != s->dt) { s->so0t_valid = false; } // the carried so0c + hdt * so0t (MdField::sw) was formed with the old step
     s->dt = time_increment;
     return 0;
 }

@@ -33,6 +33,8 @@ struct MdField // by value to every kernel
     double * so0n;
     double * so0t;
     double * so0t_next; // fused calc_solt: so0t of the NEXT substep, written by the dsoln / bc_dsoln kernels
+    double * sw;        // [neq][stride] so0c + hdt * so0t of every row (SCG_SW_SHARE): what calc_dsoln needs of a neighbour's so0c and
+    double * sw_next;   // so0t, formed once by the producer of so0t instead of being gathered as two values per face and equation
     double * js;        // [2*ndim+3][stride] the quotients of EulerJacobian::update of every row's so0c (see JacoS::pack);
     double * js_next;   // produced wherever so0t / so0t_next is, consumed by md_solncfl_staged instead of redoing them per face
     double * so1c;
@@ -70,6 +72,10 @@ __device__ __forceinline__ void prefetch_l2(void const * p) { asm volatile("pref
 // (grad*grad is +0 either way; o[d] starts at +0 and +0 + (+-0) is +0, x + (+-0) is x)
 #ifndef SCG_EQO_ZERO
 #define SCG_EQO_ZERO 2
+#endif
+
+#ifndef SCG_SW_SHARE
+#define SCG_SW_SHARE 1 // md_dsoln_eqo gathers so0c + hdt*so0t (MdField::sw) as one value instead of its two terms
 #endif
 
 #ifndef SCG_JS_SHARE
@@ -1766,7 +1772,11 @@ struct EqoGather
     static constexpr int ND = ct_ndim(TYPE);
     static constexpr int NFC = ct_nfc(TYPE);
     double un;
+#if SCG_SW_SHARE
+    double u[NFC], g[NFC][ND];
+#else
     double u[NFC], t[NFC], g[NFC][ND];
+#endif
     __device__ __forceinline__ void load(MdField const & F, int32_t const (&rcl)[NFC], int64_t k, int e)
     {
         int64_t const S = F.S;
@@ -1775,8 +1785,12 @@ struct EqoGather
         for (int f = 0; f < NFC; ++f)
         {
             int64_t const j = rcl[f];
+#if SCG_SW_SHARE
+            u[f] = F.sw[e * S + j]; // so0c + hdt * so0t, the first operation of the Taylor difference (euler_gradient.cpp:66)
+#else
             u[f] = F.so0c[e * S + j];
             t[f] = F.so0t[e * S + j];
+#endif
 #pragma unroll
             for (int d = 0; d < ND; ++d) { g[f][d] = F.so1c[(e * ND + d) * S + j]; }
         }
@@ -1956,7 +1970,11 @@ __device__ __forceinline__ void cell_dsoln_eqo(MdField const & F, MdGeo const & 
 #pragma unroll
         for (int f = 0; f < NFC; ++f)
         {
+#if SCG_SW_SHARE
+            double val = cur.u[f] - cur.un;
+#else
             double val = cur.u[f] + hdt * cur.t[f] - cur.un;
+#endif
 #pragma unroll
             for (int d = 0; d < ND; ++d) { val += jdis[f][d] * cur.g[f][d]; }
             udf[f] = val;
@@ -2010,6 +2028,10 @@ __device__ __forceinline__ void cell_dsoln_eqo(MdField const & F, MdGeo const & 
         solt_row<ND>(J, g, t);
 #pragma unroll
         for (int e = 0; e < NEQ; ++e) { F.so0t_next[e * S + k] = t[e]; }
+#if SCG_SW_SHARE
+#pragma unroll
+        for (int e = 0; e < NEQ; ++e) { F.sw_next[e * S + k] = u[e] + (F.dt * 0.5) * t[e]; }
+#endif
 #if SCG_JS_SHARE
         {
             JacoS<ND> Q;
@@ -2465,6 +2487,10 @@ __device__ __forceinline__ void cell_dsoln_eqo2(MdField const & F, MdGeo const &
         solt_row<ND>(J, g, t);
 #pragma unroll
         for (int e = 0; e < NEQ; ++e) { F.so0t_next[e * S + k] = t[e]; }
+#if SCG_SW_SHARE
+#pragma unroll
+        for (int e = 0; e < NEQ; ++e) { F.sw_next[e * S + k] = u[e] + (F.dt * 0.5) * t[e]; }
+#endif
 #if SCG_JS_SHARE
         {
             JacoS<ND> Q;
