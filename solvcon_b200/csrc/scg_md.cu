@@ -199,6 +199,10 @@ __global__ void __launch_bounds__(256) md_solt_kernel(MdField const F, int32_t r
 #pragma unroll
     for (int e = 0; e < ND + 2; ++e) { F.sw[e * S + k] = u[e] + (F.dt * 0.5) * t[e]; }
 #endif
+#if SCG_CT_PAIR
+#pragma unroll
+    for (int e = 0; e < ND + 2; ++e) { F.ct[e * S + k] = make_double2(u[e], t[e]); }
+#endif
 #if SCG_JS_SHARE
     {
         JacoS<ND> Q;
@@ -233,6 +237,10 @@ __global__ void __launch_bounds__(256) md_solt_rows_kernel(MdField const F, int3
 #if SCG_SW_SHARE
 #pragma unroll
     for (int e = 0; e < ND + 2; ++e) { F.sw[e * S + k] = u[e] + (F.dt * 0.5) * t[e]; }
+#endif
+#if SCG_CT_PAIR
+#pragma unroll
+    for (int e = 0; e < ND + 2; ++e) { F.ct[e * S + k] = make_double2(u[e], t[e]); }
 #endif
 #if SCG_JS_SHARE
     {
@@ -1080,6 +1088,10 @@ __global__ void __launch_bounds__(128) md_bc_dsoln_kernel(MdField const F, BcDev
 #pragma unroll
         for (int e = 0; e < NEQ; ++e) { F.sw_next[e * S + jcl] = u[e] + (F.dt * 0.5) * t[e]; }
 #endif
+#if SCG_CT_PAIR
+#pragma unroll
+        for (int e = 0; e < NEQ; ++e) { F.ct_next[e * S + jcl] = make_double2(u[e], t[e]); }
+#endif
 #if SCG_JS_SHARE
         {
             JacoS<ND> Q;
@@ -1336,7 +1348,7 @@ struct scg_md
     int ndim = 0, neq = 0;
     double dt = 0, sigma0 = 3.0, taumin = 0.0, tauscale = 1.0; // euler.hpp:184-188
     int cur = 0;                                               // so0[cur] is so0c, so0[1-cur] is so0n
-    DevBuf<double> so0[2], so1[2], so0t[2], sw[2], js[2], gamma, cflo, cflc, solpt, geo, eraw, stage, red, clvol;
+    DevBuf<double> so0[2], so1[2], so0t[2], sw[2], ct[2], js[2], gamma, cflo, cflc, solpt, geo, eraw, stage, red, clvol;
     // fused calc_solt (march mode 3): so0t[tcur] belongs to the current so0c/so1c; while a substep runs, its gradient
     // kernels fill so0t[1 - tcur] for the next one.  so0t_valid: so0t[1 - tcur] is complete for every covered row
     // (owned body cells and ghost rows with a boundary condition); solt_rows lists the others.
@@ -1386,6 +1398,8 @@ MdField field_of(scg_md * s)
     F.so0t_next = s->so0t[1 - s->tcur].p;
     F.sw = s->sw[s->tcur].p; // same life cycle as so0t: same producers, same buffer flip
     F.sw_next = s->sw[1 - s->tcur].p;
+    F.ct = reinterpret_cast<double2 *>(s->ct[s->tcur].p);
+    F.ct_next = reinterpret_cast<double2 *>(s->ct[1 - s->tcur].p);
     F.js = s->js[s->tcur].p;
     F.js_next = s->js[1 - s->tcur].p;
     F.fuse_solt = s->fuse_now ? 1 : 0;
@@ -1906,6 +1920,8 @@ int scg_md_create(scg_md ** out, scg_mesh * mesh, double time_increment)
     z(s->so0t[1], S * neq);
     z(s->sw[0], SCG_SW_SHARE ? S * neq : 1);
     z(s->sw[1], SCG_SW_SHARE ? S * neq : 1);
+    z(s->ct[0], SCG_CT_PAIR ? S * neq * 2 : 2);
+    z(s->ct[1], SCG_CT_PAIR ? S * neq * 2 : 2);
     z(s->js[0], SCG_JS_SHARE ? S * (2 * nd + 3) : 1);
     z(s->js[1], SCG_JS_SHARE ? S * (2 * nd + 3) : 1);
     z(s->gamma, S);

@@ -35,6 +35,8 @@ struct MdField // by value to every kernel
     double * so0t_next; // fused calc_solt: so0t of the NEXT substep, written by the dsoln / bc_dsoln kernels
     double * sw;        // [neq][stride] so0c + hdt * so0t of every row (SCG_SW_SHARE): what calc_dsoln needs of a neighbour's so0c and
     double * sw_next;   // so0t, formed once by the producer of so0t instead of being gathered as two values per face and equation
+    double2 * ct;       // [neq][stride] {so0c, so0t} of every row side by side (SCG_CT_PAIR): md_solncfl_staged gathers both with
+    double2 * ct_next;  // ONE 16-byte copy per equation instead of two 8-byte ones; produced wherever so0t / so0t_next is
     double * js;        // [2*ndim+3][stride] the quotients of EulerJacobian::update of every row's so0c (see JacoS::pack);
     double * js_next;   // produced wherever so0t / so0t_next is, consumed by md_solncfl_staged instead of redoing them per face
     double * so1c;
@@ -76,6 +78,11 @@ __device__ __forceinline__ void prefetch_l2(void const * p) { asm volatile("pref
 
 #ifndef SCG_SW_SHARE
 #define SCG_SW_SHARE 1 // md_dsoln_eqo gathers so0c + hdt*so0t (MdField::sw) as one value instead of its two terms
+#endif
+
+#ifndef SCG_CT_PAIR
+#define SCG_CT_PAIR 0 // 1: md_solncfl_staged gathers {so0c, so0t} of the neighbour as 16-byte pairs (MdField::ct).  Bit-equal; soln 1-4 %
+                      // faster, but the producers' extra 16-byte stores take it back: 3D +0.4 %, 2D -1.7 % (profiles/README.md)
 #endif
 
 #ifndef SCG_JS_SHARE
@@ -663,6 +670,12 @@ __device__ __forceinline__ void cp_async16(double * smem_dst, double const * gsr
     unsigned const d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 }
+// 16 bytes through L1 (.ca): a gathered pair
+__device__ __forceinline__ void cp_async16_ca(double * smem_dst, void const * gsrc)
+{
+    unsigned const d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 // Ask L2 for the line holding *p: no register, no scoreboard.  Used for data THIS thread reads a few microseconds
 // later (later faces / later equations of its own cell), so that the staged copies and gathers meet L2 instead of HBM.
@@ -947,8 +960,12 @@ __device__ __forceinline__ void soln_stage_issue_an(MdField const & F, MdGeo con
 #pragma unroll
     for (int e = 0; e < NEQ; ++e)
     {
+#if SCG_CT_PAIR
+        cp_async16_ca(st + (L::R_JU + 2 * e) * TB + threadIdx.x, &F.ct[e * S + j]); // this thread's pair e of the 2*NEQ rows R_JU..
+#else
         cp_async8(st + (L::R_JU + e) * TB, &F.so0c[e * S + j]);
         cp_async8(st + (L::R_JT + e) * TB, &F.so0t[e * S + j]);
+#endif
 #pragma unroll
         for (int d = 0; d < ND; ++d) { cp_async8(st + (L::R_JG + e * ND + d) * TB, &F.so1c[(e * ND + d) * S + j]); }
     }
@@ -1068,8 +1085,14 @@ __device__ __forceinline__ void cell_soln_staged(MdField const & F, MdGeo const 
 #pragma unroll
             for (int e = 0; e < NEQ; ++e)
             {
+#if SCG_CT_PAIR
+                double2 const p = *reinterpret_cast<double2 const *>(st + (L::R_JU + 2 * e) * TB + threadIdx.x);
+                ju[e] = p.x;
+                jt[e] = p.y;
+#else
                 ju[e] = st[(L::R_JU + e) * TB];
                 jt[e] = st[(L::R_JT + e) * TB];
+#endif
 #pragma unroll
                 for (int d = 0; d < ND; ++d) { jg[e][d] = st[(L::R_JG + e * ND + d) * TB]; }
             }
@@ -1174,8 +1197,12 @@ __device__ __forceinline__ void soln_stage_issue_n(MdField const & F, int64_t j,
 #pragma unroll
     for (int e = 0; e < NEQ; ++e)
     {
+#if SCG_CT_PAIR
+        cp_async16_ca(st + (L::R_JU + 2 * e) * TB + threadIdx.x, &F.ct[e * S + j]); // this thread's pair e of the 2*NEQ rows R_JU..
+#else
         cp_async8(st + (L::R_JU + e) * TB, &F.so0c[e * S + j]);
         cp_async8(st + (L::R_JT + e) * TB, &F.so0t[e * S + j]);
+#endif
 #pragma unroll
         for (int d = 0; d < ND; ++d) { cp_async8(st + (L::R_JG + e * ND + d) * TB, &F.so1c[(e * ND + d) * S + j]); }
     }
@@ -1363,8 +1390,14 @@ __device__ __forceinline__ void cell_soln_staged_bulk(MdField const & F, MdGeo c
 #pragma unroll
             for (int e = 0; e < NEQ; ++e)
             {
+#if SCG_CT_PAIR
+                double2 const p = *reinterpret_cast<double2 const *>(st + (L::R_JU + 2 * e) * TB + threadIdx.x);
+                ju[e] = p.x;
+                jt[e] = p.y;
+#else
                 ju[e] = st[(L::R_JU + e) * TB];
                 jt[e] = st[(L::R_JT + e) * TB];
+#endif
 #pragma unroll
                 for (int d = 0; d < ND; ++d) { jg[e][d] = st[(L::R_JG + e * ND + d) * TB]; }
             }
@@ -2032,6 +2065,10 @@ __device__ __forceinline__ void cell_dsoln_eqo(MdField const & F, MdGeo const & 
 #pragma unroll
         for (int e = 0; e < NEQ; ++e) { F.sw_next[e * S + k] = u[e] + (F.dt * 0.5) * t[e]; }
 #endif
+#if SCG_CT_PAIR
+#pragma unroll
+        for (int e = 0; e < NEQ; ++e) { F.ct_next[e * S + k] = make_double2(u[e], t[e]); }
+#endif
 #if SCG_JS_SHARE
         {
             JacoS<ND> Q;
@@ -2490,6 +2527,10 @@ __device__ __forceinline__ void cell_dsoln_eqo2(MdField const & F, MdGeo const &
 #if SCG_SW_SHARE
 #pragma unroll
         for (int e = 0; e < NEQ; ++e) { F.sw_next[e * S + k] = u[e] + (F.dt * 0.5) * t[e]; }
+#endif
+#if SCG_CT_PAIR
+#pragma unroll
+        for (int e = 0; e < NEQ; ++e) { F.ct_next[e * S + k] = make_double2(u[e], t[e]); }
 #endif
 #if SCG_JS_SHARE
         {
