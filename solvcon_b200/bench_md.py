@@ -408,11 +408,12 @@ class MD3DWorkload:
     def health(self):
         return field_health(self.dev)
 
-    # fp64-pipe warp-instruction lanes one cell-substep executes in the default kernels, from the committed dynamic
-    # instruction mix (profiles/r01g_sass_mix.txt: executed instructions per cell x share issued to the fp64 pipe,
-    # md_solncfl_staged + md_dsoln_eqo): hex 7.78k*0.651 + 7.84k*0.512, tet 4.57k*0.610 + 4.51k*0.505, prism
-    # 6.84k*0.620 + 6.20k*0.506.  The arithmetic is the reference's, operation for operation (no FMA contraction).
-    FP64_INSTR_PER_CELL = {"hex": 9080.0, "tet": 5070.0, "prism": 7380.0}
+    # fp64-pipe instructions one cell-substep executes in the default kernels, from the committed ncu --set full capture
+    # of the round (profiles/r02g_md3d_ncu_full_summary.txt: executed warp instructions x the share issued to the fp64
+    # pipe = inst_executed * (pipe_fp64 % / 2) / issue_active %, md_solncfl_staged + md_dsoln_eqo, per 6.666e5 cells):
+    # hex 4852 + 3528, tet 2670 + 2017, prism 4069 + 2894 (round 1: 9080 / 5070 / 7380).  The arithmetic is the
+    # reference's, operation for operation (no FMA contraction).
+    FP64_INSTR_PER_CELL = {"hex": 8380.0, "tet": 4687.0, "prism": 6963.0}
 
     def roofline_fp64(self, substep_s, clocks):
         """Second roofline of the 3D march: the fp64 pipe.  B200 issues 64 fp64 lanes per SM per clock (16 per
@@ -428,7 +429,7 @@ class MD3DWorkload:
         fmeas = (clocks.get("sm_mhz") or 0.0) * 1e6
         floor_max = lanes / (sm * 64.0 * fmax)
         out = {"bound": "fp64 pipe (64 lanes/clk/SM)", "fp64_instr_per_cell": self.FP64_INSTR_PER_CELL,
-               "source": "profiles/r01g_sass_mix.txt (dynamic mix of the ncu --set full capture)",
+               "source": "profiles/r02g_md3d_ncu_full_summary.txt (ncu --set full: executed instructions x fp64-pipe share)",
                "floor_substep_ms_at_max_clock": floor_max * 1e3,
                "ceiling_updates_per_s_at_max_clock": self.ncell / floor_max,
                "frac_of_ceiling_at_max_clock": floor_max / substep_s,
