@@ -3,6 +3,7 @@
 //
 // Device twin of solvcon::EulerCore (cpp/solvcon/multidim/euler.hpp:56-211).
 #include "scg_md_kernels.cuh"
+#include "scg_md_pair.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -306,7 +307,7 @@ __global__ void __launch_bounds__(128) md_dsoln_kernel(MdField const F, MdGeo co
 // phases only couple through the cell's own so0n (SURVEY.md 8a hazard 2), so no grid-wide sync is
 // needed.  Ghost cells must see the energy BEFORE calc_cfl's fix-up (hazard 1: bc_soln runs between
 // calc_soln and calc_cfl, euler_march.cpp:343-345); cells beside a ghost therefore park that raw
-// energy in eraw[ghost] for the boundary kernel.
+// energy in eraw[cell] for the boundary kernel (one slot per body cell: the writer needs no neighbour index).
 template <int TYPE>
 __global__ void __launch_bounds__(128) md_substep_kernel(MdField const F, MdGeo const G, double * eraw)
 {
@@ -319,11 +320,11 @@ __global__ void __launch_bounds__(128) md_substep_kernel(MdField const F, MdGeo 
     int64_t const S = F.S;
     double un[NEQ];
     cell_soln<TYPE>(F, G, i, un);
-#pragma unroll
-    for (int f = 0; f < NFC; ++f)
     {
-        int32_t const j = G.nbr[f * int64_t(G.n) + i];
-        if (j >= F.ncell) { eraw[j - F.ncell] = un[NEQ - 1]; }
+        bool beside_ghost = false;
+#pragma unroll
+        for (int f = 0; f < NFC; ++f) { beside_ghost = beside_ghost || (G.nbr[f * int64_t(G.n) + i] >= F.ncell); }
+        if (beside_ghost) { eraw[k] = un[NEQ - 1]; }
     }
     double cflo, cflc;
     cell_cfl<TYPE>(F, G, i, un, cflo, cflc);
@@ -363,11 +364,11 @@ __global__ void __launch_bounds__(128, SCG_SOLN_MINBLOCKS) md_solncfl_kernel(MdF
 #else
     cell_soln<TYPE>(F, G, i, un);
 #endif
-#pragma unroll
-    for (int f = 0; f < NFC; ++f)
     {
-        int32_t const j = G.nbr[f * int64_t(G.n) + i];
-        if (j >= F.ncell) { eraw[j - F.ncell] = un[NEQ - 1]; }
+        bool beside_ghost = false;
+#pragma unroll
+        for (int f = 0; f < NFC; ++f) { beside_ghost = beside_ghost || (G.nbr[f * int64_t(G.n) + i] >= F.ncell); }
+        if (beside_ghost) { eraw[k] = un[NEQ - 1]; }
     }
     double cflo, cflc;
     cell_cfl<TYPE>(F, G, i, un, cflo, cflc);
@@ -483,17 +484,9 @@ __global__ void __launch_bounds__(StagedCfg<TYPE>::TB, StagedCfg<TYPE>::MB) md_s
             dist = (r < dist) ? r : dist;
         }
     }
-    if (jmax >= F.ncell)
-    {
-#pragma unroll
-        for (int f = 0; f < NFC; ++f)
-        {
-            int32_t const j = G.nbr[f * int64_t(G.n) + i];
-            if (j >= F.ncell) { eraw[j - F.ncell] = un[NEQ - 1]; }
-        }
-    }
+    if (jmax >= F.ncell) { eraw[k] = un[NEQ - 1]; } // beside a ghost: park the energy calc_cfl has not fixed yet for md_bc_soln
     double cflo, cflc;
-    cfl_from_dist<ND>(F.dt / 2.0, F.gamma[k], dist, un, cflo, cflc);
+    cfl_from_dist<ND>(F.dt / 2.0, (soln_early(TYPE) ? stage_smem[SolnStage<TYPE, TB>::R_GK * TB + threadIdx.x] : F.gamma[k]), dist, un, cflo, cflc);
     F.cflo[k] = cflo;
     F.cflc[k] = cflc;
 #pragma unroll
@@ -535,9 +528,10 @@ __global__ void __launch_bounds__(StagedCfg<TYPE>::TB, StagedCfg<TYPE>::MB) md_s
 template <int TYPE>
 struct EqoCfg
 {
-    // prefetch the next equation's neighbour gather into registers
-    static constexpr bool PF = (TYPE == CT_HEX) ? SCG_EQO_PF_HEX : (TYPE == CT_PRISM || TYPE == CT_PYRAMID) ? SCG_EQO_PF_PRISM
-                             : (TYPE == CT_TET) ? SCG_EQO_PF_TET : SCG_EQO_PF_2D;
+    // prefetch of the next equation's neighbour gather: 0 none, 1 at the top of the previous equation into a second register set,
+    // 2 in the middle of the previous equation into the same registers (cell_dsoln_eqo)
+    static constexpr int PF = (TYPE == CT_HEX) ? SCG_EQO_PF_HEX : (TYPE == CT_PRISM || TYPE == CT_PYRAMID) ? SCG_EQO_PF_PRISM
+                            : (TYPE == CT_TET) ? SCG_EQO_PF_TET : SCG_EQO_PF_2D;
     static constexpr int TB = SCG_EQO_TB;
     // resident CTAs per SM the register budget is sized for (shared memory allows at least as many)
     static constexpr int MB = (TYPE == CT_HEX) ? SCG_EQO_MB_HEX
@@ -553,6 +547,45 @@ __global__ void __launch_bounds__(EqoCfg<TYPE>::TB, EqoCfg<TYPE>::MB) md_dsoln_e
     int32_t const i = G.ibeg + blockIdx.x * EqoCfg<TYPE>::TB + threadIdx.x;
     if (i >= G.iend) { return; }
     cell_dsoln_eqo<TYPE, EqoCfg<TYPE>::TB, EqoCfg<TYPE>::PF>(F, G, i, eqo_smem + threadIdx.x);
+}
+
+// the same phase with two lanes per cell (cell_dsoln_eqo_pair, scg_md_pair.cuh): hexahedra and prisms
+#ifndef SCG_PAIR_TB
+#define SCG_PAIR_TB 64
+#endif
+#ifndef SCG_PAIR_MB_HEX
+#define SCG_PAIR_MB_HEX 6
+#endif
+#ifndef SCG_PAIR_MB_PRISM
+#define SCG_PAIR_MB_PRISM 6
+#endif
+#ifndef SCG_PAIR_PF_HEX
+#define SCG_PAIR_PF_HEX 1
+#endif
+#ifndef SCG_PAIR_PF_PRISM
+#define SCG_PAIR_PF_PRISM 1
+#endif
+template <int TYPE>
+struct PairCfg
+{
+    static constexpr bool ON = (TYPE == CT_HEX || TYPE == CT_PRISM) && (0 != (SCG_EQO_PAIR_MASK & (1 << (TYPE - CT_HEX))));
+    static constexpr int TYPEP = (TYPE == CT_PRISM) ? CT_PRISM : CT_HEX; // the other types never instantiate the body
+    static constexpr int TB = SCG_PAIR_TB;
+    static constexpr int MB = (TYPE == CT_PRISM) ? SCG_PAIR_MB_PRISM : SCG_PAIR_MB_HEX;
+    static constexpr bool PF = (TYPE == CT_PRISM) ? SCG_PAIR_PF_PRISM : SCG_PAIR_PF_HEX;
+};
+
+template <int TYPE>
+__global__ void __launch_bounds__(PairCfg<TYPE>::TB, PairCfg<TYPE>::MB) md_dsoln_eqo_pair_kernel(MdField const F, MdGeo const G)
+{
+    extern __shared__ double eqo_smem[];
+    constexpr int TB = PairCfg<TYPE>::TB;
+    int const lane = threadIdx.x & 31;
+    // a warp marches 16 cells: lanes l and l ^ 16 share cell (l & 15)
+    int32_t const i_raw = G.ibeg + (blockIdx.x * (TB / 32) + (threadIdx.x >> 5)) * 16 + (lane & 15);
+    if (i_raw - (lane & 15) >= G.iend) { return; } // the whole warp is past the range
+    bool const active = i_raw < G.iend;
+    cell_dsoln_eqo_pair<TYPE, TB, PairCfg<TYPE>::PF>(F, G, active ? i_raw : G.iend - 1, lane >= 16, active, eqo_smem + threadIdx.x);
 }
 
 // second generation of the same phase for the 3D cell types (cell_dsoln_eqo2): every global load before the equation loop
@@ -928,7 +961,7 @@ __device__ __forceinline__ void matmat(double const (&a)[ND][ND], double const (
     }
 }
 
-// bc_soln_impl, euler_bc.cpp:143-215.  USE_ERAW: take the interior energy from eraw[ghost] (fused march).
+// bc_soln_impl, euler_bc.cpp:143-215.  USE_ERAW: take the interior energy from eraw[interior cell] (fused march).
 template <int ND, bool USE_ERAW>
 __global__ void __launch_bounds__(128) md_bc_soln_kernel(MdField const F, BcDev const B, double const * eraw)
 {
@@ -942,7 +975,7 @@ __global__ void __launch_bounds__(128) md_bc_soln_kernel(MdField const F, BcDev 
     double ui[NEQ], uj[NEQ];
 #pragma unroll
     for (int e = 0; e < NEQ; ++e) { ui[e] = F.so0n[e * S + icl]; }
-    if (USE_ERAW) { ui[NEQ - 1] = eraw[jcl - F.ncell]; }
+    if (USE_ERAW) { ui[NEQ - 1] = eraw[icl]; }
     if (SCG_BC_NONREFL == kind)
     {
 #pragma unroll
@@ -1510,6 +1543,20 @@ void launch_cell_phase_t(scg_md * s, MeshGroup const & g, CellPhase ph, int part
     }
     case CP_DSOLN_EQO:
     {
+        if constexpr (PairCfg<TYPE>::ON)
+        {
+            constexpr int TYPEP = PairCfg<TYPE>::TYPEP;
+            constexpr int TBP = PairCfg<TYPE>::TB;
+            constexpr int BYTESP = EqoPair<TYPEP>::template bytes<TBP>();
+            static bool attrp_set = false;
+            if (!attrp_set)
+            {
+                cudaFuncSetAttribute(md_dsoln_eqo_pair_kernel<TYPEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, BYTESP);
+                attrp_set = true;
+            }
+            md_dsoln_eqo_pair_kernel<TYPEP><<<static_cast<unsigned>(ceil_div(ncl, TBP / 2)), TBP, BYTESP, stream()>>>(F, G);
+            break;
+        }
         if constexpr (Eqo2Cfg<TYPE>::ON)
         {
             constexpr int TB2 = Eqo2Cfg<TYPE>::TB;
@@ -1929,7 +1976,7 @@ int scg_md_create(scg_md ** out, scg_mesh * mesh, double time_increment)
     z(s->cflc, S);
     z(s->solpt, S * nd);
     z(s->geo, mesh->geo_total);
-    z(s->eraw, mesh->ngstcell > 0 ? mesh->ngstcell : 1);
+    z(s->eraw, mesh->ncell > 0 ? mesh->ncell : 1); // one slot per body cell, written by the cells beside a ghost
     ok = ok && cudaSuccess == s->stage.alloc(STAGE_DOUBLES) && cudaSuccess == s->red.alloc(3 * 1024);
     if (!ok)
     {

@@ -103,6 +103,64 @@ __device__ __forceinline__ void prefetch_l2(void const * p) { asm volatile("pref
 #define SCG_SOLN_PREFETCH 0
 #endif
 
+#ifndef SCG_SOLN_EARLY
+#define SCG_SOLN_EARLY 0x34 // cell types (bit t - CT_QUAD; default hex, prism, pyramid) whose md_solncfl_staged copies the two values only the
+                            // epilogue needs (cevol[0] and gamma of the cell) with the first staged group instead of loading them -- and
+                            // waiting one exposed DRAM round trip -- after the face loop
+#endif
+__host__ __device__ constexpr bool soln_early(int type) { return 0 != ((SCG_SOLN_EARLY >> (type - CT_QUAD)) & 1); }
+
+#ifndef SCG_EQO_SOLT_PF
+#define SCG_EQO_SOLT_PF 0 // md_dsoln_eqo with register prefetch: the inputs of the fused calc_solt are loaded at the top of the LAST equation
+                          // into the registers of the (then idle) gather prefetch instead of after the loop
+#endif
+
+#ifndef SCG_EQO_RCL_SMEM
+#define SCG_EQO_RCL_SMEM 0x0f // cell types (bit t - CT_QUAD; all but prisms / pyramids, whose gathers want the L1 more) whose md_dsoln_eqo keeps the neighbour indices in shared memory during the equation
+                              // loop.  In registers ptxas hoists the loop-invariant gather offsets out of the loop and spills them: every
+                              // equation then starts with a local-memory reload whose L1 lines the gathers have evicted, and only then can
+                              // the gathers be issued (profiles/r02g: 12-25 % of the samples of the 3D kernels sit on those two waits)
+#endif
+__host__ __device__ constexpr int eqo_rcl_smem(int type) { return (SCG_EQO_RCL_SMEM >> (type - CT_QUAD)) & 1; }
+
+// Two more ways of taking loop-invariant values of md_dsoln_eqo's equation loop out of the register file (what does not fit is
+// spilled by ptxas and reloaded through L1 at the top of every equation): sigma0 / |cfl| in one shared-memory row, and the
+// displacement vectors jdis of the LAST faces in three rows per face.
+#ifndef SCG_EQO_SGM_SMEM
+#define SCG_EQO_SGM_SMEM 0x08 // cell types (bit t - CT_QUAD): tetrahedra
+#endif
+#ifndef SCG_EQO_JF_HEX
+#define SCG_EQO_JF_HEX 0
+#endif
+#ifndef SCG_EQO_JF_TET
+#define SCG_EQO_JF_TET 0
+#endif
+#ifndef SCG_EQO_JF_PRISM
+#define SCG_EQO_JF_PRISM 0
+#endif
+__host__ __device__ constexpr int eqo_sgm_smem(int type) { return (SCG_EQO_SGM_SMEM >> (type - CT_QUAD)) & 1; }
+__host__ __device__ constexpr int eqo_jdis_faces(int type)
+{
+    return (type == CT_HEX) ? SCG_EQO_JF_HEX : (type == CT_TET) ? SCG_EQO_JF_TET : (type == CT_PRISM || type == CT_PYRAMID) ? SCG_EQO_JF_PRISM : 0;
+}
+
+#ifndef SCG_EQO_OPAQUE_K
+#define SCG_EQO_OPAQUE_K 0x0f // cell types (bit t - CT_QUAD; all but prisms / pyramids) whose md_dsoln_eqo makes the row index opaque once per
+                              // equation: addresses derived from it are formed again (one IMAD each) instead of being hoisted out of the
+                              // loop as 64-bit loop invariants, which ptxas then spills
+#endif
+__host__ __device__ constexpr bool eqo_opaque_k(int type) { return 0 != ((SCG_EQO_OPAQUE_K >> (type - CT_QUAD)) & 1); }
+
+#ifndef SCG_EQO_GAMMA_PF
+#define SCG_EQO_GAMMA_PF 1 // md_dsoln_eqo without register prefetch: gamma of the cell (read by the fused calc_solt only) is requested into L2
+                           // at the top of the cell
+#endif
+
+#ifndef SCG_XCTA_PF
+#define SCG_XCTA_PF 0 // > 0: every CTA requests into L2 the streamed rows (neighbour indices, geometry) that the CTA SCG_XCTA_PF
+                      // blocks ahead will read first -- the blocks that replace the resident ones
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // flux function and Jacobian, detail::EulerJacobian<2>/<3>::update (euler_march.cpp:35-81, 94-157)
 // ------------------------------------------------------------------------------------------------
@@ -944,9 +1002,24 @@ struct SolnStage
     static constexpr int R_SC = R_VOL + 1;           // sfcnd[s][ND]
     // B
     static constexpr int R_SN = R_SC + MSF * ND;     // sfnml[s][ND]
-    static constexpr int ROWS = R_SN + MSF * ND;
+    // E (SCG_SOLN_EARLY): what only the epilogue reads, copied once with the first group
+    static constexpr int R_CV = R_SN + MSF * ND;     // cevol[0] of the cell
+    static constexpr int R_GK = R_CV + 1;            // gamma of the cell
+    static constexpr int ROWS = R_SN + MSF * ND + (soln_early(TYPE) ? 2 : 0);
     static constexpr int BYTES = ROWS * TB * int(sizeof(double));
 };
+
+// the epilogue's two values; joins the group the caller commits next
+template <int TYPE, int TB>
+__device__ __forceinline__ void soln_stage_issue_e(MdField const & F, MdGeo const & G, int64_t i, double * st)
+{
+    if constexpr (soln_early(TYPE))
+    {
+        using L = SolnStage<TYPE, TB>;
+        cp_async8(st + L::R_CV * TB, &G.cevol[i]);
+        cp_async8(st + L::R_GK * TB, &F.gamma[G.beg + i]);
+    }
+}
 
 template <int TYPE, int TB>
 __device__ __forceinline__ void soln_stage_issue_an(MdField const & F, MdGeo const & G, int64_t i, int64_t j, int f, double * st)
@@ -1023,6 +1096,7 @@ __device__ __forceinline__ void cell_soln_staged(MdField const & F, MdGeo const 
 
     int32_t jn = G.nbr[i];
     jmax = jn; // the largest neighbour index tells whether the cell touches a ghost
+    soln_stage_issue_e<TYPE, TB>(F, G, i, st);
     soln_stage_issue_an<TYPE, TB>(F, G, i, jn, 0, st);
     soln_stage_issue_b<TYPE, TB>(G, i, 0, st);
     jn = G.nbr[n + i]; // NFC >= 3
@@ -1173,7 +1247,7 @@ __device__ __forceinline__ void cell_soln_staged(MdField const & F, MdGeo const 
         if (NEQ > 4) { flux_row<ND, (NEQ > 4 ? 4 : 0), MSF>(JS, usfc, sn, hdt, nsf, acc[NEQ - 1]); }
     }
     if (d2min < CUDART_INF) { dist = sqrt_fast(d2min, dist_ok); } // no finite face distance: dist stays DBL_MAX like in the reference
-    double const cvol = G.cevol[i];
+    double const cvol = soln_early(TYPE) ? st[L::R_CV * TB] : G.cevol[i];
 #if SCG_SHARED_RCP
     DivBy<true> by_cvol(cvol);
 #pragma unroll
@@ -1344,6 +1418,7 @@ __device__ __forceinline__ void cell_soln_staged_bulk(MdField const & F, MdGeo c
     double * const wst = st - lane; // the warp's 32 columns of the staging buffer
     int32_t jn = G.nbr[i];
     jmax = jn; // the largest neighbour index tells whether the cell touches a ghost
+    soln_stage_issue_e<TYPE, TB>(F, G, i, st);
     if constexpr (2 == MODE)
     {
         soln_vec_issue_a<TYPE, TB>(G, iw0, 0, lane, wst);
@@ -1501,7 +1576,7 @@ __device__ __forceinline__ void cell_soln_staged_bulk(MdField const & F, MdGeo c
         if (NEQ > 4) { flux_row<ND, (NEQ > 4 ? 4 : 0), MSF>(JS, usfc, sn, hdt, nsf, acc[NEQ - 1]); }
     }
     if (d2min < CUDART_INF) { dist = sqrt_fast(d2min, dist_ok); } // no finite face distance: dist stays DBL_MAX like in the reference
-    double const cvol = G.cevol[i];
+    double const cvol = soln_early(TYPE) ? st[L::R_CV * TB] : G.cevol[i];
 #if SCG_SHARED_RCP
     DivBy<true> by_cvol(cvol);
 #pragma unroll
@@ -1719,16 +1794,27 @@ struct DsolnEqo
     // equation loop live on L1 (tetrahedra: 318 -> 452 us), so there it is read back from L2
     static constexpr bool G_IN_SMEM = (2 == ND) || (0 != (SCG_EQO_GSMEM_MASK & (1 << (TYPE - CT_HEX))));
     static constexpr int R_G = NFGE * RPF;
-    static constexpr int ROWS = R_G + (G_IN_SMEM ? (ND + 2) * ND : 0);
+    static constexpr int R_RCL = R_G + (G_IN_SMEM ? (ND + 2) * ND : 0); // neighbour indices: ct_nfc int32 rows (SCG_EQO_RCL_SMEM)
+    static constexpr int R_SG = R_RCL + (eqo_rcl_smem(TYPE) ? (ct_nfc(TYPE) + 1) / 2 : 0); // sigma0 / |cfl| (SCG_EQO_SGM_SMEM)
+    static constexpr int JF = eqo_jdis_faces(TYPE);                                        // faces whose jdis live in shared memory
+    static constexpr int R_JD = R_SG + eqo_sgm_smem(TYPE);                                 // jdis[NFC - JF ..][ND]
+    static constexpr int ROWS = R_JD + JF * ND;
     static constexpr int BYTES = ROWS * TB * int(sizeof(double));
 };
 
 // The arithmetic of one equation of calc_dsoln after the Taylor differences (euler_gradient.cpp:74-110):
 // the NFGE gradients, their W-1/2 weights normalised and shifted, and sigma_max.  FAST: see above;
 // returns whether every range test passed.
-template <int TYPE, int TB, bool FAST>
+struct EqoNoMid
+{
+    __device__ __forceinline__ void operator()() const {}
+};
+// `mid` runs right after the products adj(D) * udf: from there on the equation needs no gathered value, so the caller may
+// start the next equation's gather into the very registers the Taylor differences were formed from
+template <int TYPE, int TB, bool FAST, typename MID = EqoNoMid>
 __device__ __forceinline__ bool eqo_solve(double const * sadj, double const (&udf)[ct_nfc(TYPE)], double ofg1, double sgm0,
-                                          double (&grad)[ct_nfge(TYPE)][ct_ndim(TYPE)], double (&w)[ct_nfge(TYPE)], double & sigma_max)
+                                          double (&grad)[ct_nfge(TYPE)][ct_ndim(TYPE)], double (&w)[ct_nfge(TYPE)], double & sigma_max,
+                                          MID && mid = MID())
 {
     constexpr int ND = ct_ndim(TYPE);
     constexpr int NFGE = ct_nfge(TYPE);
@@ -1752,6 +1838,7 @@ __device__ __forceinline__ bool eqo_solve(double const * sadj, double const (&ud
             grad[ifge][a] = r;
         }
     }
+    mid();
 #pragma unroll
     for (int ifge = 0; ifge < NFGE; ++ifge)
     {
@@ -1830,9 +1917,13 @@ struct EqoGather
     }
 };
 
-template <int TYPE, int TB, bool PF>
+// PFM: how the neighbour gather of an equation is overlapped with arithmetic.  0: not at all (loaded at the top of its equation);
+// 1: loaded at the top of the PREVIOUS equation into a second register set; 2: loaded in the MIDDLE of the previous equation, right
+// after its products adj(D) * udf, into the same registers (no second set; ~60 % of an equation's arithmetic covers the latency)
+template <int TYPE, int TB, int PFM>
 __device__ __forceinline__ void cell_dsoln_eqo(MdField const & F, MdGeo const & G, int32_t i, double * sadj)
 {
+    constexpr bool PF = (1 == PFM);
     constexpr int ND = ct_ndim(TYPE);
     constexpr int NEQ = ND + 2;
     constexpr int NFC = ct_nfc(TYPE);
@@ -1841,6 +1932,7 @@ __device__ __forceinline__ void cell_dsoln_eqo(MdField const & F, MdGeo const & 
     int64_t const n = G.n;
     int64_t const S = F.S;
     int64_t const k = G.beg + i;
+    int64_t const k_cell = k;
     double const hdt = F.dt * 0.5;
     double const acfl = fabs(F.cflc[k]);
     double const sgm0 = F.sigma0 / acfl;
@@ -1848,8 +1940,14 @@ __device__ __forceinline__ void cell_dsoln_eqo(MdField const & F, MdGeo const & 
     double const ofg1 = 1.0 / NFGE;
 
     int32_t rcl[NFC];
+    // this thread's column of the int32 rows behind the double rows (SCG_EQO_RCL_SMEM)
+    int32_t * const srcl = reinterpret_cast<int32_t *>(sadj - threadIdx.x + DsolnEqo<TYPE, TB>::R_RCL * TB) + threadIdx.x;
     double jdis[NFC][ND];
     EqoGather<TYPE> cur;
+#if SCG_EQO_GAMMA_PF
+    // the fused calc_solt reads the cell's gamma after the equation loop -- the one line of its inputs nobody touched before
+    if (!(PF && SCG_EQO_SOLT_PF) && F.fuse_solt) { l2_prefetch(&F.gamma[k]); }
+#endif
     {
         // ---- gradient element geometry (GradientElement.cpp:137-213, :81-133)
         double icecnd[ND];
@@ -1858,7 +1956,12 @@ __device__ __forceinline__ void cell_dsoln_eqo(MdField const & F, MdGeo const & 
         double gp[NFC][ND];
 #pragma unroll
         for (int f = 0; f < NFC; ++f) { rcl[f] = G.nbr[f * n + i]; }
-        if (PF) { cur.load(F, rcl, k, 0); } // the first equation's gather travels while the geometry is worked out
+        if (eqo_rcl_smem(TYPE))
+        {
+#pragma unroll
+            for (int f = 0; f < NFC; ++f) { srcl[f * TB] = rcl[f]; }
+        }
+        if (0 != PFM) { cur.load(F, rcl, k, 0); } // the first equation's gather travels while the geometry is worked out
 #if SCG_EQO_L2PF
         // every later equation's gather is requested from HBM now; it is consumed e equations (microseconds) later
 #pragma unroll
@@ -1964,6 +2067,13 @@ __device__ __forceinline__ void cell_dsoln_eqo(MdField const & F, MdGeo const & 
                 gp[f][d] = gp[f][d] - cnd[d];
             }
         }
+        if (eqo_sgm_smem(TYPE)) { sadj[DsolnEqo<TYPE, TB>::R_SG * TB] = sgm0; }
+#pragma unroll
+        for (int f = NFC - DsolnEqo<TYPE, TB>::JF; f < NFC; ++f)
+        {
+#pragma unroll
+            for (int d = 0; d < ND; ++d) { sadj[(DsolnEqo<TYPE, TB>::R_JD + (f - (NFC - DsolnEqo<TYPE, TB>::JF)) * ND + d) * TB] = jdis[f][d]; }
+        }
         // ---- adj(D), det(D) of every gradient element -> shared memory
 #pragma unroll
         for (int ifge = 0; ifge < NFGE; ++ifge)
@@ -1989,6 +2099,9 @@ __device__ __forceinline__ void cell_dsoln_eqo(MdField const & F, MdGeo const & 
         }
     }
 
+    // the fused calc_solt's inputs ride in the prefetch registers of the last equation: needs a slot per equation in u[] / g[]
+    constexpr bool SOLT_PF = PF && SCG_EQO_SOLT_PF && !DsolnEqo<TYPE, TB>::G_IN_SMEM && NFC >= NEQ;
+    double olast[ND]; // the last equation's gradient (the others are read back)
     // ---- one equation at a time
 #pragma unroll 1
     for (int e = 0; e < NEQ; ++e)
@@ -1996,9 +2109,33 @@ __device__ __forceinline__ void cell_dsoln_eqo(MdField const & F, MdGeo const & 
         // adj/det are re-read from shared memory by every equation: without this barrier the compiler hoists
         // the NFGE*(ND*ND+1) loop-invariant loads out of the loop and spills them
         asm volatile("" ::: "memory");
+        if (eqo_rcl_smem(TYPE))
+        {
+#pragma unroll
+            for (int f = 0; f < NFC; ++f) { rcl[f] = srcl[f * TB]; }
+        }
+        int64_t k = k_cell; // see SCG_EQO_OPAQUE_K
+        if (eqo_opaque_k(TYPE)) { asm volatile("" : "+l"(k)); }
         EqoGather<TYPE> nxt;
-        if (PF) { nxt.load(F, rcl, k, e + 1 < NEQ ? e + 1 : e); }
-        else { cur.load(F, rcl, k, e); }
+        if (PF)
+        {
+            if (SOLT_PF && e + 1 == NEQ)
+            {
+                // nothing is left to gather: the prefetch registers take the inputs of the fused calc_solt -- the cell's so0n and
+                // gamma and the gradient rows this thread stored in the earlier iterations -- which travel during the last equation
+                nxt.un = F.gamma[k];
+#pragma unroll
+                for (int q = 0; q < NEQ; ++q) { nxt.u[q] = F.so0n[q * S + k]; }
+#pragma unroll
+                for (int q = 0; q < NEQ - 1; ++q)
+                {
+#pragma unroll
+                    for (int d = 0; d < ND; ++d) { nxt.g[q][d] = __ldcg(&F.so1n[(q * ND + d) * S + k]); }
+                }
+            }
+            else { nxt.load(F, rcl, k, e + 1 < NEQ ? e + 1 : e); }
+        }
+        else if (0 == PFM) { cur.load(F, rcl, k, e); }
         double udf[NFC];
 #pragma unroll
         for (int f = 0; f < NFC; ++f)
@@ -2009,7 +2146,12 @@ __device__ __forceinline__ void cell_dsoln_eqo(MdField const & F, MdGeo const & 
             double val = cur.u[f] + hdt * cur.t[f] - cur.un;
 #endif
 #pragma unroll
-            for (int d = 0; d < ND; ++d) { val += jdis[f][d] * cur.g[f][d]; }
+            for (int d = 0; d < ND; ++d)
+            {
+                double const jd = (f >= NFC - DsolnEqo<TYPE, TB>::JF) ? sadj[(DsolnEqo<TYPE, TB>::R_JD + (f - (NFC - DsolnEqo<TYPE, TB>::JF)) * ND + d) * TB]
+                                                                      : jdis[f][d];
+                val += jd * cur.g[f][d];
+            }
             udf[f] = val;
         }
         if (PF) { cur = nxt; }
@@ -2018,9 +2160,25 @@ __device__ __forceinline__ void cell_dsoln_eqo(MdField const & F, MdGeo const & 
         // every division, square root and reciprocal of the equation runs its inlined fast sequence with
         // the range tests collected in one flag, so the hot path is one basic block; when any test fails the
         // equation is redone with the plain operators (cold)
-        if (!eqo_solve<TYPE, TB, true>(sadj, udf, ofg1, sgm0, grad, w, sigma_max))
+        double const sg = eqo_sgm_smem(TYPE) ? sadj[DsolnEqo<TYPE, TB>::R_SG * TB] : sgm0;
+        auto mid = [&]() {
+            if (2 == PFM)
+            {
+                asm volatile("" ::: "memory"); // the gather is issued HERE, not hoisted to the top of the equation
+                if (e + 1 < NEQ)
+                {
+                    if (eqo_rcl_smem(TYPE))
+                    {
+#pragma unroll
+                        for (int f = 0; f < NFC; ++f) { rcl[f] = srcl[f * TB]; }
+                    }
+                    cur.load(F, rcl, k, e + 1);
+                }
+            }
+        };
+        if (!eqo_solve<TYPE, TB, true>(sadj, udf, ofg1, sg, grad, w, sigma_max, mid))
         {
-            eqo_solve<TYPE, TB, false>(sadj, udf, ofg1, sgm0, grad, w, sigma_max);
+            eqo_solve<TYPE, TB, false>(sadj, udf, ofg1, sg, grad, w, sigma_max);
         }
         double o[ND];
 #pragma unroll
@@ -2037,6 +2195,7 @@ __device__ __forceinline__ void cell_dsoln_eqo(MdField const & F, MdGeo const & 
         {
             F.so1n[(e * ND + d) * S + k] = o[d];
             if (DsolnEqo<TYPE, TB>::G_IN_SMEM) { sadj[(DsolnEqo<TYPE, TB>::R_G + e * ND + d) * TB] = o[d]; }
+            olast[d] = o[d];
         }
     }
     // ---- fused calc_solt of the NEXT substep (euler_march.cpp:161-191): this cell's so0n and so1n are final, and
@@ -2048,16 +2207,17 @@ __device__ __forceinline__ void cell_dsoln_eqo(MdField const & F, MdGeo const & 
 #pragma unroll
         for (int e = 0; e < NEQ; ++e)
         {
-            u[e] = F.so0n[e * S + k];
+            u[e] = SOLT_PF ? cur.u[e < NFC ? e : 0] : F.so0n[e * S + k];
 #pragma unroll
             for (int d = 0; d < ND; ++d)
             {
-                g[e][d] = DsolnEqo<TYPE, TB>::G_IN_SMEM ? sadj[(DsolnEqo<TYPE, TB>::R_G + e * ND + d) * TB]
-                                                        : __ldcg(&F.so1n[(e * ND + d) * S + k]);
+                g[e][d] = SOLT_PF ? (e + 1 < NEQ ? cur.g[e < NFC ? e : 0][d] : olast[d])
+                          : DsolnEqo<TYPE, TB>::G_IN_SMEM ? sadj[(DsolnEqo<TYPE, TB>::R_G + e * ND + d) * TB]
+                                                          : __ldcg(&F.so1n[(e * ND + d) * S + k]);
             }
         }
         Jaco<ND> J;
-        jaco_update<ND>(J, F.gamma[k], u);
+        jaco_update<ND>(J, SOLT_PF ? cur.un : F.gamma[k], u);
         solt_row<ND>(J, g, t);
 #pragma unroll
         for (int e = 0; e < NEQ; ++e) { F.so0t_next[e * S + k] = t[e]; }
