@@ -437,6 +437,32 @@ __global__ void __launch_bounds__(StagedCfg<TYPE>::TB, StagedCfg<TYPE>::MB) md_s
     double dist;
     bool dist_ok;
     int32_t jmax;
+#if SCG_XCTA_PF
+    {
+        // rows the block SCG_XCTA_PF further on reads before its first staged group lands: the indices, and face 0's geometry
+        int64_t const i2 = int64_t((0 != MODE) ? (G.ibeg & ~31) : G.ibeg) + (int64_t(blockIdx.x) + SCG_XCTA_PF) * TB + threadIdx.x;
+        if (i2 < G.iend)
+        {
+            int64_t const n = G.n, k2 = G.beg + i2;
+            int const nsf0 = ct_fnnd(TYPE, 0);
+#pragma unroll
+            for (int f = 0; f < NFC; ++f) { xcta_pf_row4(G.nbr + f * n, i2); }
+#pragma unroll
+            for (int d = 0; d < ND; ++d) { xcta_pf_row8(G.cecnd + d * n, i2); }
+            xcta_pf_row8(G.cevol, i2);
+            xcta_pf_row8(G.cevol + n, i2);
+#pragma unroll
+            for (int r = 0; r < nsf0 * ND; ++r)
+            {
+                xcta_pf_row8(G.sfcnd + r * n, i2);
+                xcta_pf_row8(G.sfnml + r * n, i2);
+            }
+#pragma unroll
+            for (int d = 0; d < ND; ++d) { xcta_pf_row8(F.solpt + d * F.S, k2); }
+            xcta_pf_row8(F.gamma, k2);
+        }
+    }
+#endif
     if constexpr (0 != MODE)
     {
         // Warps start on multiples of 32 cells so that the copies of the geometry rows are aligned; lanes outside
@@ -545,6 +571,25 @@ __global__ void __launch_bounds__(EqoCfg<TYPE>::TB, EqoCfg<TYPE>::MB) md_dsoln_e
 {
     extern __shared__ double eqo_smem[];
     int32_t const i = G.ibeg + blockIdx.x * EqoCfg<TYPE>::TB + threadIdx.x;
+#if SCG_XCTA_PF
+    {
+        constexpr int ND = ct_ndim(TYPE), NFC = ct_nfc(TYPE);
+        int64_t const i2 = int64_t(i) + int64_t(SCG_XCTA_PF) * EqoCfg<TYPE>::TB;
+        if (i2 < G.iend)
+        {
+            int64_t const n = G.n, k2 = G.beg + i2;
+#pragma unroll
+            for (int f = 0; f < NFC; ++f) { xcta_pf_row4(G.nbr + f * n, i2); }
+#pragma unroll
+            for (int r = 0; r < NFC * ND; ++r) { xcta_pf_row8(G.cecnd + r * n, i2); }
+            xcta_pf_row8(F.cflc, k2);
+#pragma unroll
+            for (int d = 0; d < ND; ++d) { xcta_pf_row8(F.solpt + d * F.S, k2); }
+#pragma unroll
+            for (int e = 0; e < ND + 2; ++e) { xcta_pf_row8(F.so0n + e * F.S, k2); }
+        }
+    }
+#endif
     if (i >= G.iend) { return; }
     cell_dsoln_eqo<TYPE, EqoCfg<TYPE>::TB, EqoCfg<TYPE>::PF>(F, G, i, eqo_smem + threadIdx.x);
 }

@@ -151,6 +151,14 @@ __host__ __device__ constexpr int eqo_jdis_faces(int type)
 #endif
 __host__ __device__ constexpr bool eqo_opaque_k(int type) { return 0 != ((SCG_EQO_OPAQUE_K >> (type - CT_QUAD)) & 1); }
 
+#ifndef SCG_EQO_PF_AFTER_UDF
+#define SCG_EQO_PF_AFTER_UDF 0 // 1: measured equal (hex dsoln 540 vs 543 us): the wait at the top of an equation is not scoreboard sharing
+#endif
+
+#ifndef SCG_EQO_PF3_PIN
+#define SCG_EQO_PF3_PIN 0
+#endif
+
 #ifndef SCG_EQO_GAMMA_PF
 #define SCG_EQO_GAMMA_PF 1 // md_dsoln_eqo without register prefetch: gamma of the cell (read by the fused calc_solt only) is requested into L2
                            // at the top of the cell
@@ -160,6 +168,19 @@ __host__ __device__ constexpr bool eqo_opaque_k(int type) { return 0 != ((SCG_EQ
 #define SCG_XCTA_PF 0 // > 0: every CTA requests into L2 the streamed rows (neighbour indices, geometry) that the CTA SCG_XCTA_PF
                       // blocks ahead will read first -- the blocks that replace the resident ones
 #endif
+
+// Cross-CTA L2 prefetch (SCG_XCTA_PF = D > 0).  A march kernel starts every cell with two dependent round trips: the streamed rows
+// of the cell itself (neighbour indices, geometry, its own state) and then the gathers through the indices.  The first one always
+// misses L2 (every row is read once per launch); the CTA that will take this one's place -- about one wave of resident CTAs, D
+// blocks, further on -- is known, so its rows are requested now: one lane per 128-byte line, no register held.
+__device__ __forceinline__ void xcta_pf_row8(double const * row, int64_t i2) // 8-byte rows: lanes 0 and 16 of a warp cover its 32 cells
+{
+    if (0 == (threadIdx.x & 15)) { asm volatile("prefetch.global.L2 [%0];" ::"l"(row + i2)); }
+}
+__device__ __forceinline__ void xcta_pf_row4(int32_t const * row, int64_t i2) // 4-byte rows: lane 0
+{
+    if (0 == (threadIdx.x & 31)) { asm volatile("prefetch.global.L2 [%0];" ::"l"(row + i2)); }
+}
 
 // ------------------------------------------------------------------------------------------------
 // flux function and Jacobian, detail::EulerJacobian<2>/<3>::update (euler_march.cpp:35-81, 94-157)
@@ -1919,7 +1940,8 @@ struct EqoGather
 
 // PFM: how the neighbour gather of an equation is overlapped with arithmetic.  0: not at all (loaded at the top of its equation);
 // 1: loaded at the top of the PREVIOUS equation into a second register set; 2: loaded in the MIDDLE of the previous equation, right
-// after its products adj(D) * udf, into the same registers (no second set; ~60 % of an equation's arithmetic covers the latency)
+// after its products adj(D) * udf, into the same registers (no second set; ~60 % of an equation's arithmetic covers the latency);
+// 3: like 2 but right after the Taylor differences are formed, i.e. as soon as the registers are free
 template <int TYPE, int TB, int PFM>
 __device__ __forceinline__ void cell_dsoln_eqo(MdField const & F, MdGeo const & G, int32_t i, double * sadj)
 {
@@ -2117,7 +2139,7 @@ __device__ __forceinline__ void cell_dsoln_eqo(MdField const & F, MdGeo const & 
         int64_t k = k_cell; // see SCG_EQO_OPAQUE_K
         if (eqo_opaque_k(TYPE)) { asm volatile("" : "+l"(k)); }
         EqoGather<TYPE> nxt;
-        if (PF)
+        if (PF && !SCG_EQO_PF_AFTER_UDF)
         {
             if (SOLT_PF && e + 1 == NEQ)
             {
@@ -2154,7 +2176,39 @@ __device__ __forceinline__ void cell_dsoln_eqo(MdField const & F, MdGeo const & 
             }
             udf[f] = val;
         }
+        if (PF && SCG_EQO_PF_AFTER_UDF)
+        {
+            // The second register set is loaded AFTER the last use of the first: ptxas shares its few scoreboards among all loads in
+            // flight, so a gather issued before `cur` is consumed makes that consumer wait for the new loads too (profiles/r02h: 11.6 %
+            // of the samples of hex dsoln on that one DADD).  The gather addresses are made to depend on the last Taylor difference,
+            // which keeps the scheduler from hoisting the loads back to the top of the equation.
+#pragma unroll
+            for (int f = 0; f < NFC; ++f) { asm volatile("" : "+r"(rcl[f]) : "d"(udf[NFC - 1])); }
+            nxt.load(F, rcl, k, e + 1 < NEQ ? e + 1 : e);
+        }
         if (PF) { cur = nxt; }
+        if (3 == PFM)
+        {
+            // the Taylor differences are complete (the asm consumes them, so the loads below cannot be scheduled above their last
+            // use of `cur`): the next equation's gather goes into the same registers and travels during the whole solve.  Issued
+            // AFTER the last use because ptxas shares its few scoreboards among all loads in flight: a gather issued before `cur`
+            // is consumed makes that consumer wait for the new loads too (profiles/r02h: 11.6 % of hex dsoln on that one DADD)
+#if SCG_EQO_PF3_PIN
+#pragma unroll
+            for (int f = 0; f < NFC; ++f) { asm volatile("" : "+d"(udf[f])::"memory"); }
+#else
+            asm volatile("" ::: "memory");
+#endif
+            if (e + 1 < NEQ)
+            {
+                if (eqo_rcl_smem(TYPE))
+                {
+#pragma unroll
+                    for (int f = 0; f < NFC; ++f) { rcl[f] = srcl[f * TB]; }
+                }
+                cur.load(F, rcl, k, e + 1);
+            }
+        }
         double grad[NFGE][ND], w[NFGE];
         double sigma_max;
         // every division, square root and reciprocal of the equation runs its inlined fast sequence with
