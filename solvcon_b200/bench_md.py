@@ -409,11 +409,10 @@ class MD3DWorkload:
         return field_health(self.dev)
 
     # fp64-pipe instructions one cell-substep executes in the default kernels, from the committed ncu --set full capture
-    # of the round (profiles/r02g_md3d_ncu_full_summary.txt: executed warp instructions x the share issued to the fp64
-    # pipe = inst_executed * (pipe_fp64 % / 2) / issue_active %, md_solncfl_staged + md_dsoln_eqo, per 6.666e5 cells):
-    # hex 4852 + 3528, tet 2670 + 2017, prism 4069 + 2894 (round 1: 9080 / 5070 / 7380).  The arithmetic is the
-    # reference's, operation for operation (no FMA contraction).
-    FP64_INSTR_PER_CELL = {"hex": 8380.0, "tet": 4687.0, "prism": 6963.0}
+    # of the round (profiles/r02h_md3d_ncu_full_summary.txt; executed DADD + DMUL + DFMA + DSETP of its source page, tools/ncu_hot.py's
+    # input, md_solncfl_staged + md_dsoln_eqo, per 6.666e5 cells): hex 4880 + 3540, tet 2681 + 2024, prism 4085 + 2899
+    # (round 1: 9080 / 5070 / 7380).  The arithmetic is the reference's, operation for operation (no FMA contraction).
+    FP64_INSTR_PER_CELL = {"hex": 8420.0, "tet": 4705.0, "prism": 6984.0}
 
     def roofline_fp64(self, substep_s, clocks):
         """Second roofline of the 3D march: the fp64 pipe.  B200 issues 64 fp64 lanes per SM per clock (16 per
@@ -429,7 +428,7 @@ class MD3DWorkload:
         fmeas = (clocks.get("sm_mhz") or 0.0) * 1e6
         floor_max = lanes / (sm * 64.0 * fmax)
         out = {"bound": "fp64 pipe (64 lanes/clk/SM)", "fp64_instr_per_cell": self.FP64_INSTR_PER_CELL,
-               "source": "profiles/r02g_md3d_ncu_full_summary.txt (ncu --set full: executed instructions x fp64-pipe share)",
+               "source": "profiles/r02h_md3d_ncu_full_summary.txt (ncu --set full: executed instructions x fp64-pipe share)",
                "floor_substep_ms_at_max_clock": floor_max * 1e3,
                "ceiling_updates_per_s_at_max_clock": self.ncell / floor_max,
                "frac_of_ceiling_at_max_clock": floor_max / substep_s,
