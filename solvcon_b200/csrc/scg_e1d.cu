@@ -59,6 +59,9 @@ __device__ __forceinline__ double pow_alpha(double v)
 #ifndef SCG_E1D_MINBLOCKS
 #define SCG_E1D_MINBLOCKS 3
 #endif
+#ifndef SCG_E1D_PIN_X
+#define SCG_E1D_PIN_X 1
+#endif
 
 // Everything a source solution element contributes (Euler1DKernel::derive, Euler1DCore.hpp:210-244, and
 // update_cfl at the source point, Euler1DCore.cpp:70-94).  FAST: the ten Jacobian / flux quotients share three
@@ -170,13 +173,22 @@ __global__ void __launch_bounds__(256, SCG_E1D_MINBLOCKS) e1d_half_kernel(EPlane
     double const qdt = hdt / 2.0;
 
     // ---- Euler1DKernel::set_value, Euler1DCore.hpp:194-209
+#if SCG_E1D_PIN_X
+    // The three coordinates are first needed ~350 instructions into the element; under the 80-register cap ptxas sinks their loads
+    // down to that point and the element pays a second exposed DRAM round trip there (ncu: 15 % of the samples on the first
+    // consumer).  Their lines are requested into L1 up front (an instruction ptxas keeps in place; no register held), so the sunk
+    // loads hit.
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(&ps.x[s]));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(&pt.x[s + b]));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(&pt.x[s + b + 1]));
+#endif
     double const ga = ps.ga[s];
     double const x = ps.x[s];
     double const xneg = pt.x[s + b];
     double const xpos = pt.x[s + b + 1];
-    double const xctr = (xpos + xneg) * 0.5;
     double const u0 = ps.u[0][s], u1 = ps.u[1][s], u2 = ps.u[2][s];
     double const ux0 = ps.g[0][s], ux1 = ps.g[1][s], ux2 = ps.g[2][s];
+    double const xctr = (xpos + xneg) * 0.5;
 
     // ---- derive + update_cfl of the source (expression order kept)
     constexpr bool WITH_CFL = 0 != (FLAGS & F_CFL);
