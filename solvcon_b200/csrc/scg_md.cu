@@ -549,7 +549,8 @@ __global__ void __launch_bounds__(StagedCfg<TYPE>::TB, StagedCfg<TYPE>::MB) md_s
 #define SCG_EQO_PF_TET 0
 #endif
 #ifndef SCG_EQO_PF_2D
-#define SCG_EQO_PF_2D 0
+#define SCG_EQO_PF_2D 1 // fits the 2D register budgets since the neighbour indices moved to shared memory (quad 126, tri 96 registers):
+                        // quad dsoln -7 %, tri -3 % (profiles/r02h_2d_register_prefetch_ab.txt)
 #endif
 template <int TYPE>
 struct EqoCfg
